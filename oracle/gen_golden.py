@@ -1,0 +1,62 @@
+"""Generate tests/golden/*.npz from the REFERENCE itself (oracle/_ref/libggml_ref.so).
+
+Run in the build container (where /root/reference exists):  python -m oracle.gen_golden
+The reference has no golden vectors of its own for this path, so these
+fixtures are outputs of the reference's row kernels on seeded inputs, produced through the
+hook the reference exports for tests (ggml_internal_get_quantize_fn, include/ggml.h:841-862).
+They pin the C restatement (tests/test_oracle.py) and the CUDA path (tests/test_gpu_*.py) on
+machines where only the committed files exist.
+"""
+import os
+
+import numpy as np
+
+from oracle.pyoracle import GGML_TYPE_Q4_0, GGML_TYPE_Q4_1, RefGgml, build_oracle
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def activation_rows(rng, n, k):
+    """Seeded activations with the edge cases the q8_0 quantizer has: all-zero block, single
+    non-zero, exact .5 ties after scaling (amax = 127 -> id = 1), denormal and huge scales,
+    negative amax, constant blocks."""
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    x[0] = 0.0
+    x[1] = 0.0
+    x[1, 5] = 1.0
+    x[2, :32] = np.arange(32, dtype=np.float32) - 15.5
+    x[2, 0] = 127.0
+    x[3, :32] = np.linspace(-63.5, 63.5, 32, dtype=np.float32)
+    x[3, 31] = -127.0
+    x[4] *= np.float32(1e-30)
+    x[5] *= np.float32(1e30)
+    x[6] = np.round(x[6] * 4) / 4
+    x[7, 32:64] = 3.0
+    return x
+
+
+def main():
+    build_oracle()
+    ref = RefGgml()
+    rng = np.random.default_rng(20230423)
+    os.makedirs(OUT, exist_ok=True)
+
+    # K = 64 is the smallest legal row (vec_dot asserts an even block count, lib/ggml.c:2372)
+    for k, m, n in ((64, 8, 8), (256, 40, 9), (4096, 6, 8)):
+        x = activation_rows(rng, n, k)
+        w = (rng.standard_normal((m, k)) * 0.02).astype(np.float32)
+        w[0] = 0.0                      # all-zero weight row: d = 0 blocks
+        w[1, :32] = 0.02                # constant block: q4_1 d = 0, m = value
+        out = {"x": x, "w": w, "q8": ref.quantize_q8_0(x)}
+        for name, t in (("q4_0", GGML_TYPE_Q4_0), ("q4_1", GGML_TYPE_Q4_1)):
+            wq = ref.quantize_q4_reference(w, t)
+            out[f"{name}_w"] = wq
+            out[f"{name}_deq"] = ref.dequantize_q4(wq, t, k)
+            out[f"{name}_mul_mat"] = ref.mul_mat_q(wq, x, t)        # [N, M]
+        path = os.path.join(OUT, f"rowfns_k{k}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
