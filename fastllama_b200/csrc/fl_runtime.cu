@@ -1,0 +1,485 @@
+// fl_runtime.cu -- library state, memory, lookup tables and the extern "C" entry points of
+// include/fl_cuda.h.  No CPU compute path exists here: every entry point either runs the sm_100a
+// kernels or fails loudly.
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "fl_common.cuh"
+#include "fl_kernels.h"
+
+// ---------------------------------------------------------------------------------------------
+// state
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Scratch {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+struct State {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    uint16_t *tab_silu = nullptr;   // fp16 -> fp16 silu table (device)
+    uint16_t *tab_exp = nullptr;    // fp16 -> fp16 exp table (device)
+    float2 *rope_cs = nullptr;      // [rope_pos][rope_dims/2]
+    int rope_dims = 0, rope_pos = 0;
+    Scratch scratch[4];
+    uint64_t launches = 0;
+};
+State g;
+thread_local char g_err[1024] = "";
+}  // namespace
+
+void fl_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (getenv("FASTLLAMA_B200_VERBOSE")) fprintf(stderr, "[fl_cuda] error: %s\n", g_err);
+}
+void fl_count_launch() { g.launches++; }
+
+#define FL_NEED_INIT()                                                                               \
+    do {                                                                                             \
+        if (!g.ready) {                                                                              \
+            fl_set_error("libfl_cuda is not initialised (fl_init failed or was never called; there " \
+                         "is no CPU fallback)");                                                     \
+            return -3;                                                                               \
+        }                                                                                            \
+    } while (0)
+
+static int scratch_get(int i, size_t bytes, void **out) {
+    Scratch &s = g.scratch[i];
+    if (s.cap < bytes) {
+        if (s.p) FL_CUDA_OK(cudaFree(s.p));
+        s.p = nullptr;
+        s.cap = 0;
+        size_t cap = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        FL_CUDA_OK(cudaMalloc(&s.p, cap));
+        s.cap = cap;
+    }
+    *out = s.p;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp16 lookup tables, built exactly like the reference builds them on first ggml_init
+// (reference lib/ggml.c:3676-3688): f = fp16->fp32(i); silu = f/(1+expf(-f)); exp = expf(f);
+// both rounded to fp16 (round-to-nearest-even).  Host libm, so table contents equal the
+// reference's on the same machine.
+// ---------------------------------------------------------------------------------------------
+static int build_tables() {
+    std::vector<uint16_t> silu(1 << 16), ex(1 << 16);
+    for (int i = 0; i < (1 << 16); i++) {
+        const float f = __half2float(__ushort_as_half((unsigned short)i));
+        const float sv = f / (1.0f + expf(-f));
+        const float ev = expf(f);
+        silu[i] = __half_as_ushort(__float2half_rn(sv));
+        ex[i] = __half_as_ushort(__float2half_rn(ev));
+    }
+    FL_CUDA_OK(cudaMalloc((void **)&g.tab_silu, sizeof(uint16_t) << 16));
+    FL_CUDA_OK(cudaMalloc((void **)&g.tab_exp, sizeof(uint16_t) << 16));
+    FL_CUDA_OK(cudaMemcpy(g.tab_silu, silu.data(), sizeof(uint16_t) << 16, cudaMemcpyHostToDevice));
+    FL_CUDA_OK(cudaMemcpy(g.tab_exp, ex.data(), sizeof(uint16_t) << 16, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// rope cos/sin for absolute positions, computed with the reference's recurrence
+// (reference lib/ggml.c:8655-8668): theta_0 = (float)pos, theta_{i+1} = theta_i * powf(10000, -2/n_dims)
+static int ensure_rope(int n_dims, int n_pos) {
+    if (g.rope_cs && g.rope_dims == n_dims && g.rope_pos >= n_pos) return 0;
+    int cap = n_pos < 512 ? 512 : n_pos;
+    if (g.rope_dims == n_dims && cap < 2 * g.rope_pos) cap = 2 * g.rope_pos;
+    const int half = n_dims / 2;
+    std::vector<float2> cs((size_t)cap * half);
+    const float theta_scale = powf(10000.0, -2.0f / n_dims);
+    for (int p = 0; p < cap; p++) {
+        float theta = (float)p;
+        for (int i = 0; i < half; i++) {
+            cs[(size_t)p * half + i] = make_float2(cosf(theta), sinf(theta));
+            theta *= theta_scale;
+        }
+    }
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    if (g.rope_cs) FL_CUDA_OK(cudaFree(g.rope_cs));
+    g.rope_cs = nullptr;
+    FL_CUDA_OK(cudaMalloc((void **)&g.rope_cs, cs.size() * sizeof(float2)));
+    FL_CUDA_OK(cudaMemcpy(g.rope_cs, cs.data(), cs.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    g.rope_dims = n_dims;
+    g.rope_pos = cap;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+extern "C" int fl_init(int device) {
+    if (g.ready) return 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        fl_set_error("fl_init: no CUDA device visible (%s); this backend has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return -1;
+    }
+    if (device < 0) {
+        const char *env = getenv("FASTLLAMA_DEVICE");
+        if (!env) env = getenv("LOCAL_RANK");
+        device = env ? atoi(env) : 0;
+    }
+    FL_REQUIRE(device < count, "fl_init: device %d requested but only %d visible", device, count);
+    FL_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FL_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    FL_REQUIRE(prop.major == 10, "fl_init: built for sm_100a only, device %d is sm_%d%d (%s)", device, prop.major,
+               prop.minor, prop.name);
+    FL_CUDA_OK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    g.device = device;
+    if (flk_query_device() != 0) return -1;
+    if (build_tables() != 0) return -1;
+    g.ready = true;
+    return 0;
+}
+
+extern "C" void fl_shutdown(void) {
+    if (!g.ready) return;
+    cudaStreamSynchronize(g.stream);
+    for (auto &s : g.scratch) {
+        if (s.p) cudaFree(s.p);
+        s = Scratch();
+    }
+    if (g.tab_silu) cudaFree(g.tab_silu);
+    if (g.tab_exp) cudaFree(g.tab_exp);
+    if (g.rope_cs) cudaFree(g.rope_cs);
+    cudaStreamDestroy(g.stream);
+    g = State();
+}
+
+extern "C" int fl_is_initialized(void) { return g.ready ? 1 : 0; }
+extern "C" const char *fl_last_error(void) { return g_err; }
+extern "C" void *fl_stream(void) { return (void *)g.stream; }
+extern "C" uint64_t fl_launch_count(void) { return g.launches; }
+
+extern "C" int fl_device_props(char *name, int name_len, int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor) {
+    FL_NEED_INIT();
+    cudaDeviceProp prop;
+    FL_CUDA_OK(cudaGetDeviceProperties(&prop, g.device));
+    if (name && name_len > 0) {
+        strncpy(name, prop.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (hbm_bytes) *hbm_bytes = prop.totalGlobalMem;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// memory
+// ---------------------------------------------------------------------------------------------
+extern "C" void *fl_dev_malloc(size_t bytes) {
+    if (!g.ready) {
+        fl_set_error("fl_dev_malloc: not initialised");
+        return nullptr;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        fl_set_error("fl_dev_malloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" int fl_dev_free(void *p) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    FL_CUDA_OK(cudaFree(p));
+    return 0;
+}
+extern "C" int fl_dev_memset(void *p, int value, size_t bytes) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaMemsetAsync(p, value, bytes, g.stream));
+    return 0;
+}
+extern "C" int fl_h2d(void *dst, const void *src, size_t bytes) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g.stream));
+    return 0;
+}
+extern "C" int fl_d2h(void *dst, const void *src, size_t bytes) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g.stream));
+    return 0;
+}
+extern "C" int fl_d2d(void *dst, const void *src, size_t bytes) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g.stream));
+    return 0;
+}
+extern "C" int fl_sync(void) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+extern "C" void *fl_host_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        fl_set_error("fl_host_alloc_pinned(%zu): %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" int fl_host_free_pinned(void *p) {
+    FL_CUDA_OK(cudaFreeHost(p));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-resident entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" int fl_dev_quantize_q8_0(const float *x, size_t x_row_stride_bytes, void *y, int k, int nrows) {
+    FL_NEED_INIT();
+    return flk_quantize_q8_0(g.stream, x, x_row_stride_bytes, y, k, nrows);
+}
+extern "C" int fl_dev_mul_mat_q(int type, const void *W, size_t wrs, int M, int K, const void *Yq8, int N, float *dst,
+                                size_t drs, int impl) {
+    FL_NEED_INIT();
+    return flk_mul_mat_q(g.stream, type, W, wrs, M, K, Yq8, N, dst, drs, impl);
+}
+extern "C" int fl_dev_dequantize_rows(int type, const void *W, size_t wrs, int K, const int32_t *ids, int n_ids,
+                                      float *dst, size_t drs) {
+    FL_NEED_INIT();
+    return flk_dequantize_rows(g.stream, type, W, wrs, K, ids, n_ids, dst, drs);
+}
+extern "C" int fl_dev_quantize_q4(int type, const float *x, void *y, int k, int nrows) {
+    FL_NEED_INIT();
+    return flk_quantize_q4(g.stream, type, x, y, k, nrows);
+}
+
+extern "C" int fl_dev_rms_norm(const fl_view *src, const fl_view *dst) {
+    FL_NEED_INIT();
+    return flk_rms_norm(g.stream, *src, *dst, 1e-6f);
+}
+extern "C" int fl_dev_add(const fl_view *a, const fl_view *b, const fl_view *dst) {
+    FL_NEED_INIT();
+    return flk_binary(g.stream, FLK_ADD, *a, *b, *dst);
+}
+extern "C" int fl_dev_mul(const fl_view *a, const fl_view *b, const fl_view *dst) {
+    FL_NEED_INIT();
+    return flk_binary(g.stream, FLK_MUL, *a, *b, *dst);
+}
+extern "C" int fl_dev_repeat(const fl_view *src, const fl_view *dst) {
+    FL_NEED_INIT();
+    return flk_repeat(g.stream, *src, *dst);
+}
+extern "C" int fl_dev_scale(const fl_view *t, float v) {
+    FL_NEED_INIT();
+    return flk_scale(g.stream, *t, v);
+}
+extern "C" int fl_dev_silu(const fl_view *src, const fl_view *dst) {
+    FL_NEED_INIT();
+    return flk_silu(g.stream, *src, *dst, g.tab_silu);
+}
+extern "C" int fl_dev_diag_mask_inf(const fl_view *t, int n_past) {
+    FL_NEED_INIT();
+    return flk_diag_mask_inf(g.stream, *t, n_past);
+}
+extern "C" int fl_dev_soft_max(const fl_view *t) {
+    FL_NEED_INIT();
+    return flk_soft_max(g.stream, *t, g.tab_exp);
+}
+extern "C" int fl_dev_rope(const fl_view *t, int n_past, int n_dims, int mode) {
+    FL_NEED_INIT();
+    const int need = (int)(((mode & 1) ? 0 : n_past) + t->ne[2]);
+    if (ensure_rope(n_dims, need) != 0) return -1;
+    return flk_rope(g.stream, *t, n_past, n_dims, mode, g.rope_cs, g.rope_pos);
+}
+extern "C" int fl_dev_cpy_f32(const fl_view *src, const fl_view *dst) {
+    FL_NEED_INIT();
+    return flk_cpy_f32(g.stream, *src, *dst);
+}
+extern "C" int fl_dev_mul_mat_f32(const fl_view *src0, const fl_view *src1, const fl_view *dst) {
+    FL_NEED_INIT();
+    return flk_mul_mat_f32(g.stream, *src0, *src1, *dst);
+}
+
+extern "C" void *fl_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) {
+        fl_set_error("fl_event_create failed");
+        return nullptr;
+    }
+    return (void *)e;
+}
+extern "C" int fl_event_destroy(void *ev) {
+    FL_CUDA_OK(cudaEventDestroy((cudaEvent_t)ev));
+    return 0;
+}
+extern "C" int fl_event_record(void *ev) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaEventRecord((cudaEvent_t)ev, g.stream));
+    return 0;
+}
+extern "C" int fl_event_sync(void *ev) {
+    FL_CUDA_OK(cudaEventSynchronize((cudaEvent_t)ev));
+    return 0;
+}
+extern "C" int fl_event_elapsed_ms(void *a, void *b, float *ms) {
+    FL_CUDA_OK(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+    return 0;
+}
+
+__global__ void k_flush_l2(uint4 *p, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4((unsigned)i, 1u, 2u, 3u);
+}
+
+extern "C" int fl_dev_time_mul_mat_q(int type, const void *W, size_t wrs, int M, int K, const void *Yq8, int N,
+                                     float *dst, size_t drs, int impl, int iters, size_t flush_l2_bytes,
+                                     float *ms_per_launch) {
+    FL_NEED_INIT();
+    FL_REQUIRE(iters > 0 && ms_per_launch, "fl_dev_time_mul_mat_q: bad arguments");
+    void *flush = nullptr;
+    if (flush_l2_bytes) {
+        if (scratch_get(3, flush_l2_bytes, &flush) != 0) return -1;
+    }
+    cudaEvent_t e0, e1;
+    FL_CUDA_OK(cudaEventCreate(&e0));
+    FL_CUDA_OK(cudaEventCreate(&e1));
+    double total = 0.0;
+    int rc = 0;
+    for (int i = 0; i < iters && rc == 0; i++) {
+        if (flush) k_flush_l2<<<flk_sm_count() * 8, 256, 0, g.stream>>>((uint4 *)flush, flush_l2_bytes / 16);
+        cudaEventRecord(e0, g.stream);
+        rc = flk_mul_mat_q(g.stream, type, W, wrs, M, K, Yq8, N, dst, drs, impl);
+        cudaEventRecord(e1, g.stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc != 0) return rc;
+    FL_CUDA_OK(cudaGetLastError());
+    *ms_per_launch = (float)(total / iters);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer entry points: H2D -> kernel -> D2H, result valid on return
+// ---------------------------------------------------------------------------------------------
+extern "C" int fl_quantize_rows_q8_0(const float *x, void *y, int k, int nrows) {
+    FL_NEED_INIT();
+    FL_REQUIRE(x && y && k > 0 && k % FL_QK == 0 && nrows >= 0, "fl_quantize_rows_q8_0: bad arguments (k=%d)", k);
+    if (nrows == 0) return 0;
+    const size_t xin = (size_t)k * nrows * sizeof(float), yout = (size_t)(k / FL_QK) * nrows * sizeof(fl_block_q8_0);
+    void *dx, *dy;
+    if (scratch_get(0, xin, &dx) || scratch_get(1, yout, &dy)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(dx, x, xin, cudaMemcpyHostToDevice, g.stream));
+    if (flk_quantize_q8_0(g.stream, (const float *)dx, (size_t)k * sizeof(float), dy, k, nrows)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(y, dy, yout, cudaMemcpyDeviceToHost, g.stream));
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+extern "C" int fl_quantize_row_q8_0(const float *x, void *y, int k) { return fl_quantize_rows_q8_0(x, y, k, 1); }
+
+extern "C" int fl_quantize_rows_q4(int type, const float *x, void *y, int k, int nrows) {
+    FL_NEED_INIT();
+    FL_REQUIRE(x && y && k > 0 && k % FL_QK == 0 && nrows >= 0, "fl_quantize_rows_q4: bad arguments (k=%d)", k);
+    FL_REQUIRE(type == FL_TYPE_Q4_0 || type == FL_TYPE_Q4_1, "fl_quantize_rows_q4: unsupported type %d", type);
+    if (nrows == 0) return 0;
+    const size_t xin = (size_t)k * nrows * sizeof(float), yout = (size_t)(k / FL_QK) * nrows * fl_block_bytes(type);
+    void *dx, *dy;
+    if (scratch_get(0, xin, &dx) || scratch_get(1, yout, &dy)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(dx, x, xin, cudaMemcpyHostToDevice, g.stream));
+    if (flk_quantize_q4(g.stream, type, (const float *)dx, dy, k, nrows)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(y, dy, yout, cudaMemcpyDeviceToHost, g.stream));
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+extern "C" int fl_dequantize_rows_q4(int type, const void *x, float *y, int k, int nrows) {
+    FL_NEED_INIT();
+    FL_REQUIRE(x && y && k > 0 && k % FL_QK == 0 && nrows >= 0, "fl_dequantize_rows_q4: bad arguments (k=%d)", k);
+    FL_REQUIRE(type == FL_TYPE_Q4_0 || type == FL_TYPE_Q4_1, "fl_dequantize_rows_q4: unsupported type %d", type);
+    if (nrows == 0) return 0;
+    const size_t rb = (size_t)(k / FL_QK) * fl_block_bytes(type);
+    const size_t xin = rb * nrows, yout = (size_t)k * nrows * sizeof(float);
+    void *dx, *dy;
+    if (scratch_get(0, xin, &dx) || scratch_get(1, yout, &dy)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(dx, x, xin, cudaMemcpyHostToDevice, g.stream));
+    if (flk_dequantize_rows(g.stream, type, dx, rb, k, nullptr, nrows, (float *)dy, (size_t)k)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(y, dy, yout, cudaMemcpyDeviceToHost, g.stream));
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+extern "C" int fl_get_rows_q(int type, int K, int n_ids, const void *W, int n_rows_total, const int32_t *ids, float *dst) {
+    FL_NEED_INIT();
+    FL_REQUIRE(W && ids && dst && K > 0 && K % FL_QK == 0, "fl_get_rows_q: bad arguments");
+    FL_REQUIRE(type == FL_TYPE_Q4_0 || type == FL_TYPE_Q4_1, "fl_get_rows_q: unsupported type %d", type);
+    for (int i = 0; i < n_ids; i++)
+        FL_REQUIRE(ids[i] >= 0 && ids[i] < n_rows_total, "fl_get_rows_q: id %d out of range [0,%d)", ids[i], n_rows_total);
+    if (n_ids <= 0) return 0;
+    const size_t rb = (size_t)(K / FL_QK) * fl_block_bytes(type);
+    void *dw, *di, *dy;
+    if (scratch_get(0, rb * n_rows_total, &dw) || scratch_get(1, (size_t)K * n_ids * 4, &dy) ||
+        scratch_get(2, (size_t)n_ids * 4, &di))
+        return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(dw, W, rb * n_rows_total, cudaMemcpyHostToDevice, g.stream));
+    FL_CUDA_OK(cudaMemcpyAsync(di, ids, (size_t)n_ids * 4, cudaMemcpyHostToDevice, g.stream));
+    if (flk_dequantize_rows(g.stream, type, dw, rb, K, (const int32_t *)di, n_ids, (float *)dy, (size_t)K)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(dst, dy, (size_t)K * n_ids * 4, cudaMemcpyDeviceToHost, g.stream));
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+extern "C" int fl_vec_dot_q4_q8(int type, int n, float *s, const void *x, const void *y) {
+    FL_NEED_INIT();
+    FL_REQUIRE(s && x && y && n > 0 && n % FL_QK == 0, "fl_vec_dot_q4_q8: bad arguments (n=%d)", n);
+    FL_REQUIRE(type == FL_TYPE_Q4_0 || type == FL_TYPE_Q4_1, "fl_vec_dot_q4_q8: unsupported type %d", type);
+    const size_t rb = (size_t)(n / FL_QK) * fl_block_bytes(type), qb = (size_t)(n / FL_QK) * sizeof(fl_block_q8_0);
+    void *dw, *dq, *dd;
+    if (scratch_get(0, rb, &dw) || scratch_get(1, qb, &dq) || scratch_get(2, 16, &dd)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(dw, x, rb, cudaMemcpyHostToDevice, g.stream));
+    FL_CUDA_OK(cudaMemcpyAsync(dq, y, qb, cudaMemcpyHostToDevice, g.stream));
+    if (flk_mul_mat_q(g.stream, type, dw, rb, 1, n, dq, 1, (float *)dd, 1, 1)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(s, dd, sizeof(float), cudaMemcpyDeviceToHost, g.stream));
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+extern "C" int fl_mul_mat_q_f32(int type, int M, int K, int N, const void *W, const float *X, float *dst) {
+    FL_NEED_INIT();
+    FL_REQUIRE(W && X && dst && M >= 0 && N >= 0, "fl_mul_mat_q_f32: bad arguments");
+    FL_REQUIRE(K > 0 && K % FL_QK == 0, "fl_mul_mat_q_f32: K=%d is not a multiple of 32", K);
+    FL_REQUIRE(type == FL_TYPE_Q4_0 || type == FL_TYPE_Q4_1, "fl_mul_mat_q_f32: unsupported weight type %d", type);
+    if (M == 0 || N == 0) return 0;
+    const size_t rb = (size_t)(K / FL_QK) * fl_block_bytes(type);
+    const size_t wb = rb * M, xb = (size_t)K * N * sizeof(float), qb = (size_t)(K / FL_QK) * N * sizeof(fl_block_q8_0),
+                 ob = (size_t)M * N * sizeof(float);
+    void *dw, *dxq, *dout;
+    // scratch 1 holds X (f32) followed by its q8_0 form
+    const size_t xb_al = (xb + 255) & ~(size_t)255;
+    if (scratch_get(0, wb, &dw) || scratch_get(1, xb_al + qb, &dxq) || scratch_get(2, ob, &dout)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(dw, W, wb, cudaMemcpyHostToDevice, g.stream));
+    FL_CUDA_OK(cudaMemcpyAsync(dxq, X, xb, cudaMemcpyHostToDevice, g.stream));
+    void *dq = (char *)dxq + xb_al;
+    // INIT phase of the reference op: every src1 row -> q8_0 (lib/ggml.c:8105-8119)
+    if (flk_quantize_q8_0(g.stream, (const float *)dxq, (size_t)K * sizeof(float), dq, K, N)) return -1;
+    // COMPUTE phase (lib/ggml.c:8125-8163)
+    const char *impl_env = getenv("FASTLLAMA_B200_MATVEC_IMPL");
+    const int impl = impl_env ? atoi(impl_env) : 0;
+    if (flk_mul_mat_q(g.stream, type, dw, rb, M, K, dq, N, (float *)dout, (size_t)M, impl)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(dst, dout, ob, cudaMemcpyDeviceToHost, g.stream));
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return 0;
+}

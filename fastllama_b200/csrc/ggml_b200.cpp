@@ -1,0 +1,959 @@
+// ggml_b200.cpp -- ggml-compatible host library (boundary B1, include/fl_ggml.h) whose
+// ggml_graph_compute runs on a B200 through the extern-"C" CUDA layer (include/fl_cuda.h).
+//
+// Plain host C++ (compiled by g++, no CUDA headers).  Three parts:
+//   1. tensor arena + graph builders: same observable behaviour and space accounting as the
+//      reference (reference lib/ggml.c:3666-4075, :4266-5420, :10551-10640), written from scratch;
+//   2. device residency: every host arena the graph touches (weights ctx, KV-cache ctx, compute
+//      ctx, or a bare mmap'ed range) gets an equally sized device mirror, so a tensor's device
+//      address is mirror_base + (tensor->data - arena_base) -- views, KV-slot offsets and reshapes,
+//      which ggml encodes purely as host pointer arithmetic, need no translation tables;
+//   3. the executor: walks cgraph->nodes in order and issues one or a few kernels per node
+//      (replaces ggml_graph_compute + pthread pool + ggml_compute_forward switch,
+//      reference lib/ggml.c:10811-11253, :10117-10285).
+#include "fl_ggml.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <unordered_map>
+#include <vector>
+
+#include "fl_cuda.h"
+
+// ================================================================================================
+// small utilities
+// ================================================================================================
+[[noreturn]] static void b200_abort(const char *file, int line, const char *fmt, ...) {
+    fprintf(stderr, "GGML_B200_ASSERT: %s:%d: ", file, line);
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "\n");
+    fflush(stderr);
+    abort();
+}
+#define B200_ASSERT(cond)                                        \
+    do {                                                         \
+        if (!(cond)) b200_abort(__FILE__, __LINE__, "%s", #cond); \
+    } while (0)
+#define B200_FAIL(...) b200_abort(__FILE__, __LINE__, __VA_ARGS__)
+// every call into the CUDA layer is checked; a failure is fatal (like GGML_ASSERT -> abort())
+#define FLC(expr)                                                                                 \
+    do {                                                                                          \
+        if ((expr) != 0) b200_abort(__FILE__, __LINE__, "%s failed: %s", #expr, fl_last_error()); \
+    } while (0)
+
+static const int k_blck[GGML_TYPE_COUNT] = {1, 1, 32, 32, 16, 16, 32, 1, 1, 1};
+static const size_t k_tsize[GGML_TYPE_COUNT] = {4, 2, 20, 24, 10, 12, 40, 1, 2, 4};
+static const char *k_tname[GGML_TYPE_COUNT] = {"f32", "f16", "q4_0", "q4_1", "q4_2", "q4_3", "q8_0", "i8", "i16", "i32"};
+static const char *k_opname[GGML_OP_COUNT] = {
+    "NONE", "DUP", "ADD", "SUB", "MUL", "DIV", "SQR", "SQRT", "SUM", "MEAN", "REPEAT", "ABS", "SGN", "NEG", "STEP",
+    "RELU", "GELU", "SILU", "NORM", "RMS_NORM", "MUL_MAT", "SCALE", "CPY", "CONT", "RESHAPE", "VIEW", "PERMUTE",
+    "TRANSPOSE", "GET_ROWS", "DIAG_MASK_INF", "SOFT_MAX", "ROPE", "CONV_1D_1S", "CONV_1D_2S", "FLASH_ATTN", "FLASH_FF",
+    "MAP_UNARY", "MAP_BINARY"};
+static constexpr size_t MEM_ALIGN = 16;
+
+extern "C" {
+
+void ggml_time_init(void) {}
+int64_t ggml_time_us(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (int64_t)ts.tv_sec * 1000000 + (int64_t)ts.tv_nsec / 1000;
+}
+int64_t ggml_time_ms(void) { return ggml_time_us() / 1000; }
+
+// IEEE binary16 <-> binary32, round-to-nearest-even (what _cvtss_sh / _cvtsh_ss do)
+float ggml_fp16_to_fp32(ggml_fp16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {
+            int e = -1;
+            do { e++; man <<= 1; } while ((man & 0x400u) == 0);
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3FFu) << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+    else bits = sign | ((exp + 112u) << 23) | (man << 13);
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+ggml_fp16_t ggml_fp32_to_fp16(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    const uint32_t ax = x & 0x7FFFFFFFu;
+    if (ax >= 0x7F800000u) return (ggml_fp16_t)(sign | 0x7C00u | (ax > 0x7F800000u ? 0x200u | ((ax >> 13) & 0x3FFu) : 0u));
+    if (ax >= 0x477FF000u) return (ggml_fp16_t)(sign | 0x7C00u);               // rounds to inf
+    if (ax < 0x33000001u) return (ggml_fp16_t)sign;                             // rounds to zero
+    int e = (int)(ax >> 23) - 127;
+    uint32_t man = (ax & 0x7FFFFFu) | 0x800000u;
+    uint32_t shift, hexp;
+    if (e < -14) { shift = (uint32_t)(13 + (-14 - e)); hexp = 0; }
+    else         { shift = 13; hexp = (uint32_t)(e + 15); }
+    uint32_t hman = man >> shift;
+    const uint32_t rem = man & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (hman & 1u))) hman++;
+    uint32_t out = (e < -14) ? hman : (((hexp << 10) | (hman & 0x3FFu)) + ((hman & 0x800u) ? 0x400u : 0u));
+    if (e >= -14 && (hman & 0x800u)) out = ((hexp + 1) << 10);                  // mantissa overflow
+    return (ggml_fp16_t)(sign | out);
+}
+
+int ggml_cpu_has_blas(void) { return 0; }
+int ggml_cpu_has_cublas(void) { return 0; }
+
+int64_t ggml_nelements(const struct ggml_tensor *t) { return t->ne[0] * t->ne[1] * t->ne[2] * t->ne[3]; }
+size_t ggml_nbytes(const struct ggml_tensor *t) { return (size_t)(ggml_nelements(t) * (int64_t)k_tsize[t->type]) / k_blck[t->type]; }
+int ggml_blck_size(enum ggml_type type) { return k_blck[type]; }
+size_t ggml_type_size(enum ggml_type type) { return k_tsize[type]; }
+float ggml_type_sizef(enum ggml_type type) { return (float)k_tsize[type] / k_blck[type]; }
+const char *ggml_type_name(enum ggml_type type) { return k_tname[type]; }
+size_t ggml_element_size(const struct ggml_tensor *t) { return k_tsize[t->type]; }
+bool ggml_is_quantized(enum ggml_type type) { return type >= GGML_TYPE_Q4_0 && type <= GGML_TYPE_Q8_0; }
+
+}  // extern "C"
+
+static inline int64_t nrows(const ggml_tensor *t) { return t->ne[1] * t->ne[2] * t->ne[3]; }
+static inline bool same_shape(const ggml_tensor *a, const ggml_tensor *b) {
+    return a->ne[0] == b->ne[0] && a->ne[1] == b->ne[1] && a->ne[2] == b->ne[2] && a->ne[3] == b->ne[3];
+}
+static inline bool is_contiguous(const ggml_tensor *t) {
+    return t->nb[0] == k_tsize[t->type] && t->nb[1] == (t->nb[0] * t->ne[0]) / k_blck[t->type] &&
+           t->nb[2] == t->nb[1] * t->ne[1] && t->nb[3] == t->nb[2] * t->ne[2];
+}
+
+// ================================================================================================
+// 1. contexts: a pool of 64 bump arenas over caller-provided (or owned) buffers
+// ================================================================================================
+struct ggml_context {
+    size_t mem_size;
+    char *mem_buffer;
+    bool owned, no_alloc;
+    int n_objects;
+    ggml_object *first, *last;
+    ggml_scratch scratch, scratch_save;
+};
+namespace {
+struct Slot { bool used; ggml_context ctx; };
+Slot g_slots[GGML_MAX_CONTEXTS];
+}  // namespace
+static void mirrors_on_ctx_init(ggml_context *ctx);
+static void mirrors_on_ctx_free(ggml_context *ctx);
+static void mirrors_on_scratch(void *data, size_t size);
+
+extern "C" struct ggml_context *ggml_init(struct ggml_init_params params) {
+    for (auto &slot : g_slots) {
+        if (slot.used) continue;
+        slot.used = true;
+        ggml_context *c = &slot.ctx;
+        memset(c, 0, sizeof(*c));
+        c->mem_size = (params.mem_size + MEM_ALIGN - 1) & ~(MEM_ALIGN - 1);
+        c->owned = params.mem_buffer == nullptr;
+        c->mem_buffer = c->owned ? (char *)aligned_alloc(MEM_ALIGN, c->mem_size ? c->mem_size : MEM_ALIGN) : (char *)params.mem_buffer;
+        c->no_alloc = params.no_alloc;
+        B200_ASSERT(c->mem_buffer != nullptr);
+        B200_ASSERT(((uintptr_t)c->mem_buffer % MEM_ALIGN) == 0);
+        mirrors_on_ctx_init(c);
+        return c;
+    }
+    return nullptr;
+}
+
+extern "C" void ggml_free(struct ggml_context *ctx) {
+    for (auto &slot : g_slots) {
+        if (&slot.ctx != ctx) continue;
+        mirrors_on_ctx_free(ctx);
+        if (ctx->owned) free(ctx->mem_buffer);
+        slot.used = false;
+        return;
+    }
+}
+
+extern "C" size_t ggml_used_mem(const struct ggml_context *ctx) { return ctx->last ? ctx->last->offs + ctx->last->size : 0; }
+
+extern "C" size_t ggml_set_scratch(struct ggml_context *ctx, struct ggml_scratch scratch) {
+    const size_t prev = ctx->scratch.data ? ctx->scratch.offs : 0;
+    ctx->scratch = scratch;
+    if (scratch.data) mirrors_on_scratch(scratch.data, scratch.size);
+    return prev;
+}
+
+// Space accounting follows the reference bump allocator exactly (lib/ggml.c:3809-3928): an object
+// header, then the tensor struct, then (unless the data lives elsewhere) the payload rounded up to
+// 16 bytes; with a scratch buffer active the payload goes to the scratch arena instead.
+static ggml_tensor *new_tensor_impl(ggml_context *ctx, ggml_type type, int n_dims, const int64_t *ne, void *data) {
+    const size_t cur_end = ctx->last ? ctx->last->offs + ctx->last->size : 0;
+    size_t payload = 0;
+    if (data == nullptr && !ctx->no_alloc) {
+        payload = k_tsize[type] * (size_t)(ne[0] / k_blck[type]);
+        for (int i = 1; i < n_dims; i++) payload *= (size_t)ne[i];
+        payload = (payload + MEM_ALIGN - 1) / MEM_ALIGN * MEM_ALIGN;
+    }
+    ggml_object *obj = (ggml_object *)(ctx->mem_buffer + cur_end);
+    size_t obj_size;
+    if (ctx->scratch.data == nullptr || data != nullptr) {
+        obj_size = payload + sizeof(ggml_tensor);
+        if (cur_end + obj_size + sizeof(ggml_object) > ctx->mem_size) {
+            fprintf(stderr, "ggml_new_tensor_impl: not enough space in the context's memory pool (needed %zu, available %zu)\n",
+                    cur_end + obj_size + sizeof(ggml_object), ctx->mem_size);
+            return nullptr;
+        }
+    } else {
+        if (ctx->scratch.offs + payload > ctx->scratch.size) {
+            fprintf(stderr, "ggml_new_tensor_impl: not enough space in the scratch memory\n");
+            return nullptr;
+        }
+        obj_size = sizeof(ggml_tensor);
+        if (cur_end + obj_size + sizeof(ggml_object) > ctx->mem_size) {
+            fprintf(stderr, "ggml_new_tensor_impl: not enough space in the context's memory pool\n");
+            return nullptr;
+        }
+        data = (char *)ctx->scratch.data + ctx->scratch.offs;
+        ctx->scratch.offs += payload;
+    }
+    obj->offs = cur_end + sizeof(ggml_object);
+    obj->size = obj_size;
+    obj->next = nullptr;
+    if (ctx->last) ctx->last->next = obj; else ctx->first = obj;
+    ctx->last = obj;
+    ctx->n_objects++;
+
+    ggml_tensor *t = (ggml_tensor *)(ctx->mem_buffer + obj->offs);
+    memset(t, 0, sizeof(*t));
+    t->type = type;
+    t->n_dims = n_dims;
+    for (int i = 0; i < GGML_MAX_DIMS; i++) t->ne[i] = i < n_dims ? ne[i] : 1;
+    t->nb[0] = k_tsize[type];
+    t->nb[1] = t->nb[0] * (size_t)(t->ne[0] / k_blck[type]);
+    for (int i = 2; i < GGML_MAX_DIMS; i++) t->nb[i] = t->nb[i - 1] * (size_t)t->ne[i - 1];
+    t->op = GGML_OP_NONE;
+    t->data = (data == nullptr && !ctx->no_alloc) ? (void *)(t + 1) : data;
+    return t;
+}
+
+extern "C" {
+struct ggml_tensor *ggml_new_tensor(struct ggml_context *ctx, enum ggml_type type, int n_dims, const int64_t *ne) {
+    return new_tensor_impl(ctx, type, n_dims, ne, nullptr);
+}
+struct ggml_tensor *ggml_new_tensor_1d(struct ggml_context *ctx, enum ggml_type type, int64_t ne0) {
+    return new_tensor_impl(ctx, type, 1, &ne0, nullptr);
+}
+struct ggml_tensor *ggml_new_tensor_2d(struct ggml_context *ctx, enum ggml_type type, int64_t ne0, int64_t ne1) {
+    const int64_t ne[2] = {ne0, ne1};
+    return new_tensor_impl(ctx, type, 2, ne, nullptr);
+}
+struct ggml_tensor *ggml_new_tensor_3d(struct ggml_context *ctx, enum ggml_type type, int64_t ne0, int64_t ne1, int64_t ne2) {
+    const int64_t ne[3] = {ne0, ne1, ne2};
+    return new_tensor_impl(ctx, type, 3, ne, nullptr);
+}
+struct ggml_tensor *ggml_new_tensor_4d(struct ggml_context *ctx, enum ggml_type type, int64_t ne0, int64_t ne1, int64_t ne2, int64_t ne3) {
+    const int64_t ne[4] = {ne0, ne1, ne2, ne3};
+    return new_tensor_impl(ctx, type, 4, ne, nullptr);
+}
+// scalar constants never go to the scratch arena (reference lib/ggml.c:3978-4003)
+struct ggml_tensor *ggml_new_i32(struct ggml_context *ctx, int32_t value) {
+    ctx->scratch_save = ctx->scratch;
+    ctx->scratch.data = nullptr;
+    ggml_tensor *t = ggml_new_tensor_1d(ctx, GGML_TYPE_I32, 1);
+    ctx->scratch = ctx->scratch_save;
+    *(int32_t *)t->data = value;
+    return t;
+}
+struct ggml_tensor *ggml_new_f32(struct ggml_context *ctx, float value) {
+    ctx->scratch_save = ctx->scratch;
+    ctx->scratch.data = nullptr;
+    ggml_tensor *t = ggml_new_tensor_1d(ctx, GGML_TYPE_F32, 1);
+    ctx->scratch = ctx->scratch_save;
+    *(float *)t->data = value;
+    return t;
+}
+struct ggml_tensor *ggml_dup_tensor(struct ggml_context *ctx, const struct ggml_tensor *src) {
+    return new_tensor_impl(ctx, src->type, src->n_dims, src->ne, nullptr);
+}
+struct ggml_tensor *ggml_view_tensor(struct ggml_context *ctx, const struct ggml_tensor *src) {
+    ggml_tensor *t = new_tensor_impl(ctx, src->type, src->n_dims, src->ne, src->data);
+    for (int i = 0; i < GGML_MAX_DIMS; i++) t->nb[i] = src->nb[i];
+    return t;
+}
+struct ggml_tensor *ggml_set_zero(struct ggml_tensor *t) {
+    memset(t->data, 0, ggml_nbytes(t));
+    return t;
+}
+struct ggml_tensor *ggml_set_i32(struct ggml_tensor *t, int32_t value) {
+    const int64_t n = ggml_nelements(t);
+    B200_ASSERT(is_contiguous(t));
+    switch (t->type) {
+        case GGML_TYPE_I8:  for (int64_t i = 0; i < n; i++) ((int8_t *)t->data)[i] = (int8_t)value; break;
+        case GGML_TYPE_I16: for (int64_t i = 0; i < n; i++) ((int16_t *)t->data)[i] = (int16_t)value; break;
+        case GGML_TYPE_I32: for (int64_t i = 0; i < n; i++) ((int32_t *)t->data)[i] = value; break;
+        case GGML_TYPE_F16: for (int64_t i = 0; i < n; i++) ((ggml_fp16_t *)t->data)[i] = ggml_fp32_to_fp16((float)value); break;
+        case GGML_TYPE_F32: for (int64_t i = 0; i < n; i++) ((float *)t->data)[i] = (float)value; break;
+        default: B200_FAIL("ggml_set_i32: unsupported type %s", k_tname[t->type]);
+    }
+    return t;
+}
+struct ggml_tensor *ggml_set_f32(struct ggml_tensor *t, float value) {
+    const int64_t n = ggml_nelements(t);
+    B200_ASSERT(is_contiguous(t));
+    switch (t->type) {
+        case GGML_TYPE_I8:  for (int64_t i = 0; i < n; i++) ((int8_t *)t->data)[i] = (int8_t)value; break;
+        case GGML_TYPE_I16: for (int64_t i = 0; i < n; i++) ((int16_t *)t->data)[i] = (int16_t)value; break;
+        case GGML_TYPE_I32: for (int64_t i = 0; i < n; i++) ((int32_t *)t->data)[i] = (int32_t)value; break;
+        case GGML_TYPE_F16: for (int64_t i = 0; i < n; i++) ((ggml_fp16_t *)t->data)[i] = ggml_fp32_to_fp16(value); break;
+        case GGML_TYPE_F32: for (int64_t i = 0; i < n; i++) ((float *)t->data)[i] = value; break;
+        default: B200_FAIL("ggml_set_f32: unsupported type %s", k_tname[t->type]);
+    }
+    return t;
+}
+void *ggml_get_data(const struct ggml_tensor *t) { return t->data; }
+float *ggml_get_data_f32(const struct ggml_tensor *t) { return (float *)t->data; }
+
+// ================================================================================================
+// graph builders (host only).  Inference graphs carry no gradients, so ->grad stays NULL.
+// ================================================================================================
+static ggml_tensor *op_node(ggml_tensor *res, ggml_op op, ggml_tensor *a, ggml_tensor *b) {
+    res->op = op;
+    res->src0 = a;
+    res->src1 = b;
+    return res;
+}
+#define NO_GRAD(t) B200_ASSERT((t) == nullptr || (t)->grad == nullptr)
+
+struct ggml_tensor *ggml_dup(struct ggml_context *ctx, struct ggml_tensor *a) {
+    NO_GRAD(a);
+    return op_node(ggml_dup_tensor(ctx, a), GGML_OP_DUP, a, nullptr);
+}
+struct ggml_tensor *ggml_add(struct ggml_context *ctx, struct ggml_tensor *a, struct ggml_tensor *b) {
+    NO_GRAD(a); NO_GRAD(b);
+    B200_ASSERT(same_shape(a, b));
+    return op_node(ggml_dup_tensor(ctx, a), GGML_OP_ADD, a, b);
+}
+struct ggml_tensor *ggml_add_inplace(struct ggml_context *ctx, struct ggml_tensor *a, struct ggml_tensor *b) {
+    B200_ASSERT(same_shape(a, b));
+    return op_node(ggml_view_tensor(ctx, a), GGML_OP_ADD, a, b);
+}
+struct ggml_tensor *ggml_mul(struct ggml_context *ctx, struct ggml_tensor *a, struct ggml_tensor *b) {
+    NO_GRAD(a); NO_GRAD(b);
+    B200_ASSERT(same_shape(a, b));
+    return op_node(ggml_dup_tensor(ctx, a), GGML_OP_MUL, a, b);
+}
+struct ggml_tensor *ggml_repeat(struct ggml_context *ctx, struct ggml_tensor *a, struct ggml_tensor *b) {
+    NO_GRAD(a);
+    B200_ASSERT(b->ne[0] % a->ne[0] == 0 && b->ne[1] % a->ne[1] == 0 && b->ne[2] % a->ne[2] == 0 && b->ne[3] % a->ne[3] == 0);
+    if (same_shape(a, b)) return a;      // reference lib/ggml.c:4602-4604
+    return op_node(ggml_new_tensor(ctx, a->type, b->n_dims, b->ne), GGML_OP_REPEAT, a, b);
+}
+struct ggml_tensor *ggml_silu(struct ggml_context *ctx, struct ggml_tensor *a) {
+    NO_GRAD(a);
+    return op_node(ggml_dup_tensor(ctx, a), GGML_OP_SILU, a, nullptr);
+}
+struct ggml_tensor *ggml_rms_norm(struct ggml_context *ctx, struct ggml_tensor *a) {
+    NO_GRAD(a);
+    return op_node(ggml_dup_tensor(ctx, a), GGML_OP_RMS_NORM, a, nullptr);
+}
+struct ggml_tensor *ggml_mul_mat(struct ggml_context *ctx, struct ggml_tensor *a, struct ggml_tensor *b) {
+    NO_GRAD(a); NO_GRAD(b);
+    B200_ASSERT(a->ne[0] == b->ne[0] && a->ne[2] == b->ne[2] && a->ne[3] == b->ne[3]);   // ggml_can_mul_mat
+    B200_ASSERT(a->nb[0] <= a->nb[1]);                                                    // !ggml_is_transposed(a)
+    const int64_t ne[4] = {a->ne[1], b->ne[1], a->ne[2], b->ne[3]};
+    return op_node(ggml_new_tensor(ctx, GGML_TYPE_F32, std::min(a->n_dims, b->n_dims), ne), GGML_OP_MUL_MAT, a, b);
+}
+struct ggml_tensor *ggml_scale(struct ggml_context *ctx, struct ggml_tensor *a, struct ggml_tensor *b) {
+    NO_GRAD(a); NO_GRAD(b);
+    B200_ASSERT(ggml_nelements(b) == 1);
+    return op_node(ggml_view_tensor(ctx, a), GGML_OP_SCALE, a, b);          // in place, returns view(a)
+}
+struct ggml_tensor *ggml_cpy(struct ggml_context *ctx, struct ggml_tensor *a, struct ggml_tensor *b) {
+    NO_GRAD(a); NO_GRAD(b);
+    B200_ASSERT(ggml_nelements(a) == ggml_nelements(b));
+    return op_node(ggml_view_tensor(ctx, b), GGML_OP_CPY, a, b);            // result is a view of the destination
+}
+struct ggml_tensor *ggml_cont(struct ggml_context *ctx, struct ggml_tensor *a) {
+    NO_GRAD(a);
+    return op_node(ggml_dup_tensor(ctx, a), GGML_OP_CONT, a, nullptr);
+}
+struct ggml_tensor *ggml_reshape(struct ggml_context *ctx, struct ggml_tensor *a, struct ggml_tensor *b) {
+    NO_GRAD(a);
+    B200_ASSERT(is_contiguous(a) && is_contiguous(b) && ggml_nelements(a) == ggml_nelements(b));
+    return op_node(new_tensor_impl(ctx, a->type, b->n_dims, b->ne, a->data), GGML_OP_RESHAPE, a, nullptr);
+}
+struct ggml_tensor *ggml_reshape_2d(struct ggml_context *ctx, struct ggml_tensor *a, int64_t ne0, int64_t ne1) {
+    NO_GRAD(a);
+    B200_ASSERT(is_contiguous(a) && ggml_nelements(a) == ne0 * ne1);
+    const int64_t ne[2] = {ne0, ne1};
+    return op_node(new_tensor_impl(ctx, a->type, 2, ne, a->data), GGML_OP_RESHAPE, a, nullptr);
+}
+struct ggml_tensor *ggml_reshape_3d(struct ggml_context *ctx, struct ggml_tensor *a, int64_t ne0, int64_t ne1, int64_t ne2) {
+    NO_GRAD(a);
+    B200_ASSERT(is_contiguous(a) && ggml_nelements(a) == ne0 * ne1 * ne2);
+    const int64_t ne[3] = {ne0, ne1, ne2};
+    return op_node(new_tensor_impl(ctx, a->type, 3, ne, a->data), GGML_OP_RESHAPE, a, nullptr);
+}
+struct ggml_tensor *ggml_view_1d(struct ggml_context *ctx, struct ggml_tensor *a, int64_t ne0, size_t offset) {
+    NO_GRAD(a);
+    return op_node(new_tensor_impl(ctx, a->type, 1, &ne0, (char *)a->data + offset), GGML_OP_VIEW, a, nullptr);
+}
+struct ggml_tensor *ggml_view_2d(struct ggml_context *ctx, struct ggml_tensor *a, int64_t ne0, int64_t ne1, size_t nb1, size_t offset) {
+    NO_GRAD(a);
+    const int64_t ne[2] = {ne0, ne1};
+    ggml_tensor *t = new_tensor_impl(ctx, a->type, 2, ne, (char *)a->data + offset);
+    t->nb[1] = nb1;
+    t->nb[2] = t->nb[1] * (size_t)ne1;
+    t->nb[3] = t->nb[2];
+    return op_node(t, GGML_OP_VIEW, a, nullptr);
+}
+struct ggml_tensor *ggml_view_3d(struct ggml_context *ctx, struct ggml_tensor *a, int64_t ne0, int64_t ne1, int64_t ne2, size_t nb1, size_t nb2, size_t offset) {
+    NO_GRAD(a);
+    const int64_t ne[3] = {ne0, ne1, ne2};
+    ggml_tensor *t = new_tensor_impl(ctx, a->type, 3, ne, (char *)a->data + offset);
+    t->nb[1] = nb1;
+    t->nb[2] = nb2;
+    t->nb[3] = t->nb[2] * (size_t)ne2;
+    return op_node(t, GGML_OP_VIEW, a, nullptr);
+}
+struct ggml_tensor *ggml_permute(struct ggml_context *ctx, struct ggml_tensor *a, int ax0, int ax1, int ax2, int ax3) {
+    NO_GRAD(a);
+    const int ax[4] = {ax0, ax1, ax2, ax3};
+    bool seen[4] = {false, false, false, false};
+    for (int i = 0; i < 4; i++) {
+        B200_ASSERT(ax[i] >= 0 && ax[i] < 4 && !seen[ax[i]]);
+        seen[ax[i]] = true;
+    }
+    ggml_tensor *t = ggml_view_tensor(ctx, a);
+    for (int i = 0; i < 4; i++) {       // source axis i becomes axis ax[i]
+        t->ne[ax[i]] = a->ne[i];
+        t->nb[ax[i]] = a->nb[i];
+    }
+    return op_node(t, GGML_OP_PERMUTE, a, nullptr);
+}
+struct ggml_tensor *ggml_transpose(struct ggml_context *ctx, struct ggml_tensor *a) {
+    NO_GRAD(a);
+    ggml_tensor *t = ggml_view_tensor(ctx, a);
+    t->ne[0] = a->ne[1]; t->ne[1] = a->ne[0];
+    t->nb[0] = a->nb[1]; t->nb[1] = a->nb[0];
+    return op_node(t, GGML_OP_TRANSPOSE, a, nullptr);
+}
+struct ggml_tensor *ggml_get_rows(struct ggml_context *ctx, struct ggml_tensor *a, struct ggml_tensor *b) {
+    NO_GRAD(a); NO_GRAD(b);
+    B200_ASSERT(a->ne[2] == 1 && a->ne[3] == 1 && b->ne[1] == 1 && b->ne[2] == 1 && b->ne[3] == 1 && b->type == GGML_TYPE_I32);
+    return op_node(ggml_new_tensor_2d(ctx, GGML_TYPE_F32, a->ne[0], b->ne[0]), GGML_OP_GET_ROWS, a, b);
+}
+struct ggml_tensor *ggml_diag_mask_inf(struct ggml_context *ctx, struct ggml_tensor *a, int n_past) {
+    NO_GRAD(a);
+    ggml_tensor *t = ggml_view_tensor(ctx, a);
+    ggml_tensor *p = ggml_new_i32(ctx, n_past);
+    return op_node(t, GGML_OP_DIAG_MASK_INF, a, p);
+}
+struct ggml_tensor *ggml_soft_max(struct ggml_context *ctx, struct ggml_tensor *a) {
+    NO_GRAD(a);
+    return op_node(ggml_view_tensor(ctx, a), GGML_OP_SOFT_MAX, a, nullptr);
+}
+struct ggml_tensor *ggml_rope(struct ggml_context *ctx, struct ggml_tensor *a, int n_past, int n_dims, int mode) {
+    NO_GRAD(a);
+    B200_ASSERT(n_past >= 0);
+    ggml_tensor *t = ggml_view_tensor(ctx, a);
+    ggml_tensor *p = ggml_new_tensor_1d(ctx, GGML_TYPE_I32, 3);
+    ((int32_t *)p->data)[0] = n_past;
+    ((int32_t *)p->data)[1] = n_dims;
+    ((int32_t *)p->data)[2] = mode;
+    return op_node(t, GGML_OP_ROPE, a, p);
+}
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// graph construction: depth-first post-order like the reference (lib/ggml.c:10551-10600) so node
+// order -- and therefore execution order on the stream -- is identical.  The reference finds
+// "already visited" by scanning the node list (O(n^2), ~0.4 ms for a 7B graph); we stamp each
+// tensor's spare padding bytes with (graph epoch, index) instead.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Stamp { uint32_t epoch; int32_t index; };     // lives in ggml_tensor::padding (8 bytes)
+static_assert(sizeof(Stamp) == 8, "stamp must fit the tensor padding");
+uint32_t g_epoch = 0;                                // last epoch handed out
+// Which epoch a cgraph's stamps carry.  `clean` = every tensor of the graph was stamped under this
+// entry (false for a graph we first meet half-built, e.g. a by-value copy of ggml_build_forward's
+// result): then membership falls back to the reference's pointer scan.
+struct GraphEpoch { const ggml_cgraph *g; uint32_t epoch; bool clean; };
+GraphEpoch g_graph_epochs[8];
+int g_graph_epoch_next = 0;
+
+inline Stamp *stamp_of(ggml_tensor *t) { return (Stamp *)t->padding; }
+
+GraphEpoch *lookup_epoch(const ggml_cgraph *g) {
+    for (auto &ge : g_graph_epochs)
+        if (ge.g == g && ge.epoch != 0) return &ge;
+    return nullptr;
+}
+GraphEpoch *new_epoch(const ggml_cgraph *g, bool clean) {
+    if (++g_epoch == 0) ++g_epoch;
+    GraphEpoch *slot = lookup_epoch(g);
+    if (!slot) {
+        slot = &g_graph_epochs[g_graph_epoch_next];
+        g_graph_epoch_next = (g_graph_epoch_next + 1) % 8;
+    }
+    *slot = GraphEpoch{g, g_epoch, clean};
+    return slot;
+}
+
+// index encoding: >= 0 node index, < 0 -> leaf index = -1 - index
+bool graph_contains(const ggml_cgraph *g, const ggml_tensor *t, uint32_t epoch, bool interleaved) {
+    const Stamp *s = (const Stamp *)t->padding;
+    if (s->epoch == epoch) {
+        if (s->index >= 0 && s->index < g->n_nodes && g->nodes[s->index] == t) return true;
+        if (s->index < 0 && -1 - s->index < g->n_leafs && g->leafs[-1 - s->index] == t) return true;
+    }
+    if (!interleaved) return false;
+    for (int i = 0; i < g->n_nodes; i++) if (g->nodes[i] == t) return true;     // another graph re-stamped it
+    for (int i = 0; i < g->n_leafs; i++) if (g->leafs[i] == t) return true;
+    return false;
+}
+
+void visit(ggml_cgraph *g, ggml_tensor *t, uint32_t epoch, bool interleaved) {
+    if (graph_contains(g, t, epoch, interleaved)) return;
+    if (t->src0) visit(g, t->src0, epoch, interleaved);
+    if (t->src1) visit(g, t->src1, epoch, interleaved);
+    for (int i = 0; i < GGML_MAX_OPT; i++) if (t->opt[i]) visit(g, t->opt[i], epoch, interleaved);
+    Stamp *s = stamp_of(t);
+    if (t->op == GGML_OP_NONE && t->grad == nullptr) {
+        B200_ASSERT(g->n_leafs < GGML_MAX_NODES);
+        s->epoch = epoch; s->index = -1 - g->n_leafs;
+        g->leafs[g->n_leafs++] = t;
+    } else {
+        B200_ASSERT(g->n_nodes < GGML_MAX_NODES);
+        s->epoch = epoch; s->index = g->n_nodes;
+        g->grads[g->n_nodes] = t->grad;
+        g->nodes[g->n_nodes++] = t;
+    }
+}
+}  // namespace
+
+extern "C" void ggml_build_forward_expand(struct ggml_cgraph *g, struct ggml_tensor *tensor) {
+    const bool fresh = g->n_nodes == 0 && g->n_leafs == 0;
+    GraphEpoch *ge = fresh ? new_epoch(g, true) : lookup_epoch(g);
+    if (!ge) ge = new_epoch(g, false);
+    // stamps are authoritative only while no other graph has been started since (it may have
+    // re-stamped shared tensors such as weights) and the graph was stamped from its first node
+    const bool scan = !ge->clean || ge->epoch != g_epoch;
+    const int n0 = g->n_nodes;
+    visit(g, tensor, ge->epoch, scan);
+    if (g->n_nodes > n0) B200_ASSERT(g->nodes[g->n_nodes - 1] == tensor);
+}
+extern "C" struct ggml_cgraph ggml_build_forward(struct ggml_tensor *tensor) {
+    static thread_local ggml_cgraph g;               // returned by value; the static avoids a 96 KB stack temp
+    memset(&g, 0, sizeof(g));
+    g.n_threads = GGML_DEFAULT_N_THREADS;
+    // build into the static, then re-key the epoch entry so the caller's copy keeps working
+    ggml_build_forward_expand(&g, tensor);
+    return g;
+}
+
+// ================================================================================================
+// 2. device residency: mirrors of host arenas
+// ================================================================================================
+namespace {
+enum MirrorKind { MK_ARENA = 0, MK_EXTERNAL = 1, MK_SCRATCH = 2 };
+struct Mirror {
+    const char *host;        // arena base
+    size_t size;
+    char *dev;               // equally sized device allocation (lazy)
+    ggml_context *ctx;       // live context owning the arena, or nullptr (freed / not an arena)
+    size_t uploaded;         // bytes [0, uploaded) of a persistent arena already copied to the device
+    int kind;                // MK_ARENA: a ggml context buffer; MK_EXTERNAL: a bare tensor range that is
+                             // not a ggml arena (mmap'ed weights), uploaded once; MK_SCRATCH: a
+                             // ggml_set_scratch buffer (activations only, never uploaded)
+};
+std::vector<Mirror> g_mirrors;
+int g_last_mirror = -1;
+bool g_verbose = false;
+
+struct Stats { uint64_t n_evals = 0; double last_us = 0, total_us = 0; uint64_t graph_replays = 0; } g_stats;
+
+void ensure_backend() {
+    static bool done = false;
+    if (done) return;
+    if (fl_init(-1) != 0) B200_FAIL("cannot initialise the B200 backend: %s", fl_last_error());
+    g_verbose = getenv("FASTLLAMA_B200_VERBOSE") != nullptr;
+    done = true;
+}
+
+void drop_mirror(Mirror &m) {
+    if (m.dev) {
+        if (fl_is_initialized()) fl_dev_free(m.dev);
+        m.dev = nullptr;
+    }
+}
+
+int find_mirror(const void *p) {
+    const char *c = (const char *)p;
+    if (g_last_mirror >= 0 && g_last_mirror < (int)g_mirrors.size()) {
+        const Mirror &m = g_mirrors[g_last_mirror];
+        if (c >= m.host && c < m.host + m.size) return g_last_mirror;
+    }
+    for (int i = 0; i < (int)g_mirrors.size(); i++) {
+        const Mirror &m = g_mirrors[i];
+        if (c >= m.host && c < m.host + m.size) return g_last_mirror = i;
+    }
+    return -1;
+}
+
+Mirror &mirror_alloc(Mirror &m) {
+    if (!m.dev) {
+        ensure_backend();
+        m.dev = (char *)fl_dev_malloc(m.size);
+        if (!m.dev) B200_FAIL("device mirror of %zu bytes: %s", m.size, fl_last_error());
+        if (g_verbose) fprintf(stderr, "[ggml_b200] mirror %p +%zu MiB -> dev %p%s\n", (const void *)m.host, m.size >> 20, (void *)m.dev, m.kind == MK_EXTERNAL ? " (external)" : m.kind == MK_SCRATCH ? " (scratch)" : "");
+    }
+    return m;
+}
+}  // namespace
+
+static void mirrors_on_ctx_init(ggml_context *ctx) {
+    // an arena re-created over the same buffer (Model::eval does this every call) re-uses its mirror
+    for (auto it = g_mirrors.begin(); it != g_mirrors.end();) {
+        const bool same = it->host == ctx->mem_buffer && it->size == ctx->mem_size;
+        const bool overlap = it->host < ctx->mem_buffer + ctx->mem_size && ctx->mem_buffer < it->host + it->size;
+        if (same) { it->ctx = ctx; it->uploaded = 0; return; }
+        if (overlap && it->ctx == nullptr) { drop_mirror(*it); it = g_mirrors.erase(it); g_last_mirror = -1; continue; }
+        ++it;
+    }
+    g_mirrors.push_back(Mirror{ctx->mem_buffer, ctx->mem_size, nullptr, ctx, 0, MK_ARENA});
+}
+static void mirrors_on_scratch(void *data, size_t size) {
+    for (auto &m : g_mirrors)
+        if (m.host == (const char *)data && m.size == size) return;
+    g_mirrors.push_back(Mirror{(const char *)data, size, nullptr, nullptr, 0, MK_SCRATCH});
+}
+static void mirrors_on_ctx_free(ggml_context *ctx) {
+    for (auto &m : g_mirrors)
+        if (m.ctx == ctx) m.ctx = nullptr;          // keep the device allocation for the next ggml_init over this buffer
+}
+
+// host pointer -> device pointer.  `compute_ctx` is the arena of the graph being run: nothing in it
+// is uploaded here (its leafs are handled per graph); every other arena is persistent and is
+// uploaded once, incrementally as it fills.
+static char *dev_ptr(const void *host, size_t nbytes, const ggml_context *compute_ctx) {
+    int i = find_mirror(host);
+    if (i < 0) {
+        // not inside any ggml arena: the tensor's data points at foreign memory (mmap'ed weights)
+        g_mirrors.push_back(Mirror{(const char *)host, nbytes, nullptr, nullptr, 0, MK_EXTERNAL});
+        i = (int)g_mirrors.size() - 1;
+    }
+    Mirror &m = mirror_alloc(g_mirrors[i]);
+    const size_t off = (const char *)host - m.host;
+    if (m.kind != MK_ARENA && off + nbytes > m.size)
+        B200_FAIL("tensor at %p (+%zu) straddles the end of a registered range %p (+%zu)", host, nbytes, (const void *)m.host, m.size);
+    size_t want = 0;
+    if (m.kind == MK_EXTERNAL) want = m.size;
+    else if (m.kind == MK_ARENA && m.ctx != compute_ctx) want = std::min(m.size, std::max(off + nbytes, m.ctx ? ggml_used_mem(m.ctx) : (size_t)0));
+    if (want > m.uploaded) {
+        if (g_verbose) fprintf(stderr, "[ggml_b200] upload %p [%zu, %zu) -> device\n", (const void *)m.host, m.uploaded, want);
+        FLC(fl_h2d(m.dev + m.uploaded, m.host + m.uploaded, want - m.uploaded));
+        m.uploaded = want;
+    }
+    return m.dev + off;
+}
+
+extern "C" void ggml_b200_invalidate(const void *ptr, size_t size) {
+    const int i = find_mirror(ptr);
+    if (i < 0 || !g_mirrors[i].dev) return;
+    Mirror &m = g_mirrors[i];
+    const size_t off = (const char *)ptr - m.host;
+    const size_t end = std::min(off + size, m.uploaded);
+    if (end > off) FLC(fl_h2d(m.dev + off, m.host + off, end - off));
+}
+extern "C" void ggml_b200_sync_to_host(const void *ptr, size_t size) {
+    const int i = find_mirror(ptr);
+    if (i < 0 || !g_mirrors[i].dev) return;
+    Mirror &m = g_mirrors[i];
+    const size_t off = (const char *)ptr - m.host;
+    const size_t n = std::min(size, m.size - off);
+    FLC(fl_d2h((void *)(m.host + off), m.dev + off, n));
+    FLC(fl_sync());
+}
+extern "C" void ggml_b200_release_all(void) {
+    if (fl_is_initialized()) fl_sync();
+    for (auto &m : g_mirrors) drop_mirror(m);
+    g_mirrors.erase(std::remove_if(g_mirrors.begin(), g_mirrors.end(), [](const Mirror &m) { return m.ctx == nullptr; }), g_mirrors.end());
+    for (auto &m : g_mirrors) m.uploaded = 0;
+    g_last_mirror = -1;
+}
+extern "C" void ggml_b200_get_stats(struct ggml_b200_stats *out) {
+    out->n_evals = g_stats.n_evals;
+    out->last_eval_device_us = g_stats.last_us;
+    out->total_device_us = g_stats.total_us;
+    out->launches = fl_is_initialized() ? fl_launch_count() : 0;
+    out->graph_replays = g_stats.graph_replays;
+}
+
+// ================================================================================================
+// 3. executor
+// ================================================================================================
+namespace {
+struct Exec {
+    const ggml_context *ctx;
+    void *q8_work = nullptr;     // device scratch for quantised activations (the reference's "wdata")
+    size_t q8_cap = 0;
+};
+Exec g_exec;
+
+fl_view view_of(const ggml_tensor *t, const ggml_context *cctx) {
+    fl_view v;
+    v.data = dev_ptr(t->data, ggml_nbytes(t), cctx);
+    for (int i = 0; i < 4; i++) { v.ne[i] = t->ne[i]; v.nb[i] = (int64_t)t->nb[i]; }
+    return v;
+}
+
+void need_f32(const ggml_tensor *t, const char *what) {
+    if (t->type != GGML_TYPE_F32) B200_FAIL("%s: tensor type %s is not supported by the B200 backend (f32 only)", what, k_tname[t->type]);
+}
+
+void exec_mul_mat(const ggml_tensor *node, const ggml_context *cctx) {
+    const ggml_tensor *a = node->src0, *b = node->src1;
+    need_f32(b, "mul_mat src1");
+    if (a->type == GGML_TYPE_F32) {
+        fl_view va = view_of(a, cctx), vb = view_of(b, cctx), vd = view_of(node, cctx);
+        FLC(fl_dev_mul_mat_f32(&va, &vb, &vd));
+        return;
+    }
+    if (a->type != GGML_TYPE_Q4_0 && a->type != GGML_TYPE_Q4_1)
+        B200_FAIL("mul_mat: weight type %s is not supported by the B200 backend (q4_0, q4_1, f32)", k_tname[a->type]);
+    // ggml_compute_forward_mul_mat_q_f32 preconditions (reference lib/ggml.c:7969-7991)
+    B200_ASSERT(a->ne[2] == 1 && a->ne[3] == 1 && b->ne[2] == 1 && b->ne[3] == 1);
+    B200_ASSERT(a->nb[0] == k_tsize[a->type] && b->nb[0] == sizeof(float) && node->nb[0] == sizeof(float));
+    B200_ASSERT(a->ne[0] % 32 == 0 && a->ne[0] == b->ne[0]);
+    const int M = (int)a->ne[1], K = (int)a->ne[0], N = (int)b->ne[1];
+    const size_t q8_bytes = (size_t)(K / 32) * 40 * (size_t)N;
+    if (g_exec.q8_cap < q8_bytes) {
+        if (g_exec.q8_work) FLC(fl_dev_free(g_exec.q8_work));
+        g_exec.q8_cap = std::max(q8_bytes, (size_t)1 << 20);
+        g_exec.q8_work = fl_dev_malloc(g_exec.q8_cap);
+        if (!g_exec.q8_work) B200_FAIL("q8_0 work buffer: %s", fl_last_error());
+    }
+    const char *W = dev_ptr(a->data, ggml_nbytes(a), cctx);
+    const float *X = (const float *)dev_ptr(b->data, ggml_nbytes(b), cctx);
+    float *D = (float *)dev_ptr(node->data, ggml_nbytes(node), cctx);
+    // INIT phase: src1 rows -> q8_0 (reference lib/ggml.c:8105-8119)
+    FLC(fl_dev_quantize_q8_0(X, b->nb[1], g_exec.q8_work, K, N));
+    // COMPUTE phase (reference lib/ggml.c:8125-8163)
+    FLC(fl_dev_mul_mat_q((int)a->type, W, a->nb[1], M, K, g_exec.q8_work, N, D, node->nb[1] / sizeof(float), 0));
+}
+
+void exec_node(ggml_tensor *node, const ggml_context *cctx) {
+    switch (node->op) {
+        case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE:
+            return;                                   // pure address arithmetic, already in node->data / nb
+        case GGML_OP_GET_ROWS: {
+            const ggml_tensor *a = node->src0, *ids = node->src1;
+            if (a->type != GGML_TYPE_Q4_0 && a->type != GGML_TYPE_Q4_1)
+                B200_FAIL("get_rows: table type %s is not supported by the B200 backend (q4_0, q4_1)", k_tname[a->type]);
+            FLC(fl_dev_dequantize_rows((int)a->type, dev_ptr(a->data, ggml_nbytes(a), cctx), a->nb[1], (int)a->ne[0],
+                                       (const int32_t *)dev_ptr(ids->data, ggml_nbytes(ids), cctx), (int)ggml_nelements(ids),
+                                       (float *)dev_ptr(node->data, ggml_nbytes(node), cctx), node->nb[1] / sizeof(float)));
+            return;
+        }
+        case GGML_OP_RMS_NORM: {
+            need_f32(node->src0, "rms_norm");
+            fl_view s = view_of(node->src0, cctx), d = view_of(node, cctx);
+            FLC(fl_dev_rms_norm(&s, &d));
+            return;
+        }
+        case GGML_OP_ADD: case GGML_OP_MUL: {
+            need_f32(node->src0, k_opname[node->op]); need_f32(node->src1, k_opname[node->op]);
+            fl_view a = view_of(node->src0, cctx), b = view_of(node->src1, cctx), d = view_of(node, cctx);
+            if (node->op == GGML_OP_ADD) FLC(fl_dev_add(&a, &b, &d)); else FLC(fl_dev_mul(&a, &b, &d));
+            return;
+        }
+        case GGML_OP_REPEAT: {
+            need_f32(node->src0, "repeat");
+            fl_view s = view_of(node->src0, cctx), d = view_of(node, cctx);
+            FLC(fl_dev_repeat(&s, &d));
+            return;
+        }
+        case GGML_OP_SILU: {
+            need_f32(node->src0, "silu");
+            fl_view s = view_of(node->src0, cctx), d = view_of(node, cctx);
+            FLC(fl_dev_silu(&s, &d));
+            return;
+        }
+        case GGML_OP_MUL_MAT:
+            exec_mul_mat(node, cctx);
+            return;
+        case GGML_OP_SCALE: {
+            need_f32(node->src0, "scale");
+            if (node->src1->op != GGML_OP_NONE) B200_FAIL("scale: the factor must be a host constant (ggml_new_f32)");
+            fl_view d = view_of(node, cctx);
+            FLC(fl_dev_scale(&d, *(const float *)node->src1->data));
+            return;
+        }
+        case GGML_OP_DIAG_MASK_INF: {
+            need_f32(node->src0, "diag_mask_inf");
+            fl_view d = view_of(node, cctx);
+            FLC(fl_dev_diag_mask_inf(&d, *(const int32_t *)node->src1->data));
+            return;
+        }
+        case GGML_OP_SOFT_MAX: {
+            need_f32(node->src0, "soft_max");
+            fl_view d = view_of(node, cctx);
+            FLC(fl_dev_soft_max(&d));
+            return;
+        }
+        case GGML_OP_ROPE: {
+            need_f32(node->src0, "rope");
+            const int32_t *p = (const int32_t *)node->src1->data;
+            fl_view d = view_of(node, cctx);
+            FLC(fl_dev_rope(&d, p[0], p[1], p[2]));
+            return;
+        }
+        case GGML_OP_CPY: case GGML_OP_DUP: case GGML_OP_CONT: {
+            need_f32(node->src0, "cpy src"); need_f32(node, "cpy dst (an f16 KV cache is not supported)");
+            fl_view s = view_of(node->src0, cctx), d = view_of(node, cctx);
+            FLC(fl_dev_cpy_f32(&s, &d));
+            return;
+        }
+        default:
+            B200_FAIL("op %s is outside the LLaMA eval set and has no B200 implementation (and there is no CPU fallback)", k_opname[node->op]);
+    }
+}
+
+inline bool in_ctx(const ggml_context *c, const void *p) {
+    return c && (const char *)p >= c->mem_buffer && (const char *)p < c->mem_buffer + c->mem_size;
+}
+}  // namespace
+
+extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph *g) {
+    ensure_backend();
+    static void *ev0 = nullptr, *ev1 = nullptr;
+    if (!ev0) { ev0 = fl_event_create(); ev1 = fl_event_create(); }
+    const int64_t t_start = ggml_time_us();
+    static const bool sync_all = getenv("FASTLLAMA_B200_SYNC_ALL") != nullptr;
+
+    g->work = nullptr;
+    g->work_size = 0;
+
+    // Leafs.  Weights / KV cache live in persistent arenas (uploaded once by dev_ptr).  Constants the
+    // host wrote into the compute arena while building the graph are uploaded per graph, but only
+    // those a device op reads as DATA (token ids); rope / mask / scale parameters are read on the
+    // host at dispatch, so ~130 tiny copies per 7B token are avoided.
+    {
+        const ggml_tensor *done[16];
+        int n_done = 0;
+        auto upload_leaf = [&](const ggml_tensor *t) {
+            if (!t || t->op != GGML_OP_NONE || !t->data || !in_ctx(ctx, t->data)) return;
+            for (int i = 0; i < n_done; i++) if (done[i] == t) return;
+            const size_t nb = ggml_nbytes(t);
+            FLC(fl_h2d(dev_ptr(t->data, nb, ctx), t->data, nb));
+            if (n_done < 16) done[n_done++] = t;
+        };
+        for (int i = 0; i < g->n_nodes; i++) {
+            const ggml_tensor *n = g->nodes[i];
+            const bool param_only = n->op == GGML_OP_SCALE || n->op == GGML_OP_DIAG_MASK_INF || n->op == GGML_OP_ROPE;
+            upload_leaf(n->src0);
+            if (!param_only) upload_leaf(n->src1);
+        }
+    }
+
+    FLC(fl_event_record(ev0));
+    for (int i = 0; i < g->n_nodes; i++) exec_node(g->nodes[i], ctx);
+    FLC(fl_event_record(ev1));
+
+    // results the caller may read on the host (reference lib/llama.cpp:476-489): graph sinks that
+    // live in the compute arena (the logits) and the input of the last mul_mat (the embeddings).
+    std::vector<char> consumed((size_t)g->n_nodes, 0);
+    {
+        const GraphEpoch *ge = lookup_epoch(g);
+        const bool by_stamp = ge && ge->clean && ge->epoch == g_epoch;
+        std::unordered_map<const ggml_tensor *, int> index;
+        if (!by_stamp)
+            for (int i = 0; i < g->n_nodes; i++) index[g->nodes[i]] = i;
+        auto mark = [&](const ggml_tensor *s) {
+            if (!s) return;
+            if (by_stamp) {
+                const Stamp *st = (const Stamp *)s->padding;
+                if (st->epoch == ge->epoch && st->index >= 0 && st->index < g->n_nodes && g->nodes[st->index] == s) consumed[st->index] = 1;
+            } else {
+                auto it = index.find(s);
+                if (it != index.end()) consumed[it->second] = 1;
+            }
+        };
+        for (int i = 0; i < g->n_nodes; i++) {
+            mark(g->nodes[i]->src0); mark(g->nodes[i]->src1);
+            for (int k = 0; k < GGML_MAX_OPT; k++) mark(g->nodes[i]->opt[k]);
+        }
+    }
+    const ggml_tensor *last_mm = nullptr;
+    for (int i = g->n_nodes - 1; i >= 0 && !last_mm; i--)
+        if (g->nodes[i]->op == GGML_OP_MUL_MAT) last_mm = g->nodes[i];
+    for (int i = 0; i < g->n_nodes; i++) {
+        ggml_tensor *t = g->nodes[i];
+        const bool want = sync_all || !consumed[i] || (last_mm && t == last_mm->src1);
+        if (!want || !in_ctx(ctx, t->data) || !is_contiguous(t)) continue;
+        const size_t nb = ggml_nbytes(t);
+        FLC(fl_d2h(t->data, dev_ptr(t->data, nb, ctx), nb));
+    }
+    FLC(fl_sync());
+
+    float ms = 0.f;
+    FLC(fl_event_elapsed_ms(ev0, ev1, &ms));
+    g_stats.n_evals++;
+    g_stats.last_us = ms * 1000.0;
+    g_stats.total_us += ms * 1000.0;
+    g->perf_runs++;
+    g->perf_time_us += ggml_time_us() - t_start;
+}
+
+// ================================================================================================
+// quantisation entry points (model-file creation, test hook) -- all on the GPU
+// ================================================================================================
+static void hist_add(const uint8_t *blocks, size_t nblocks, size_t bb, size_t qoff, int64_t *hist) {
+    if (!hist) return;
+    for (size_t i = 0; i < nblocks; i++) {
+        const uint8_t *qs = blocks + i * bb + qoff;
+        for (int j = 0; j < 16; j++) { hist[qs[j] & 0xF]++; hist[qs[j] >> 4]++; }
+    }
+}
+extern "C" size_t ggml_quantize_q4_0(const float *src, void *dst, int n, int k, int64_t *hist) {
+    ensure_backend();
+    B200_ASSERT(k % 32 == 0 && n % k == 0);
+    FLC(fl_quantize_rows_q4(FL_Q4_0, src, dst, k, n / k));
+    hist_add((const uint8_t *)dst, (size_t)n / 32, 20, 4, hist);
+    return (size_t)n / 32 * 20;
+}
+extern "C" size_t ggml_quantize_q4_1(const float *src, void *dst, int n, int k, int64_t *hist) {
+    ensure_backend();
+    B200_ASSERT(k % 32 == 0 && n % k == 0);
+    FLC(fl_quantize_rows_q4(FL_Q4_1, src, dst, k, n / k));
+    hist_add((const uint8_t *)dst, (size_t)n / 32, 24, 8, hist);
+    return (size_t)n / 32 * 24;
+}
+extern "C" size_t ggml_quantize_chunk(enum ggml_type type, const float *src, void *dst, int start, int n, int64_t *hist) {
+    B200_ASSERT(start % 32 == 0);
+    switch (type) {
+        case GGML_TYPE_Q4_0: return ggml_quantize_q4_0(src + start, (char *)dst + (size_t)start / 32 * 20, n, n, hist);
+        case GGML_TYPE_Q4_1: return ggml_quantize_q4_1(src + start, (char *)dst + (size_t)start / 32 * 24, n, n, hist);
+        default: B200_FAIL("ggml_quantize_chunk: type %s is not supported by the B200 backend (q4_0, q4_1)", k_tname[type]);
+    }
+}
+
+namespace {
+template <int T> void hook_dequantize(const void *x, float *y, int k) { ensure_backend(); FLC(fl_dequantize_rows_q4(T, x, y, k, 1)); }
+template <int T> void hook_quantize_ref(const float *x, void *y, int k) { ensure_backend(); FLC(fl_quantize_rows_q4(T, x, y, k, 1)); }
+void hook_quantize_q8(const float *x, void *y, int k) { ensure_backend(); FLC(fl_quantize_row_q8_0(x, y, k)); }
+template <int T> void hook_vec_dot(const int n, float *s, const void *x, const void *y) { ensure_backend(); FLC(fl_vec_dot_q4_q8(T, n, s, x, y)); }
+}  // namespace
+
+extern "C" quantize_fns_t ggml_internal_get_quantize_fn(size_t i) {
+    quantize_fns_t f = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (i == GGML_TYPE_Q4_0) f = {hook_dequantize<FL_Q4_0>, hook_quantize_ref<FL_Q4_0>, hook_quantize_ref<FL_Q4_0>, hook_quantize_q8, hook_vec_dot<FL_Q4_0>};
+    if (i == GGML_TYPE_Q4_1) f = {hook_dequantize<FL_Q4_1>, hook_quantize_ref<FL_Q4_1>, hook_quantize_ref<FL_Q4_1>, hook_quantize_q8, hook_vec_dot<FL_Q4_1>};
+    if (i == GGML_TYPE_Q8_0) f.quantize_row_q = f.quantize_row_q_reference = f.quantize_row_q_dot = hook_quantize_q8;
+    return f;
+}

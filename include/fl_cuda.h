@@ -1,0 +1,140 @@
+/*
+ * fl_cuda.h -- the thin extern-"C" CUDA layer of the B200 backend (libfl_cuda.so).
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.  Every entry point
+ * cites the reference interface it replaces (file:line relative to the reference tree).
+ *
+ * Two groups:
+ *   (1) HOST-BUFFER entry points: drop-in replacements for the row functions the reference
+ *       dispatches through quantize_fns[type] (lib/ggml.c:1731-1773, type quantize_fns_t
+ *       include/ggml.h:850-862) and for ggml_compute_forward_mul_mat_q_f32.  Inputs and outputs
+ *       are host memory; each call does H2D -> sm_100a kernel -> D2H on the library stream and
+ *       returns when the result is in the output buffer.  This is what a cgo/ctypes/FFI binding of
+ *       the reference's test hook (ggml_internal_get_quantize_fn) would bind.
+ *   (2) DEVICE-RESIDENT entry points (fl_dev_*): the same kernels on device pointers, used by the
+ *       ggml-compatible graph executor (include/fl_ggml.h) so weights, KV cache and activations
+ *       never leave HBM between ops.
+ *
+ * Conventions: every function returning int returns 0 on success, negative on error
+ * (fl_last_error() describes it).  There is no CPU fallback: without a CUDA device fl_init fails
+ * and every other entry point fails with "not initialised".  Single caller thread (the reference
+ * drives ggml from one thread); all work is issued on one internal stream.
+ */
+#ifndef FL_CUDA_H
+#define FL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ggml_type values the backend understands (include/ggml.h:201-214; file-format contract) */
+enum { FL_F32 = 0, FL_F16 = 1, FL_Q4_0 = 2, FL_Q4_1 = 3, FL_Q8_0 = 6 };
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int fl_init(int device);              /* idempotent; device = -1 -> $FASTLLAMA_DEVICE or $LOCAL_RANK or 0 */
+void fl_shutdown(void);
+int fl_is_initialized(void);
+const char *fl_last_error(void);
+int fl_device_props(char *name, int name_len, int *sm_count, size_t *hbm_bytes, int *cc_major, int *cc_minor);
+void *fl_stream(void);                /* the cudaStream_t all launches use (for CUDA-event timing) */
+
+/* ---- (1) host-buffer entry points --------------------------------------------------------- */
+
+/* quantize_row_q8_0 == quantize_fns[Q4_0|Q4_1].quantize_row_q_dot (lib/ggml.c:1299-1441; AVX2
+ * semantics: d = amax/127, id = 127/amax, round-half-even, s = d*sum).  x: k floats, y: k/32
+ * q8_0 blocks.  Bit-exact with the reference. */
+int fl_quantize_row_q8_0(const float *x, void *y, int k);
+int fl_quantize_rows_q8_0(const float *x, void *y, int k, int nrows);
+
+/* quantize_row_q4_0_reference / _q4_1_reference == quantize_fns[type].quantize_row_q_reference,
+ * the functions that define model-file contents (lib/ggml.c:630-664, :917-956, used by
+ * ggml_quantize_q4_0/_q4_1 :12122-12166).  Bit-exact. */
+int fl_quantize_rows_q4(int type, const float *x, void *y, int k, int nrows);
+
+/* dequantize_row_q4_0 / _q4_1 == quantize_fns[type].dequantize_row_q (lib/ggml.c:1443-1665).
+ * Bit-exact (q4_1 uses a fused multiply-add like the reference's GNU-mode x86 build). */
+int fl_dequantize_rows_q4(int type, const void *x, float *y, int k, int nrows);
+
+/* ggml_vec_dot_q4_0_q8_0 / ggml_vec_dot_q4_1_q8_0 == quantize_fns[type].vec_dot_q
+ * (lib/ggml.c:2368-2714): *s = sum over k/32 blocks.  Integer block sums exact; fp32
+ * accumulation order differs from the AVX2 lanes (tolerance in tests/test_gpu_rowfns.py). */
+int fl_vec_dot_q4_q8(int type, int n, float *s, const void *x, const void *y);
+
+/* ggml_compute_forward_mul_mat_q_f32 (lib/ggml.c:7928-8176) on host buffers:
+ * W: M rows of K/32 blocks of `type`, X: N rows of K floats, dst: N rows of M floats.
+ * INIT phase (q8_0 quantisation of X) + COMPUTE phase both run on the GPU. */
+int fl_mul_mat_q_f32(int type, int M, int K, int N, const void *W, const float *X, float *dst);
+
+/* get_rows on a quantized matrix (ggml_compute_forward_get_rows_q, lib/ggml.c:8333-8360) */
+int fl_get_rows_q(int type, int K, int n_ids, const void *W, int n_rows_total, const int32_t *ids, float *dst);
+
+/* ---- (2) device-resident entry points ------------------------------------------------------ */
+void *fl_dev_malloc(size_t bytes);
+int fl_dev_free(void *p);
+int fl_dev_memset(void *p, int value, size_t bytes);
+int fl_h2d(void *dst_dev, const void *src_host, size_t bytes);   /* async on the library stream */
+int fl_d2h(void *dst_host, const void *src_dev, size_t bytes);   /* async; call fl_sync before reading */
+int fl_d2d(void *dst_dev, const void *src_dev, size_t bytes);
+int fl_sync(void);
+void *fl_host_alloc_pinned(size_t bytes);
+int fl_host_free_pinned(void *p);
+
+/* activations -> q8_0 rows.  x row r starts at x + r*x_row_stride_bytes; y rows are packed. */
+int fl_dev_quantize_q8_0(const float *x, size_t x_row_stride_bytes, void *y, int k, int nrows);
+
+/* dst[n*dst_row_stride + m] = vec_dot(W row m, Yq8 row n).  impl: 0 = auto, 1 = plain
+ * warp-per-row LDG kernel, 2 = TMA-bulk-staged persistent matvec (N = 1 only). */
+int fl_dev_mul_mat_q(int type, const void *W, size_t w_row_stride_bytes, int M, int K, const void *Yq8, int N,
+                     float *dst, size_t dst_row_stride_elems, int impl);
+
+int fl_dev_dequantize_rows(int type, const void *W, size_t w_row_stride_bytes, int K, const int32_t *ids_dev,
+                           int n_ids, float *dst, size_t dst_row_stride_elems);
+int fl_dev_quantize_q4(int type, const float *x, void *y, int k, int nrows);
+
+/* Timing helper for bench.py / profiling: runs fl_dev_mul_mat_q `iters` times between two CUDA
+ * events on the library stream and returns the mean milliseconds per launch.  When
+ * flush_l2_bytes > 0 a buffer of that size is overwritten before every timed launch (outside
+ * the event pair) so weights are re-read from HBM. */
+int fl_dev_time_mul_mat_q(int type, const void *W, size_t w_row_stride_bytes, int M, int K, const void *Yq8, int N,
+                          float *dst, size_t dst_row_stride_elems, int impl, int iters, size_t flush_l2_bytes,
+                          float *ms_per_launch);
+
+/* ---- the other ops of the LLaMA eval graph, device-resident ------
+ * fl_view is a strided 4-D view in ggml conventions (reference include/ggml.h:279-309): ne[] are
+ * element counts, nb[] byte strides.  All tensors f32.  Reference implementations cited in
+ * fastllama_b200/csrc/fl_ops_kernels.cu. */
+typedef struct fl_view {
+    void *data;
+    int64_t ne[4];
+    int64_t nb[4];
+} fl_view;
+
+int fl_dev_rms_norm(const fl_view *src, const fl_view *dst);                 /* eps = 1e-6 (lib/ggml.c:7404) */
+int fl_dev_add(const fl_view *a, const fl_view *b, const fl_view *dst);
+int fl_dev_mul(const fl_view *a, const fl_view *b, const fl_view *dst);
+int fl_dev_repeat(const fl_view *src, const fl_view *dst);
+int fl_dev_scale(const fl_view *t, float v);                                /* in place */
+int fl_dev_silu(const fl_view *src, const fl_view *dst);                    /* fp16-table silu (lib/ggml.c:3207-3215) */
+int fl_dev_diag_mask_inf(const fl_view *t, int n_past);                     /* in place */
+int fl_dev_soft_max(const fl_view *t);                                      /* in place, fp16-table exp */
+int fl_dev_rope(const fl_view *t, int n_past, int n_dims, int mode);        /* in place */
+int fl_dev_cpy_f32(const fl_view *src, const fl_view *dst);
+int fl_dev_mul_mat_f32(const fl_view *src0, const fl_view *src1, const fl_view *dst);
+
+/* CUDA events on the library stream (device-side timing for the graph executor and bench.py) */
+void *fl_event_create(void);
+int fl_event_destroy(void *ev);
+int fl_event_record(void *ev);
+int fl_event_sync(void *ev);
+int fl_event_elapsed_ms(void *ev_start, void *ev_stop, float *ms);
+
+/* number of kernels this library has launched since fl_init (bench.py "gpu_launches") */
+uint64_t fl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FL_CUDA_H */
