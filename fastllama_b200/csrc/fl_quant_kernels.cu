@@ -12,6 +12,10 @@
 // block contributes fma(dx*dy, float(sum_i), acc) exactly as in the reference, only the order in
 // which the per-block terms are added in fp32 differs (lane-strided + shuffle tree here, 8 AVX
 // lanes there).
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "fl_common.cuh"
 #include "fl_kernels.h"
 
@@ -209,19 +213,22 @@ k_mul_mat_q_plain(const uint8_t *__restrict__ W, size_t w_row_stride, int M, int
 //   grid  = one CTA per SM; CTA b owns the contiguous row range [M*b/G, M*(b+1)/G) -- a single
 //           contiguous byte range of HBM, so every tile is ONE 1-D bulk copy (UBLKCP), no tensor
 //           map needed, and the per-CTA byte imbalance is at most one row.
-//   smem  = ring of S stages x (R rows x row_bytes); a producer lane keeps all S stages in flight
-//           (mbarrier full/empty pairs), so ~200 KB per SM of HBM reads are outstanding.
-//   warps = kparts x G consumer warps + 1 producer warp.  A consumer warp is bound to one K-slice
-//           ("part", <= 128 blocks) of the row for the whole kernel, so the q8_0 activations of its
-//           slice live in registers in prepared form (no smem/L1 traffic for y at all); it walks the
-//           rows of each tile that belong to its group.  Lanes stride over the slice's blocks:
-//           lane t reads block t, t+32, ... with 5 x LDS.32 (q4_0, stride 5 words: conflict-free)
-//           or 3 x LDS.64 (q4_1, stride 6 words: conflict-free per half-warp).
+//   smem  = the q8_0 activation vector (staged once by a bulk copy) + a ring of S stages x
+//           (R rows x row_bytes).  A producer lane keeps all S stages in flight (mbarrier
+//           full/empty pairs), so ~200 KB per SM of HBM reads are outstanding.
+//   warps = TG tile-groups x G row-groups x kparts K-slices of consumer warps + 1 producer warp.
+//           Tile t is consumed by tile-group t % TG, so several tiles are worked on at once and a
+//           tile can be small (fine-grained ring: data is usable as soon as ~20 KB have landed).
+//           A consumer warp is bound to one K-slice ("part", <= 128 blocks) of the row for the
+//           whole kernel, so the activations of its slice live in registers in prepared form; it
+//           walks the rows of its tiles that belong to its row-group.  Lanes stride over the
+//           slice's blocks: lane t reads block t, t+32, ... with 5 x LDS.32 (q4_0, stride 5 words:
+//           conflict-free) or 3 x LDS.64 (q4_1, stride 6 words: conflict-free per half-warp).
 //   reduce: per-lane sequential fma over its blocks -> 5-step xor-shuffle tree -> (kparts > 1)
 //           fixed-order sum of the parts through smem.  Deterministic.
 // =================================================================================================
 #define FL_RING_NBL 4          // blocks per lane per part (part <= 128 blocks = 4096 weights)
-#define FL_RING_MAX_STAGES 8
+#define FL_RING_MAX_STAGES 16
 #define FL_RING_MAX_PARTS 8
 #define FL_RING_MAX_THREADS 576   // (16 consumer warps + producer) rounded up; 65536/576 = 113 regs/thread
 
@@ -233,22 +240,47 @@ struct fl_ring_params {
     uint32_t row_bytes;
     int R;            // rows per tile
     int S;            // stages
-    int kparts, G;    // consumer warps = kparts * G
+    int kparts, G, TG;   // consumer warps = TG * G * kparts
     int P;            // blocks per part
     uint32_t stage_bytes;
-    uint32_t off_partial, off_stage0;   // dynamic smem layout
+    uint32_t y_bytes;                              // nb * 40, multiple of 16
+    uint32_t off_y, off_partial, off_stage0;       // dynamic smem layout
 };
 
+// one block of one row: weights from smem, activations from registers
 template <int TYPE>
+__device__ __forceinline__ void fl_ring_block(const uint8_t *blk, const fl_yprep &yp, float &acc, float &accm) {
+    uint32_t w[4];
+    float dx;
+    if (TYPE == FL_TYPE_Q4_0) {
+        const uint32_t *bw = (const uint32_t *)blk;
+        dx = __uint_as_float(bw[0]);
+        w[0] = bw[1]; w[1] = bw[2]; w[2] = bw[3]; w[3] = bw[4];
+    } else {
+        const uint2 *bw = (const uint2 *)blk;     // 24-B blocks, 8-B aligned
+        const uint2 dm = bw[0], q01 = bw[1], q23 = bw[2];
+        dx = __uint_as_float(dm.x);
+        accm = __fmaf_rn(__uint_as_float(dm.y), yp.s, accm);
+        w[0] = q01.x; w[1] = q01.y; w[2] = q23.x; w[3] = q23.y;
+    }
+    const int isum = fl_block_isum(w, yp);
+    acc = __fmaf_rn(__fmul_rn(dx, yp.d), (float)isum, acc);
+}
+
+// NFULL = number of leading block slots (of FL_RING_NBL) that are valid for EVERY lane of every
+// part; the remaining slots are lane-predicated.  K = 4096 -> NFULL = 4: no predication at all.
+template <int TYPE, int NFULL>
 __global__ void __launch_bounds__(FL_RING_MAX_THREADS, 1) k_matvec_q4_ring(const fl_ring_params prm) {
     constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bars = (uint64_t *)smem;                       // [0..S) full, [S..2S) empty
+    uint64_t *bars = (uint64_t *)smem;                       // [0..S) full, [S..2S) empty, [2S] activations
+    const fl_block_q8_0 *ysm = (const fl_block_q8_0 *)(smem + prm.off_y);
     float *partial = (float *)(smem + prm.off_partial);      // [S][R][kparts]
     uint8_t *stage0 = smem + prm.off_stage0;
 
-    const int S = prm.S, R = prm.R, kparts = prm.kparts, G = prm.G;
-    const int CW = kparts * G;
+    const int S = prm.S, R = prm.R, kparts = prm.kparts, G = prm.G, TG = prm.TG;
+    const int WPG = kparts * G;                              // warps per tile-group
+    const int CW = WPG * TG;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const int r0 = (int)(((long)prm.M * blockIdx.x) / gridDim.x);
@@ -257,11 +289,13 @@ __global__ void __launch_bounds__(FL_RING_MAX_THREADS, 1) k_matvec_q4_ring(const
     const int ntiles = (nrows + R - 1) / R;
 
     const uint32_t bar0 = fl_smem_u32(bars);
+    const uint32_t bar_y = bar0 + 8u * (2 * S);
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) {
             fl_mbar_init(bar0 + 8u * s, 1);                 // full: producer's expect_tx arrive
-            fl_mbar_init(bar0 + 8u * (S + s), CW);          // empty: one arrive per consumer warp
+            fl_mbar_init(bar0 + 8u * (S + s), WPG);         // empty: one arrive per consuming warp
         }
+        fl_mbar_init(bar_y, 1);
         fl_mbar_fence_init();
     }
     __syncthreads();
@@ -269,40 +303,42 @@ __global__ void __launch_bounds__(FL_RING_MAX_THREADS, 1) k_matvec_q4_ring(const
     if (warp == CW) {
         // ------------------------------ producer ------------------------------
         if (lane == 0) {
+            // activations first (tiny, L2-resident), then the weight stream
+            fl_mbar_expect_tx(bar_y, prm.y_bytes);
+            fl_bulk_g2s(fl_smem_u32(ysm), prm.Y, prm.y_bytes, bar_y);
             const uint64_t pol = fl_policy_evict_first();
             const uint8_t *src = prm.W + (size_t)r0 * prm.row_bytes;
+            int s = 0;
+            uint32_t ph = 1;                                // parity to wait for on the empty barrier
             for (int t = 0; t < ntiles; t++) {
-                const int s = t % S;
-                const uint32_t u = (uint32_t)(t / S);
-                fl_mbar_wait(bar0 + 8u * (S + s), (u & 1u) ^ 1u);
+                fl_mbar_wait(bar0 + 8u * (S + s), ph);
                 const int rows = min(R, nrows - t * R);
                 const uint32_t bytes = (uint32_t)rows * prm.row_bytes;
                 fl_mbar_expect_tx(bar0 + 8u * s, bytes);
-                const uint32_t dsts = fl_smem_u32(stage0 + (size_t)s * prm.stage_bytes);
-                // chunk the tile so several copies are in flight inside the TMA unit
-                const uint32_t CH = 8192;
-                for (uint32_t o = 0; o < bytes; o += CH) {
-                    const uint32_t nbts = min(CH, bytes - o);
-                    fl_bulk_g2s_hint(dsts + o, src + (size_t)t * R * prm.row_bytes + o, nbts, bar0 + 8u * s, pol);
-                }
+                fl_bulk_g2s_hint(fl_smem_u32(stage0 + (size_t)s * prm.stage_bytes), src + (size_t)t * R * prm.row_bytes, bytes,
+                                 bar0 + 8u * s, pol);
+                if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
         return;
     }
 
     // ------------------------------ consumers ------------------------------
-    const int p = warp % kparts, g = warp / kparts;
+    const int tg = warp / WPG;
+    const int wl = warp - tg * WPG;                          // warp index inside the tile-group
+    const int p = wl % kparts, g = wl / kparts;
     const int b0 = p * prm.P;
     const int b1 = min(prm.nb, b0 + prm.P);
 
+    fl_mbar_wait(bar_y, 0);
     fl_yprep yp[FL_RING_NBL];
     bool valid[FL_RING_NBL];
 #pragma unroll
     for (int j = 0; j < FL_RING_NBL; j++) {
         const int ib = b0 + lane + 32 * j;
-        valid[j] = ib < b1;
+        valid[j] = (j < NFULL) || ib < b1;
         if (valid[j]) {
-            fl_prep_y<TYPE>(prm.Y + ib, yp[j]);
+            fl_prep_y<TYPE>(ysm + ib, yp[j]);
         } else {
             yp[j].d = 0.f; yp[j].s = 0.f; yp[j].c = 0;
 #pragma unroll
@@ -310,34 +346,23 @@ __global__ void __launch_bounds__(FL_RING_MAX_THREADS, 1) k_matvec_q4_ring(const
         }
     }
 
-    for (int t = 0; t < ntiles; t++) {
-        const int s = t % S;
-        const uint32_t u = (uint32_t)(t / S);
-        fl_mbar_wait(bar0 + 8u * s, u & 1u);
+    // this warp consumes tiles tg, tg + TG, ...; stage of tile t is t % S, its use count t / S
+    int s = tg % S;
+    uint32_t ph = (uint32_t)(tg / S) & 1u;
+    const int s_step = TG % S, u_step = TG / S;
+    for (int t = tg; t < ntiles; t += TG) {
+        fl_mbar_wait(bar0 + 8u * s, ph);
         const uint8_t *tile = stage0 + (size_t)s * prm.stage_bytes;
         const int rows = min(R, nrows - t * R);
         for (int rr = g; rr < rows; rr += G) {
-            const uint8_t *wrow = tile + (size_t)rr * prm.row_bytes;
+            const uint8_t *wrow = tile + (size_t)rr * prm.row_bytes + (size_t)(b0 + lane) * BB;
             float acc = 0.0f, accm = 0.0f;
 #pragma unroll
             for (int j = 0; j < FL_RING_NBL; j++) {
-                if (valid[j]) {
-                    const uint8_t *blk = wrow + (size_t)(b0 + lane + 32 * j) * BB;
-                    uint32_t w[4];
-                    float dx;
-                    if (TYPE == FL_TYPE_Q4_0) {
-                        const uint32_t *bw = (const uint32_t *)blk;
-                        dx = __uint_as_float(bw[0]);
-                        w[0] = bw[1]; w[1] = bw[2]; w[2] = bw[3]; w[3] = bw[4];
-                    } else {
-                        const uint2 *bw = (const uint2 *)blk;     // 24-B blocks, 8-B aligned
-                        const uint2 dm = bw[0], q01 = bw[1], q23 = bw[2];
-                        dx = __uint_as_float(dm.x);
-                        accm = __fmaf_rn(__uint_as_float(dm.y), yp[j].s, accm);
-                        w[0] = q01.x; w[1] = q01.y; w[2] = q23.x; w[3] = q23.y;
-                    }
-                    const int isum = fl_block_isum(w, yp[j]);
-                    acc = __fmaf_rn(__fmul_rn(dx, yp[j].d), (float)isum, acc);
+                if (j < NFULL) {
+                    fl_ring_block<TYPE>(wrow + (size_t)(32 * j) * BB, yp[j], acc, accm);
+                } else if (valid[j]) {
+                    fl_ring_block<TYPE>(wrow + (size_t)(32 * j) * BB, yp[j], acc, accm);
                 }
             }
             float tot = fl_warp_sum(acc);
@@ -350,15 +375,18 @@ __global__ void __launch_bounds__(FL_RING_MAX_THREADS, 1) k_matvec_q4_ring(const
         __syncwarp();
         if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));      // this warp is done reading stage s
         if (kparts > 1) {
-            // consumers-only barrier (the producer warp never joins barrier 1)
-            asm volatile("bar.sync 1, %0;" ::"r"(CW * 32) : "memory");
-            if ((int)threadIdx.x < rows) {
-                const float *pp = partial + ((size_t)s * R + threadIdx.x) * kparts;
+            // barrier of this tile-group's consumer warps only (ids 1..TG; the producer never joins)
+            asm volatile("bar.sync %0, %1;" ::"r"(tg + 1), "r"(WPG * 32) : "memory");
+            const int tl = (int)threadIdx.x - tg * WPG * 32;
+            if (tl < rows) {
+                const float *pp = partial + ((size_t)s * R + tl) * kparts;
                 float tot = pp[0];
                 for (int q = 1; q < kparts; q++) tot = __fadd_rn(tot, pp[q]);
-                prm.dst[r0 + t * R + threadIdx.x] = tot;
+                prm.dst[r0 + t * R + tl] = tot;
             }
         }
+        s += s_step; ph ^= (uint32_t)(u_step & 1);
+        if (s >= S) { s -= S; ph ^= 1u; }
     }
 }
 
@@ -441,59 +469,91 @@ static int launch_plain(cudaStream_t st, int type, const void *W, size_t wrs, in
 
 // ring configuration for a given shape; returns false when the shape does not qualify
 static bool ring_config(int type, const void *W, size_t wrs, int M, int K, fl_ring_params &p, int &threads,
-                        size_t &smem_bytes) {
+                        size_t &smem_bytes, int &nfull) {
     const int bb = fl_block_bytes(type);
     const int nb = K / FL_QK;
     const size_t row_bytes = (size_t)nb * bb;
     if (wrs != row_bytes) return false;                       // rows must be contiguous (one bulk copy per tile)
     if (row_bytes % 16 != 0 || ((uintptr_t)W & 15) != 0) return false;
+    if (((size_t)nb * 40) % 16 != 0) return false;            // activation vector is bulk-copied too
     const int kparts = (nb + 127) / 128;
     if (kparts > FL_RING_MAX_PARTS) return false;
     if (M < 2 * g_sm_count) return false;                     // too few rows to be worth a persistent grid
     const int P = (nb + kparts - 1) / kparts;
-    // rows per tile: ~40 KB tiles; G row groups so that kparts*G <= 16 consumer warps and every
-    // group owns whole rows of each tile
-    int R = (int)(40960 / row_bytes);
-    if (R < 1) R = 1;
-    if (R > 32) R = 32;
-    int G = 16 / kparts;
-    if (G < 1) G = 1;
-    if (G > R) G = R;
-    R = (R / G) * G;
+    const int last = nb - (kparts - 1) * P;                   // size of the last (smallest) part
+    if (last <= 0) return false;
+    nfull = std::min(P, last) / 32;
+    if (nfull > FL_RING_NBL) nfull = FL_RING_NBL;
+    // 16 consumer warps = TG tile-groups x G row-groups x kparts K-slices; a tile holds G rows (one
+    // per row-group).  Smallest TG in {1,2,4} whose tile fits the target size (fine-grained ring:
+    // data is usable as soon as one tile has landed, and several tiles are consumed concurrently).
+    static int tile_target = -1;
+    if (tile_target < 0) {
+        const char *e = getenv("FASTLLAMA_B200_RING_TILE_KB");
+        tile_target = (e ? atoi(e) : 24) * 1024;
+    }
+    const int Gmax = std::max(1, 16 / kparts);
+    int G = Gmax, TG = 1;
+    for (int tgc = 1; tgc <= 4; tgc *= 2) {
+        const int gc = std::max(1, Gmax / tgc);
+        G = gc; TG = tgc;
+        if ((size_t)gc * row_bytes <= (size_t)tile_target || gc == 1) break;
+    }
+    const int R = G;
     const size_t stage_bytes = (size_t)R * row_bytes;          // multiple of 16
+    const size_t y_bytes = (size_t)nb * 40;
     int S = FL_RING_MAX_STAGES;
-    size_t off = 0;
+    size_t off_y = 0, off_partial = 0, off = 0;
     for (;; S--) {
         if (S < 2) return false;
-        off = 128 + (size_t)S * R * kparts * sizeof(float);     // barriers, then the partial sums
+        off_y = ((size_t)(2 * S + 1) * 8 + 127) & ~(size_t)127;
+        off_partial = (off_y + y_bytes + 127) & ~(size_t)127;
+        off = off_partial + (size_t)S * R * kparts * sizeof(float);
         off = (off + 127) & ~(size_t)127;
         if (off + (size_t)S * stage_bytes <= (size_t)g_smem_optin) break;
     }
-    const int CW = kparts * G;
-    p.M = M; p.nb = nb; p.row_bytes = (uint32_t)row_bytes; p.R = R; p.S = S; p.kparts = kparts; p.G = G; p.P = P;
+    if (TG > S) TG = S;
+    const int CW = kparts * G * TG;
+    p.M = M; p.nb = nb; p.row_bytes = (uint32_t)row_bytes; p.R = R; p.S = S; p.kparts = kparts; p.G = G; p.TG = TG; p.P = P;
     p.stage_bytes = (uint32_t)stage_bytes;
-    p.off_partial = 128;                                        // 16 barriers x 8 B
+    p.y_bytes = (uint32_t)y_bytes;
+    p.off_y = (uint32_t)off_y;
+    p.off_partial = (uint32_t)off_partial;
     p.off_stage0 = (uint32_t)off;
     smem_bytes = off + (size_t)S * stage_bytes;
     threads = (CW + 1) * 32;
     return threads <= FL_RING_MAX_THREADS;
 }
 
-static int launch_ring(cudaStream_t st, int type, fl_ring_params &p, int threads, size_t smem_bytes) {
-    static size_t attr_set[2] = {0, 0};
-    const int ti = (type == FL_TYPE_Q4_0) ? 0 : 1;
-    if (attr_set[ti] < smem_bytes) {
-        if (type == FL_TYPE_Q4_0)
-            FL_CUDA_OK(cudaFuncSetAttribute(k_matvec_q4_ring<FL_TYPE_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
-        else
-            FL_CUDA_OK(cudaFuncSetAttribute(k_matvec_q4_ring<FL_TYPE_Q4_1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
-        attr_set[ti] = (size_t)g_smem_optin;
+typedef void (*ring_kernel_t)(const fl_ring_params);
+static ring_kernel_t ring_kernel(int type, int nfull) {
+    if (type == FL_TYPE_Q4_0) {
+        switch (nfull) {
+            case 4: return k_matvec_q4_ring<FL_TYPE_Q4_0, 4>;
+            case 3: return k_matvec_q4_ring<FL_TYPE_Q4_0, 3>;
+            case 2: return k_matvec_q4_ring<FL_TYPE_Q4_0, 2>;
+            case 1: return k_matvec_q4_ring<FL_TYPE_Q4_0, 1>;
+            default: return k_matvec_q4_ring<FL_TYPE_Q4_0, 0>;
+        }
     }
-    const int grid = g_sm_count;
-    if (type == FL_TYPE_Q4_0)
-        k_matvec_q4_ring<FL_TYPE_Q4_0><<<grid, threads, smem_bytes, st>>>(p);
-    else
-        k_matvec_q4_ring<FL_TYPE_Q4_1><<<grid, threads, smem_bytes, st>>>(p);
+    switch (nfull) {
+        case 4: return k_matvec_q4_ring<FL_TYPE_Q4_1, 4>;
+        case 3: return k_matvec_q4_ring<FL_TYPE_Q4_1, 3>;
+        case 2: return k_matvec_q4_ring<FL_TYPE_Q4_1, 2>;
+        case 1: return k_matvec_q4_ring<FL_TYPE_Q4_1, 1>;
+        default: return k_matvec_q4_ring<FL_TYPE_Q4_1, 0>;
+    }
+}
+
+static int launch_ring(cudaStream_t st, int type, int nfull, fl_ring_params &p, int threads, size_t smem_bytes) {
+    static bool attr_set[2][FL_RING_NBL + 1] = {{false}};
+    const int ti = (type == FL_TYPE_Q4_0) ? 0 : 1;
+    ring_kernel_t kern = ring_kernel(type, nfull);
+    if (!attr_set[ti][nfull]) {
+        FL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+        attr_set[ti][nfull] = true;
+    }
+    kern<<<g_sm_count, threads, smem_bytes, st>>>(p);
     fl_count_launch();
     FL_CUDA_OK(cudaGetLastError());
     return 0;
@@ -508,13 +568,14 @@ int flk_mul_mat_q(cudaStream_t st, int type, const void *W, size_t wrs, int M, i
     fl_ring_params p;
     int threads = 0;
     size_t smem = 0;
-    const bool ring_ok = (N == 1) && ring_config(type, W, wrs, M, K, p, threads, smem);
+    int nfull = 0;
+    const bool ring_ok = (N == 1) && ring_config(type, W, wrs, M, K, p, threads, smem, nfull);
     if (impl == 2) FL_REQUIRE(ring_ok, "mul_mat_q: shape M=%d K=%d N=%d does not qualify for the ring kernel", M, K, N);
     if ((impl == 0 || impl == 2) && ring_ok) {
         p.W = (const uint8_t *)W;
         p.Y = (const fl_block_q8_0 *)Yq8;
         p.dst = dst;
-        return launch_ring(st, type, p, threads, smem);
+        return launch_ring(st, type, nfull, p, threads, smem);
     }
     return launch_plain(st, type, W, wrs, M, K, Yq8, N, dst, drs);
 }

@@ -336,40 +336,113 @@ extern "C" int fl_event_elapsed_ms(void *a, void *b, float *ms) {
     return 0;
 }
 
-__global__ void k_flush_l2(uint4 *p, size_t n16) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
-        p[i] = make_uint4((unsigned)i, 1u, 2u, 3u);
+// L2 "flush" that leaves CLEAN lines behind: reading a buffer larger than L2 evicts the previous
+// working set without creating dirty lines whose write-back would compete with the timed kernel.
+__global__ void k_flush_l2(const uint4 *__restrict__ p, size_t n16, unsigned *sink) {
+    unsigned acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcg(p + i);
+        acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (acc == 0x9e3779b9u) *sink = acc;      // practically never; keeps the loads alive
 }
 
+// Timing helper.  W may hold `n_copies` identical copies of the matrix, `copy_stride_bytes` apart;
+// launch i reads copy i % n_copies, so with n_copies * matrix bytes > L2 every launch streams its
+// weights from HBM exactly as in a decode step (where every matrix is read once per token) and no
+// flush kernel sits between the timed launches.  Events bracket the whole batch of `iters` launches.
 extern "C" int fl_dev_time_mul_mat_q(int type, const void *W, size_t wrs, int M, int K, const void *Yq8, int N,
                                      float *dst, size_t drs, int impl, int iters, size_t flush_l2_bytes,
                                      float *ms_per_launch) {
+    return fl_dev_time_mul_mat_q_rot(type, W, wrs, M, K, Yq8, N, dst, drs, impl, iters, flush_l2_bytes, 0, 1, ms_per_launch);
+}
+
+// plain streaming-read kernel: calibrates what a trivial kernel achieves on the same bytes
+__global__ void __launch_bounds__(512) k_stream_read(const uint4 *__restrict__ p, size_t n16, unsigned *sink) {
+    unsigned acc = 0;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        const uint4 a = __ldcs(p + i), b = __ldcs(p + i + stride), c = __ldcs(p + i + 2 * stride), d = __ldcs(p + i + 3 * stride);
+        acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+    }
+    for (; i < n16; i += stride) {
+        const uint4 a = __ldcs(p + i);
+        acc ^= a.x ^ a.y ^ a.z ^ a.w;
+    }
+    if (acc == 0x9e3779b9u) *sink = acc;
+}
+
+// mode: 0 = eager launches, 1 = the batch is captured into a CUDA graph and the graph launch is
+// timed (no host launch overhead between kernels), 2 = like 1 but with the calibration read kernel
+// over the same byte range instead of the matvec.
+extern "C" int fl_dev_time_mul_mat_q_rot(int type, const void *W, size_t wrs, int M, int K, const void *Yq8, int N,
+                                         float *dst, size_t drs, int impl, int iters, size_t flush_l2_bytes,
+                                         size_t copy_stride_bytes, int n_copies, float *ms_per_launch) {
     FL_NEED_INIT();
-    FL_REQUIRE(iters > 0 && ms_per_launch, "fl_dev_time_mul_mat_q: bad arguments");
+    FL_REQUIRE(iters > 0 && ms_per_launch && n_copies >= 1, "fl_dev_time_mul_mat_q: bad arguments");
+    const int mode = impl >> 8;
+    impl &= 0xFF;
     void *flush = nullptr;
     if (flush_l2_bytes) {
-        if (scratch_get(3, flush_l2_bytes, &flush) != 0) return -1;
+        if (scratch_get(3, flush_l2_bytes + 256, &flush) != 0) return -1;
     }
+    void *sink = nullptr;
+    if (scratch_get(2, 256, &sink) != 0) return -1;
+    const size_t mat_bytes = (size_t)M * wrs;
+    auto launch_all = [&]() -> int {
+        for (int i = 0; i < iters; i++) {
+            const char *Wi = (const char *)W + (size_t)(i % n_copies) * copy_stride_bytes;
+            if (mode == 2) {
+                k_stream_read<<<flk_sm_count() * 4, 512, 0, g.stream>>>((const uint4 *)Wi, mat_bytes / 16, (unsigned *)sink);
+                fl_count_launch();
+            } else {
+                const int rc = flk_mul_mat_q(g.stream, type, Wi, wrs, M, K, Yq8, N, dst, drs, impl);
+                if (rc) return rc;
+            }
+        }
+        return 0;
+    };
     cudaEvent_t e0, e1;
     FL_CUDA_OK(cudaEventCreate(&e0));
     FL_CUDA_OK(cudaEventCreate(&e1));
-    double total = 0.0;
     int rc = 0;
-    for (int i = 0; i < iters && rc == 0; i++) {
-        if (flush) k_flush_l2<<<flk_sm_count() * 8, 256, 0, g.stream>>>((uint4 *)flush, flush_l2_bytes / 16);
+    float ms = 0.f;
+    if (mode == 0) {
+        if (flush) k_flush_l2<<<flk_sm_count() * 8, 256, 0, g.stream>>>((const uint4 *)flush, flush_l2_bytes / 16, (unsigned *)((char *)flush + flush_l2_bytes));
         cudaEventRecord(e0, g.stream);
-        rc = flk_mul_mat_q(g.stream, type, W, wrs, M, K, Yq8, N, dst, drs, impl);
+        rc = launch_all();
         cudaEventRecord(e1, g.stream);
         cudaEventSynchronize(e1);
-        float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        total += ms;
+    } else {
+        // one eager launch first (sets function attributes outside the capture)
+        if (mode != 2) rc = flk_mul_mat_q(g.stream, type, W, wrs, M, K, Yq8, N, dst, drs, impl);
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        if (rc == 0) {
+            FL_CUDA_OK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+            rc = launch_all();
+            cudaError_t ce = cudaStreamEndCapture(g.stream, &graph);
+            if (rc == 0 && ce != cudaSuccess) { fl_set_error("graph capture failed: %s", cudaGetErrorString(ce)); rc = -1; }
+        }
+        if (rc == 0) {
+            FL_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+            FL_CUDA_OK(cudaGraphLaunch(exec, g.stream));          // warm-up pass
+            cudaEventRecord(e0, g.stream);
+            FL_CUDA_OK(cudaGraphLaunch(exec, g.stream));
+            cudaEventRecord(e1, g.stream);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (rc != 0) return rc;
     FL_CUDA_OK(cudaGetLastError());
-    *ms_per_launch = (float)(total / iters);
+    *ms_per_launch = ms / iters;
     return 0;
 }
 

@@ -61,6 +61,7 @@ SIGNATURES = {
     "fl_dev_dequantize_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "fl_dev_quantize_q4": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "fl_dev_time_mul_mat_q": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_float)]),
+    "fl_dev_time_mul_mat_q_rot": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_float)]),
     "fl_dev_rms_norm": (C.c_int, [_VP, _VP]),
     "fl_dev_add": (C.c_int, [_VP, _VP, _VP]),
     "fl_dev_mul": (C.c_int, [_VP, _VP, _VP]),

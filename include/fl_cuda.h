@@ -94,13 +94,17 @@ int fl_dev_dequantize_rows(int type, const void *W, size_t w_row_stride_bytes, i
                            int n_ids, float *dst, size_t dst_row_stride_elems);
 int fl_dev_quantize_q4(int type, const float *x, void *y, int k, int nrows);
 
-/* Timing helper for bench.py / profiling: runs fl_dev_mul_mat_q `iters` times between two CUDA
- * events on the library stream and returns the mean milliseconds per launch.  When
- * flush_l2_bytes > 0 a buffer of that size is overwritten before every timed launch (outside
- * the event pair) so weights are re-read from HBM. */
+/* Timing helpers for bench.py / profiling (CUDA events on the library stream, mean ms per launch
+ * over `iters` back-to-back launches).  W may hold n_copies identical copies of the matrix,
+ * copy_stride_bytes apart; launch i reads copy i % n_copies, so with n_copies * bytes > L2 every
+ * launch streams its weights from HBM, as in a decode step where each matrix is read once per token.
+ * flush_l2_bytes > 0: a buffer of that size is READ once before the timed batch (clean eviction). */
 int fl_dev_time_mul_mat_q(int type, const void *W, size_t w_row_stride_bytes, int M, int K, const void *Yq8, int N,
                           float *dst, size_t dst_row_stride_elems, int impl, int iters, size_t flush_l2_bytes,
                           float *ms_per_launch);
+int fl_dev_time_mul_mat_q_rot(int type, const void *W, size_t w_row_stride_bytes, int M, int K, const void *Yq8, int N,
+                              float *dst, size_t dst_row_stride_elems, int impl, int iters, size_t flush_l2_bytes,
+                              size_t copy_stride_bytes, int n_copies, float *ms_per_launch);
 
 /* ---- the other ops of the LLaMA eval graph, device-resident ------
  * fl_view is a strided 4-D view in ggml conventions (reference include/ggml.h:279-309): ne[] are
