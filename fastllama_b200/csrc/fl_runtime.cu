@@ -336,6 +336,36 @@ extern "C" int fl_event_elapsed_ms(void *a, void *b, float *ms) {
     return 0;
 }
 
+// Counter-based Gaussian fill for synthetic model files (tools only): element i depends on (seed, i)
+// alone, so the file contents are reproducible on any grid.  splitmix64 -> two uniforms -> Box-Muller.
+__device__ __forceinline__ uint64_t fl_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void k_fill_normal(float *__restrict__ p, size_t n, uint64_t seed, float std) {
+    const size_t npairs = (n + 1) / 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t h = fl_splitmix64(seed * 0xD1B54A32D192ED03ull + i);
+        const float u1 = ((float)(uint32_t)(h >> 40) + 1.0f) * (1.0f / 16777217.0f);     // (0, 1)
+        const float u2 = (float)(uint32_t)((h >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);  // [0, 1)
+        const float r = sqrtf(-2.0f * logf(u1)) * std;
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        p[2 * i] = r * cs;
+        if (2 * i + 1 < n) p[2 * i + 1] = r * sn;
+    }
+}
+extern "C" int fl_dev_fill_normal(float *p, size_t n, uint64_t seed, float std) {
+    FL_NEED_INIT();
+    if (n == 0) return 0;
+    k_fill_normal<<<flk_sm_count() * 8, 256, 0, g.stream>>>(p, n, seed, std);
+    fl_count_launch();
+    FL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // L2 "flush" that leaves CLEAN lines behind: reading a buffer larger than L2 evicts the previous
 // working set without creating dirty lines whose write-back would compete with the timed kernel.
 __global__ void k_flush_l2(const uint4 *__restrict__ p, size_t n16, unsigned *sink) {

@@ -141,6 +141,7 @@ struct ggml_context {
     int n_objects;
     ggml_object *first, *last;
     ggml_scratch scratch, scratch_save;
+    int mirror_id;            // index of this arena's device mirror record
 };
 namespace {
 struct Slot { bool used; ggml_context ctx; };
@@ -149,6 +150,7 @@ Slot g_slots[GGML_MAX_CONTEXTS];
 static void mirrors_on_ctx_init(ggml_context *ctx);
 static void mirrors_on_ctx_free(ggml_context *ctx);
 static void mirrors_on_scratch(void *data, size_t size);
+static void mirrors_note_alloc(ggml_context *ctx, size_t end);
 
 extern "C" struct ggml_context *ggml_init(struct ggml_init_params params) {
     for (auto &slot : g_slots) {
@@ -226,6 +228,7 @@ static ggml_tensor *new_tensor_impl(ggml_context *ctx, ggml_type type, int n_dim
     if (ctx->last) ctx->last->next = obj; else ctx->first = obj;
     ctx->last = obj;
     ctx->n_objects++;
+    mirrors_note_alloc(ctx, obj->offs + obj->size);
 
     ggml_tensor *t = (ggml_tensor *)(ctx->mem_buffer + obj->offs);
     memset(t, 0, sizeof(*t));
@@ -561,15 +564,21 @@ extern "C" struct ggml_cgraph ggml_build_forward(struct ggml_tensor *tensor) {
 // ================================================================================================
 namespace {
 enum MirrorKind { MK_ARENA = 0, MK_EXTERNAL = 1, MK_SCRATCH = 2 };
+// The reference wraps every ggml_context in an RAII type whose defaulted move leaves the pointer in
+// the moved-from temporary, so contexts are "freed" right after they are created and their pool
+// slots are re-used (reference include/tensor/mem_context.hpp:31-43) -- harmless there because
+// ggml_free only releases the slot.  Mirrors are therefore keyed by the ARENA (host range), never
+// by context identity or lifetime; how far an arena has been filled is recorded by the allocator.
 struct Mirror {
     const char *host;        // arena base
     size_t size;
     char *dev;               // equally sized device allocation (lazy)
-    ggml_context *ctx;       // live context owning the arena, or nullptr (freed / not an arena)
+    size_t alloc_end;        // bytes of the arena handed out by the bump allocator so far
     size_t uploaded;         // bytes [0, uploaded) of a persistent arena already copied to the device
     int kind;                // MK_ARENA: a ggml context buffer; MK_EXTERNAL: a bare tensor range that is
                              // not a ggml arena (mmap'ed weights), uploaded once; MK_SCRATCH: a
                              // ggml_set_scratch buffer (activations only, never uploaded)
+    bool alive;
 };
 std::vector<Mirror> g_mirrors;
 int g_last_mirror = -1;
@@ -596,11 +605,11 @@ int find_mirror(const void *p) {
     const char *c = (const char *)p;
     if (g_last_mirror >= 0 && g_last_mirror < (int)g_mirrors.size()) {
         const Mirror &m = g_mirrors[g_last_mirror];
-        if (c >= m.host && c < m.host + m.size) return g_last_mirror;
+        if (m.alive && c >= m.host && c < m.host + m.size) return g_last_mirror;
     }
     for (int i = 0; i < (int)g_mirrors.size(); i++) {
         const Mirror &m = g_mirrors[i];
-        if (c >= m.host && c < m.host + m.size) return g_last_mirror = i;
+        if (m.alive && c >= m.host && c < m.host + m.size) return g_last_mirror = i;
     }
     return -1;
 }
@@ -618,33 +627,42 @@ Mirror &mirror_alloc(Mirror &m) {
 
 static void mirrors_on_ctx_init(ggml_context *ctx) {
     // an arena re-created over the same buffer (Model::eval does this every call) re-uses its mirror
-    for (auto it = g_mirrors.begin(); it != g_mirrors.end();) {
-        const bool same = it->host == ctx->mem_buffer && it->size == ctx->mem_size;
-        const bool overlap = it->host < ctx->mem_buffer + ctx->mem_size && ctx->mem_buffer < it->host + it->size;
-        if (same) { it->ctx = ctx; it->uploaded = 0; return; }
-        if (overlap && it->ctx == nullptr) { drop_mirror(*it); it = g_mirrors.erase(it); g_last_mirror = -1; continue; }
-        ++it;
+    int found = -1;
+    for (int i = 0; i < (int)g_mirrors.size(); i++) {
+        Mirror &m = g_mirrors[i];
+        if (!m.alive) continue;
+        const bool same = m.host == ctx->mem_buffer && m.size == ctx->mem_size;
+        const bool overlap = m.host < ctx->mem_buffer + ctx->mem_size && ctx->mem_buffer < m.host + m.size;
+        if (same) { found = i; m.alloc_end = 0; m.uploaded = 0; m.kind = MK_ARENA; }
+        else if (overlap) { drop_mirror(m); m.alive = false; }      // the buffer was re-allocated
     }
-    g_mirrors.push_back(Mirror{ctx->mem_buffer, ctx->mem_size, nullptr, ctx, 0, MK_ARENA});
+    if (found < 0) {
+        g_mirrors.push_back(Mirror{ctx->mem_buffer, ctx->mem_size, nullptr, 0, 0, MK_ARENA, true});
+        found = (int)g_mirrors.size() - 1;
+    }
+    ctx->mirror_id = found;
+    g_last_mirror = -1;
+}
+static void mirrors_on_ctx_free(ggml_context *) {}   // the arena (and its device mirror) outlives the context slot
+static void mirrors_note_alloc(ggml_context *ctx, size_t end) {
+    Mirror &m = g_mirrors[ctx->mirror_id];
+    if (m.alive && m.host == ctx->mem_buffer && end > m.alloc_end) m.alloc_end = end;
 }
 static void mirrors_on_scratch(void *data, size_t size) {
     for (auto &m : g_mirrors)
-        if (m.host == (const char *)data && m.size == size) return;
-    g_mirrors.push_back(Mirror{(const char *)data, size, nullptr, nullptr, 0, MK_SCRATCH});
-}
-static void mirrors_on_ctx_free(ggml_context *ctx) {
-    for (auto &m : g_mirrors)
-        if (m.ctx == ctx) m.ctx = nullptr;          // keep the device allocation for the next ggml_init over this buffer
+        if (m.alive && m.host == (const char *)data && m.size == size) return;
+    g_mirrors.push_back(Mirror{(const char *)data, size, nullptr, 0, 0, MK_SCRATCH, true});
 }
 
 // host pointer -> device pointer.  `compute_ctx` is the arena of the graph being run: nothing in it
-// is uploaded here (its leafs are handled per graph); every other arena is persistent and is
-// uploaded once, incrementally as it fills.
+// is uploaded here (its leafs are handled per graph).  Every other arena is persistent (weights, KV
+// cache): whatever the allocator has handed out beyond the already-uploaded prefix is copied once;
+// lower addresses are never re-copied, so data the device has written there (KV cache) is safe.
 static char *dev_ptr(const void *host, size_t nbytes, const ggml_context *compute_ctx) {
     int i = find_mirror(host);
     if (i < 0) {
         // not inside any ggml arena: the tensor's data points at foreign memory (mmap'ed weights)
-        g_mirrors.push_back(Mirror{(const char *)host, nbytes, nullptr, nullptr, 0, MK_EXTERNAL});
+        g_mirrors.push_back(Mirror{(const char *)host, nbytes, nullptr, 0, 0, MK_EXTERNAL, true});
         i = (int)g_mirrors.size() - 1;
     }
     Mirror &m = mirror_alloc(g_mirrors[i]);
@@ -653,7 +671,7 @@ static char *dev_ptr(const void *host, size_t nbytes, const ggml_context *comput
         B200_FAIL("tensor at %p (+%zu) straddles the end of a registered range %p (+%zu)", host, nbytes, (const void *)m.host, m.size);
     size_t want = 0;
     if (m.kind == MK_EXTERNAL) want = m.size;
-    else if (m.kind == MK_ARENA && m.ctx != compute_ctx) want = std::min(m.size, std::max(off + nbytes, m.ctx ? ggml_used_mem(m.ctx) : (size_t)0));
+    else if (m.kind == MK_ARENA && !(compute_ctx && m.host == compute_ctx->mem_buffer)) want = std::min(m.size, m.alloc_end);
     if (want > m.uploaded) {
         if (g_verbose) fprintf(stderr, "[ggml_b200] upload %p [%zu, %zu) -> device\n", (const void *)m.host, m.uploaded, want);
         FLC(fl_h2d(m.dev + m.uploaded, m.host + m.uploaded, want - m.uploaded));
@@ -681,9 +699,11 @@ extern "C" void ggml_b200_sync_to_host(const void *ptr, size_t size) {
 }
 extern "C" void ggml_b200_release_all(void) {
     if (fl_is_initialized()) fl_sync();
-    for (auto &m : g_mirrors) drop_mirror(m);
-    g_mirrors.erase(std::remove_if(g_mirrors.begin(), g_mirrors.end(), [](const Mirror &m) { return m.ctx == nullptr; }), g_mirrors.end());
-    for (auto &m : g_mirrors) m.uploaded = 0;
+    for (auto &m : g_mirrors) {
+        drop_mirror(m);
+        m.uploaded = 0;
+        if (m.kind != MK_ARENA) m.alive = false;
+    }
     g_last_mirror = -1;
 }
 extern "C" void ggml_b200_get_stats(struct ggml_b200_stats *out) {

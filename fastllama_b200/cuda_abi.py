@@ -73,6 +73,7 @@ SIGNATURES = {
     "fl_dev_rope": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int]),
     "fl_dev_cpy_f32": (C.c_int, [_VP, _VP]),
     "fl_dev_mul_mat_f32": (C.c_int, [_VP, _VP, _VP]),
+    "fl_dev_fill_normal": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_float]),
     "fl_event_create": (C.c_void_p, []),
     "fl_event_destroy": (C.c_int, [C.c_void_p]),
     "fl_event_record": (C.c_int, [C.c_void_p]),

@@ -128,6 +128,10 @@ int fl_dev_rope(const fl_view *t, int n_past, int n_dims, int mode);        /* i
 int fl_dev_cpy_f32(const fl_view *src, const fl_view *dst);
 int fl_dev_mul_mat_f32(const fl_view *src0, const fl_view *src1, const fl_view *dst);
 
+/* Tooling: counter-based N(0, std^2) fill (element i depends on (seed, i) only) used to create
+ * synthetic model files on the device; not part of the hot path. */
+int fl_dev_fill_normal(float *p_dev, size_t n, uint64_t seed, float std);
+
 /* CUDA events on the library stream (device-side timing for the graph executor and bench.py) */
 void *fl_event_create(void);
 int fl_event_destroy(void *ev);

@@ -1,0 +1,207 @@
+/*
+ * mock_fl_cuda.c -- TEST-ONLY stand-in for libfl_cuda.so that runs on the CPU.
+ *
+ * Purpose: exercise the HOST logic of libggml_b200 / the drop-in pyfastllama.so (arena mirrors,
+ * upload policy, graph walking, output copy-back) in the GPU-less build container.  "Device" memory
+ * is malloc'ed host memory kept strictly separate from the caller's arenas, so a missing upload or
+ * copy-back shows up exactly as it would on the GPU.  It is never shipped, never loaded by the
+ * product (tests copy libggml_b200.so next to it so that $ORIGIN resolves here), and its arithmetic
+ * comes from the oracle (oracle/q4_oracle.c) plus plain scalar loops.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fl_cuda.h"
+
+/* oracle (linked in) */
+void orc_quantize_row_q8_0(const float *x, void *vy, int k);
+void orc_quantize_row_q4_0(const float *x, void *vy, int k);
+void orc_quantize_row_q4_1(const float *x, void *vy, int k);
+void orc_dequantize_row_q4_0(const void *vx, float *y, int k);
+void orc_dequantize_row_q4_1(const void *vx, float *y, int k);
+void orc_vec_dot_q4_0_q8_0(int n, float *s, const void *vx, const void *vy);
+void orc_vec_dot_q4_1_q8_0(int n, float *s, const void *vx, const void *vy);
+
+static int g_ready = 0;
+static uint64_t g_launches = 0;
+static char g_err[256] = "";
+static uint16_t tab_silu[1 << 16], tab_exp[1 << 16];
+
+static float h2f(uint16_t h) {
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1F, m = h & 0x3FF, bits;
+    if (e == 0) {
+        if (!m) bits = sign;
+        else { int k = -1; do { k++; m <<= 1; } while (!(m & 0x400)); bits = sign | ((uint32_t)(127 - 15 - k) << 23) | ((m & 0x3FF) << 13); }
+    } else if (e == 31) bits = sign | 0x7F800000u | (m << 13);
+    else bits = sign | ((e + 112) << 23) | (m << 13);
+    float f; memcpy(&f, &bits, 4); return f;
+}
+#include <immintrin.h>
+static uint16_t f2h(float f) { return (uint16_t)_cvtss_sh(f, 0); }
+
+int fl_init(int device) {
+    (void)device;
+    if (!g_ready) {
+        for (int i = 0; i < (1 << 16); i++) {
+            float f = h2f((uint16_t)i);
+            tab_silu[i] = f2h(f / (1.0f + expf(-f)));
+            tab_exp[i] = f2h(expf(f));
+        }
+        g_ready = 1;
+    }
+    return 0;
+}
+void fl_shutdown(void) { g_ready = 0; }
+int fl_is_initialized(void) { return g_ready; }
+const char *fl_last_error(void) { return g_err; }
+int fl_device_props(char *name, int n, int *sm, size_t *hbm, int *maj, int *mnr) {
+    if (name && n > 0) snprintf(name, (size_t)n, "mock-cpu");
+    if (sm) *sm = 1; if (hbm) *hbm = 0; if (maj) *maj = 0; if (mnr) *mnr = 0;
+    return 0;
+}
+void *fl_stream(void) { return NULL; }
+uint64_t fl_launch_count(void) { return g_launches; }
+void *fl_dev_malloc(size_t b) { void *p = malloc(b ? b : 1); if (p) memset(p, 0xA5, b); return p; }   /* poison */
+int fl_dev_free(void *p) { free(p); return 0; }
+int fl_dev_memset(void *p, int v, size_t b) { memset(p, v, b); return 0; }
+int fl_h2d(void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
+int fl_d2h(void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
+int fl_d2d(void *d, const void *s, size_t b) { memmove(d, s, b); return 0; }
+int fl_sync(void) { return 0; }
+void *fl_host_alloc_pinned(size_t b) { return malloc(b ? b : 1); }
+int fl_host_free_pinned(void *p) { free(p); return 0; }
+void *fl_event_create(void) { return malloc(8); }
+int fl_event_destroy(void *e) { free(e); return 0; }
+int fl_event_record(void *e) { (void)e; return 0; }
+int fl_event_sync(void *e) { (void)e; return 0; }
+int fl_event_elapsed_ms(void *a, void *b, float *ms) { (void)a; (void)b; *ms = 0.f; return 0; }
+int fl_dev_fill_normal(float *p, size_t n, uint64_t seed, float std) { (void)seed; for (size_t i = 0; i < n; i++) p[i] = std * (float)((i * 2654435761u) % 1000) / 1000.f; return 0; }
+
+int fl_dev_quantize_q8_0(const float *x, size_t stride, void *y, int k, int nrows) {
+    g_launches++;
+    for (int r = 0; r < nrows; r++) orc_quantize_row_q8_0((const float *)((const char *)x + r * stride), (char *)y + (size_t)r * (k / 32) * 40, k);
+    return 0;
+}
+int fl_dev_quantize_q4(int type, const float *x, void *y, int k, int nrows) {
+    g_launches++;
+    const int bb = type == 2 ? 20 : 24;
+    for (int r = 0; r < nrows; r++) {
+        if (type == 2) orc_quantize_row_q4_0(x + (size_t)r * k, (char *)y + (size_t)r * (k / 32) * bb, k);
+        else orc_quantize_row_q4_1(x + (size_t)r * k, (char *)y + (size_t)r * (k / 32) * bb, k);
+    }
+    return 0;
+}
+int fl_dev_mul_mat_q(int type, const void *W, size_t wrs, int M, int K, const void *Y, int N, float *dst, size_t drs, int impl) {
+    (void)impl; g_launches++;
+    for (int n = 0; n < N; n++)
+        for (int m = 0; m < M; m++) {
+            float *o = dst + (size_t)n * drs + m;
+            const void *wr = (const char *)W + (size_t)m * wrs, *yr = (const char *)Y + (size_t)n * (K / 32) * 40;
+            if (type == 2) orc_vec_dot_q4_0_q8_0(K, o, wr, yr); else orc_vec_dot_q4_1_q8_0(K, o, wr, yr);
+        }
+    return 0;
+}
+int fl_dev_dequantize_rows(int type, const void *W, size_t wrs, int K, const int32_t *ids, int n, float *dst, size_t drs) {
+    g_launches++;
+    for (int i = 0; i < n; i++) {
+        const void *wr = (const char *)W + (size_t)(ids ? ids[i] : i) * wrs;
+        if (type == 2) orc_dequantize_row_q4_0(wr, dst + (size_t)i * drs, K); else orc_dequantize_row_q4_1(wr, dst + (size_t)i * drs, K);
+    }
+    return 0;
+}
+int fl_dev_time_mul_mat_q(int t, const void *W, size_t a, int M, int K, const void *Y, int N, float *d, size_t b, int i, int it, size_t f, float *ms) {
+    (void)t; (void)W; (void)a; (void)M; (void)K; (void)Y; (void)N; (void)d; (void)b; (void)i; (void)it; (void)f; *ms = 0; return 0;
+}
+int fl_dev_time_mul_mat_q_rot(int t, const void *W, size_t a, int M, int K, const void *Y, int N, float *d, size_t b, int i, int it, size_t f, size_t cs, int nc, float *ms) {
+    (void)t; (void)W; (void)a; (void)M; (void)K; (void)Y; (void)N; (void)d; (void)b; (void)i; (void)it; (void)f; (void)cs; (void)nc; *ms = 0; return 0;
+}
+
+/* host-buffer entry points */
+int fl_quantize_rows_q8_0(const float *x, void *y, int k, int n) { return fl_dev_quantize_q8_0(x, (size_t)k * 4, y, k, n); }
+int fl_quantize_row_q8_0(const float *x, void *y, int k) { return fl_quantize_rows_q8_0(x, y, k, 1); }
+int fl_quantize_rows_q4(int t, const float *x, void *y, int k, int n) { return fl_dev_quantize_q4(t, x, y, k, n); }
+int fl_dequantize_rows_q4(int t, const void *x, float *y, int k, int n) { return fl_dev_dequantize_rows(t, x, (size_t)(k / 32) * (t == 2 ? 20 : 24), k, NULL, n, y, (size_t)k); }
+int fl_vec_dot_q4_q8(int t, int n, float *s, const void *x, const void *y) { if (t == 2) orc_vec_dot_q4_0_q8_0(n, s, x, y); else orc_vec_dot_q4_1_q8_0(n, s, x, y); return 0; }
+int fl_mul_mat_q_f32(int t, int M, int K, int N, const void *W, const float *X, float *dst) {
+    void *q = malloc((size_t)(K / 32) * 40 * (size_t)(N ? N : 1));
+    fl_dev_quantize_q8_0(X, (size_t)K * 4, q, K, N);
+    fl_dev_mul_mat_q(t, W, (size_t)(K / 32) * (t == 2 ? 20 : 24), M, K, q, N, dst, (size_t)M, 0);
+    free(q);
+    return 0;
+}
+int fl_get_rows_q(int t, int K, int n, const void *W, int total, const int32_t *ids, float *dst) { (void)total; return fl_dev_dequantize_rows(t, W, (size_t)(K / 32) * (t == 2 ? 20 : 24), K, ids, n, dst, (size_t)K); }
+
+/* ---- strided ops ------------------------------------------------------------------------------ */
+static inline char *at(const fl_view *v, int64_t i0, int64_t i1, int64_t i2, int64_t i3) {
+    return (char *)v->data + i0 * v->nb[0] + i1 * v->nb[1] + i2 * v->nb[2] + i3 * v->nb[3];
+}
+static inline char *lin(const fl_view *v, int64_t n) {
+    int64_t i0 = n % v->ne[0]; n /= v->ne[0];
+    int64_t i1 = n % v->ne[1]; n /= v->ne[1];
+    int64_t i2 = n % v->ne[2]; int64_t i3 = n / v->ne[2];
+    return at(v, i0, i1, i2, i3);
+}
+static inline int64_t nel(const fl_view *v) { return v->ne[0] * v->ne[1] * v->ne[2] * v->ne[3]; }
+
+int fl_dev_rms_norm(const fl_view *s, const fl_view *d) {
+    g_launches++;
+    for (int64_t i3 = 0; i3 < s->ne[3]; i3++) for (int64_t i2 = 0; i2 < s->ne[2]; i2++) for (int64_t i1 = 0; i1 < s->ne[1]; i1++) {
+        const float *x = (const float *)at(s, 0, i1, i2, i3); float *y = (float *)at(d, 0, i1, i2, i3);
+        double sum = 0; for (int64_t i = 0; i < s->ne[0]; i++) sum += (double)(x[i] * x[i]);
+        float mean = (float)(sum / (double)s->ne[0]); float sc = 1.0f / sqrtf(mean + 1e-6f);
+        for (int64_t i = 0; i < s->ne[0]; i++) y[i] = x[i] * sc;
+    }
+    return 0;
+}
+int fl_dev_add(const fl_view *a, const fl_view *b, const fl_view *d) { g_launches++; for (int64_t i = 0; i < nel(d); i++) *(float *)lin(d, i) = *(float *)lin(a, i) + *(float *)lin(b, i); return 0; }
+int fl_dev_mul(const fl_view *a, const fl_view *b, const fl_view *d) { g_launches++; for (int64_t i = 0; i < nel(d); i++) *(float *)lin(d, i) = *(float *)lin(a, i) * *(float *)lin(b, i); return 0; }
+int fl_dev_repeat(const fl_view *s, const fl_view *d) {
+    g_launches++;
+    for (int64_t i3 = 0; i3 < d->ne[3]; i3++) for (int64_t i2 = 0; i2 < d->ne[2]; i2++) for (int64_t i1 = 0; i1 < d->ne[1]; i1++) for (int64_t i0 = 0; i0 < d->ne[0]; i0++)
+        *(float *)at(d, i0, i1, i2, i3) = *(float *)at(s, i0 % s->ne[0], i1 % s->ne[1], i2 % s->ne[2], i3 % s->ne[3]);
+    return 0;
+}
+int fl_dev_scale(const fl_view *t, float v) { g_launches++; for (int64_t i = 0; i < nel(t); i++) *(float *)lin(t, i) *= v; return 0; }
+int fl_dev_silu(const fl_view *s, const fl_view *d) { g_launches++; for (int64_t i = 0; i < nel(d); i++) *(float *)lin(d, i) = h2f(tab_silu[f2h(*(float *)lin(s, i))]); return 0; }
+int fl_dev_diag_mask_inf(const fl_view *t, int n_past) {
+    g_launches++;
+    for (int64_t k = 0; k < t->ne[2] * t->ne[3]; k++) for (int64_t j = 0; j < t->ne[1]; j++) for (int64_t i = n_past; i < t->ne[0]; i++)
+        if (i > n_past + j) *(float *)((char *)t->data + k * t->nb[2] + j * t->nb[1] + i * t->nb[0]) = -INFINITY;
+    return 0;
+}
+int fl_dev_soft_max(const fl_view *t) {
+    g_launches++;
+    for (int64_t r = 0; r < t->ne[1] * t->ne[2] * t->ne[3]; r++) {
+        float *p = (float *)((char *)t->data + r * t->nb[1]); float mx = -INFINITY; double sum = 0;
+        for (int64_t i = 0; i < t->ne[0]; i++) if (p[i] > mx) mx = p[i];
+        for (int64_t i = 0; i < t->ne[0]; i++) { if (p[i] == -INFINITY) p[i] = 0; else { float v = h2f(tab_exp[f2h(p[i] - mx)]); sum += v; p[i] = v; } }
+        float inv = (float)(1.0 / sum); for (int64_t i = 0; i < t->ne[0]; i++) p[i] *= inv;
+    }
+    return 0;
+}
+int fl_dev_rope(const fl_view *t, int n_past, int n_dims, int mode) {
+    g_launches++;
+    const float ts = powf(10000.0f, -2.0f / n_dims);
+    for (int64_t i3 = 0; i3 < t->ne[3]; i3++) for (int64_t i2 = ((mode & 1) ? n_past : 0); i2 < t->ne[2]; i2++) for (int64_t i1 = 0; i1 < t->ne[1]; i1++) {
+        float theta = (float)((mode & 1) ? i2 : n_past + i2);
+        for (int i0 = 0; i0 < n_dims; i0 += 2) {
+            float c = cosf(theta), s = sinf(theta); theta *= ts;
+            float *p0 = (float *)at(t, (mode & 2) ? i0 / 2 : i0, i1, i2, i3), *p1 = (float *)at(t, (mode & 2) ? i0 / 2 + n_dims / 2 : i0 + 1, i1, i2, i3);
+            float x0 = *p0, x1 = *p1; *p0 = x0 * c - x1 * s; *p1 = x0 * s + x1 * c;
+        }
+    }
+    return 0;
+}
+int fl_dev_cpy_f32(const fl_view *s, const fl_view *d) { g_launches++; for (int64_t i = 0; i < nel(s); i++) *(float *)lin(d, i) = *(float *)lin(s, i); return 0; }
+int fl_dev_mul_mat_f32(const fl_view *a, const fl_view *b, const fl_view *d) {
+    g_launches++;
+    for (int64_t i3 = 0; i3 < d->ne[3]; i3++) for (int64_t i2 = 0; i2 < d->ne[2]; i2++) for (int64_t i1 = 0; i1 < d->ne[1]; i1++) for (int64_t i0 = 0; i0 < d->ne[0]; i0++) {
+        const float *x = (const float *)at(a, 0, i0, i2, i3), *y = (const float *)at(b, 0, i1, i2, i3); float acc = 0;
+        for (int64_t k = 0; k < a->ne[0]; k++) acc += x[k] * y[k];
+        *(float *)at(d, i0, i1, i2, i3) = acc;
+    }
+    return 0;
+}
