@@ -585,6 +585,9 @@ int g_last_mirror = -1;
 bool g_verbose = false;
 
 struct Stats { uint64_t n_evals = 0; double last_us = 0, total_us = 0; uint64_t graph_replays = 0; } g_stats;
+bool g_profile = false;
+std::vector<ggml_b200_kernel_stat> g_kstats;
+void *g_pev0 = nullptr, *g_pev1 = nullptr;
 
 void ensure_backend() {
     static bool done = false;
@@ -706,6 +709,17 @@ extern "C" void ggml_b200_release_all(void) {
     }
     g_last_mirror = -1;
 }
+extern "C" void ggml_b200_set_profile(int on) {
+    ensure_backend();
+    if (!g_pev0) { g_pev0 = fl_event_create(); g_pev1 = fl_event_create(); }
+    g_profile = on != 0;
+    if (on) g_kstats.clear();
+}
+extern "C" int ggml_b200_get_kernel_stats(struct ggml_b200_kernel_stat *out, int max_entries) {
+    const int n = std::min((int)g_kstats.size(), max_entries);
+    for (int i = 0; i < n; i++) out[i] = g_kstats[i];
+    return n;
+}
 extern "C" void ggml_b200_get_stats(struct ggml_b200_stats *out) {
     out->n_evals = g_stats.n_evals;
     out->last_eval_device_us = g_stats.last_us;
@@ -764,7 +778,23 @@ void exec_mul_mat(const ggml_tensor *node, const ggml_context *cctx) {
     // INIT phase: src1 rows -> q8_0 (reference lib/ggml.c:8105-8119)
     FLC(fl_dev_quantize_q8_0(X, b->nb[1], g_exec.q8_work, K, N));
     // COMPUTE phase (reference lib/ggml.c:8125-8163)
+    if (g_profile) FLC(fl_event_record(g_pev0));
     FLC(fl_dev_mul_mat_q((int)a->type, W, a->nb[1], M, K, g_exec.q8_work, N, D, node->nb[1] / sizeof(float), 0));
+    if (g_profile) {
+        FLC(fl_event_record(g_pev1));
+        FLC(fl_event_sync(g_pev1));
+        float ms = 0.f;
+        FLC(fl_event_elapsed_ms(g_pev0, g_pev1, &ms));
+        ggml_b200_kernel_stat *e = nullptr;
+        for (auto &k : g_kstats) if (k.type == (int)a->type && k.M == M && k.K == K && k.N == N) e = &k;
+        if (!e) {
+            g_kstats.push_back(ggml_b200_kernel_stat{(int)a->type, M, K, N, 0, 0.0,
+                                                     (double)M * (K / 32) * (double)k_tsize[a->type] + (double)(K / 32) * 40.0 * N + 4.0 * M * N});
+            e = &g_kstats.back();
+        }
+        e->launches++;
+        e->total_ms += ms;
+    }
 }
 
 void exec_node(ggml_tensor *node, const ggml_context *cctx) {

@@ -20,7 +20,7 @@ FTYPE = {Q4_0: 2, Q4_1: 3}
 BLOCK_BYTES = {Q4_0: 20, Q4_1: 24}
 
 LLAMA_SIZES = {     # n_embd, n_head, n_layer (n_mult 256, n_vocab 32000); reference lib/llama.cpp:129-139
-    "7B": (4096, 32, 32), "13B": (5120, 40, 40), "30B": (6656, 52, 60), "65B": (8192, 64, 80),
+    "toy": (256, 4, 2), "7B": (4096, 32, 32), "13B": (5120, 40, 40), "30B": (6656, 52, 60), "65B": (8192, 64, 80),
 }
 
 

@@ -203,6 +203,12 @@ void ggml_b200_release_all(void);
 /* Counters for bench.py: evals run, device microseconds of the last eval (CUDA events), kernels launched */
 struct ggml_b200_stats { uint64_t n_evals; double last_eval_device_us; double total_device_us; uint64_t launches; uint64_t graph_replays; };
 void ggml_b200_get_stats(struct ggml_b200_stats *out);
+/* Profile mode (bench.py roofline leg): every quantised mul_mat launch is bracketed by CUDA events on
+ * the launching stream and accumulated per (type, M, K, N).  algo_bytes = M*(K/32)*block + (K/32)*40*N
+ * + 4*M*N per launch.  Turning it on resets the table. */
+struct ggml_b200_kernel_stat { int type, M, K, N; uint64_t launches; double total_ms; double algo_bytes_per_launch; };
+void ggml_b200_set_profile(int on);
+int ggml_b200_get_kernel_stats(struct ggml_b200_kernel_stat *out, int max_entries);
 
 #ifdef __cplusplus
 }
