@@ -1,0 +1,10 @@
+// fl_decode.h -- internal launcher interface of the fused decode kernels (fl_decode_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fl_cuda.h"
+
+int flk_mv_fused_supported(int type, int K, int mtot);
+int flk_mv_fused(cudaStream_t st, const fl_mv_args *args);
+int flk_attn_decode(cudaStream_t st, const float *q, const float *kcache, const float *vcache, float *out, const int *n_past,
+                    int n_embd, int n_head, int n_ctx, float scale, const uint16_t *exp_tab);

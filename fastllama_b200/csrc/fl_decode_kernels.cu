@@ -1,0 +1,513 @@
+// fl_decode_kernels.cu -- the fused decode step (N = 1): 5 kernels per transformer layer.
+//
+//   k_mv_fused     the TMA-ring matvec of fl_quant_kernels.cu with
+//                    * up to 3 weight matrices sharing one input in ONE launch (wq|wk|wv, w1|w3):
+//                      the CTA's contiguous slice of the concatenated row space is cut into tiles that
+//                      never straddle a matrix, each tile still one 1-D bulk copy;
+//                    * a fused PROLOGUE that builds the q8_0 activations in shared memory from f32:
+//                        PRO_PLAIN    y = q8(x)
+//                        PRO_RMSNORM  y = q8(gamma * rms_norm(x))        (reference lib/ggml.c:7378-7434 + mul)
+//                        PRO_SILUMUL  y = q8(silu_f16tab(a) * b)          (reference lib/ggml.c:3207-3215 + mul)
+//                      replacing the rms_norm / mul / silu / quantize_row_q8_0 launches (and the q8 work
+//                      buffer round trip); every CTA rebuilds the vector itself (K*4 bytes from L2);
+//                    * a fused EPILOGUE:
+//                        EPI_STORE    dst = W y
+//                        EPI_RESADD   dst = W y + residual                (the ggml_add after wo / w2)
+//                        EPI_QKV      q -> rope -> q buffer; k -> rope -> K cache slot n_past;
+//                                     v -> V cache column n_past          (rope + the two ggml_cpy,
+//                                     reference lib/llama.cpp:328-343)
+//   k_attn_decode  one CTA per head: scores over the cached positions, fp16-table soft_max, weighted
+//                  sum of V (reference lib/llama.cpp:346-398 for N = 1)
+//
+// n_past is read from device memory so that a captured CUDA graph of the whole token step can be
+// replayed for every token.  Arithmetic per element is identical to the unfused kernels (same
+// roundings, same table lookups); see DESIGN.md "Parity".
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "fl_common.cuh"
+#include "fl_decode.h"
+#include "fl_kernels.h"
+
+// ---- shared with fl_quant_kernels.cu (duplicated small device helpers) ----------------------------
+struct fd_yprep {
+    uint32_t ye[4], yo[4];
+    float d, s;
+    int c;
+};
+template <int TYPE>
+__device__ __forceinline__ void fd_prep_y(const fl_block_q8_0 *yb, fd_yprep &p) {
+    const uint32_t *q = (const uint32_t *)yb->qs;
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t a = q[2 * j], b = q[2 * j + 1];
+        p.ye[j] = __byte_perm(a, b, 0x6420);
+        p.yo[j] = __byte_perm(a, b, 0x7531);
+        sum = fl_dp4a_ss(0x01010101u, a, sum);
+        sum = fl_dp4a_ss(0x01010101u, b, sum);
+    }
+    p.d = yb->d;
+    p.s = yb->s;
+    p.c = (TYPE == FL_TYPE_Q4_0) ? -8 * sum : 0;
+}
+__device__ __forceinline__ int fd_block_isum(const uint32_t w[4], const fd_yprep &p) {
+    int lo = p.c, hi = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        lo = fl_dp4a_us(w[j] & 0x0F0F0F0Fu, p.ye[j], lo);
+        hi = fl_dp4a_us(w[j] & 0xF0F0F0F0u, p.yo[j], hi);
+    }
+    return lo + (hi >> 4);
+}
+template <int TYPE>
+__device__ __forceinline__ void fd_block(const uint8_t *blk, const fd_yprep &yp, float &acc, float &accm) {
+    uint32_t w[4];
+    float dx;
+    if (TYPE == FL_TYPE_Q4_0) {
+        const uint32_t *bw = (const uint32_t *)blk;
+        dx = __uint_as_float(bw[0]);
+        w[0] = bw[1]; w[1] = bw[2]; w[2] = bw[3]; w[3] = bw[4];
+    } else {
+        const uint2 *bw = (const uint2 *)blk;
+        const uint2 dm = bw[0], q01 = bw[1], q23 = bw[2];
+        dx = __uint_as_float(dm.x);
+        accm = __fmaf_rn(__uint_as_float(dm.y), yp.s, accm);
+        w[0] = q01.x; w[1] = q01.y; w[2] = q23.x; w[3] = q23.y;
+    }
+    const int isum = fd_block_isum(w, yp);
+    acc = __fmaf_rn(__fmul_rn(dx, yp.d), (float)isum, acc);
+}
+
+#define FD_NBL 4
+#define FD_MAX_THREADS 576
+#define FD_MAX_TILES 96
+#define FD_MAX_VEC_PER_THREAD 24      // K <= 512 * 24 = 12288 ... larger K uses more passes (handled by loop)
+
+struct fd_tile {
+    uint32_t src_off_lo, src_off_hi;   // byte offset from seg W base
+    int row0;                          // first row, relative to its segment
+    short rows, seg;
+};
+
+// device-side copy of the launch description (fl_mv_args) plus the ring geometry
+struct fd_params {
+    fl_mv_args a;
+    int nb;
+    uint32_t row_bytes;
+    int R, S, kparts, G, TG, P;
+    uint32_t stage_bytes;
+    uint32_t off_tiles, off_y, off_red, off_rowbuf, off_stage0;
+    int mtot;
+};
+
+template <int TYPE, int NFULL>
+__global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params prm) {
+    constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bars = (uint64_t *)smem;
+    fd_tile *tiles = (fd_tile *)(smem + prm.off_tiles);
+    fl_block_q8_0 *ysm = (fl_block_q8_0 *)(smem + prm.off_y);
+    double *red = (double *)(smem + prm.off_red);            // [16] block-reduce scratch + [1] scale slot
+    float *rowbuf = (float *)(smem + prm.off_rowbuf);        // [S][R][kparts]
+    uint8_t *stage0 = smem + prm.off_stage0;
+    __shared__ int s_ntiles;
+
+    const fl_mv_args &A = prm.a;
+    const int S = prm.S, R = prm.R, kparts = prm.kparts, G = prm.G, TG = prm.TG;
+    const int WPG = kparts * G, CW = WPG * TG;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K = prm.nb * 32;
+
+    // this CTA's slice of the concatenated row space, kept even so rope pairs never split
+    const int half = prm.mtot / 2;
+    const int r0 = 2 * (int)(((long)half * blockIdx.x) / gridDim.x);
+    const int r1 = 2 * (int)(((long)half * (blockIdx.x + 1)) / gridDim.x);
+
+    const uint32_t bar0 = fl_smem_u32(bars);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) {
+            fl_mbar_init(bar0 + 8u * s, 1);
+            fl_mbar_init(bar0 + 8u * (S + s), WPG);
+        }
+        fl_mbar_fence_init();
+        // tile table: tiles never straddle a matrix
+        int n = 0, r = r0, sbase = 0;
+        for (int sg = 0; sg < A.nseg && r < r1; sg++) {
+            const int send = sbase + A.seg_rows[sg];
+            while (r < r1 && r < send && n < FD_MAX_TILES) {
+                const int rows = min(R, min(r1, send) - r);
+                const uint64_t off = (uint64_t)(r - sbase) * prm.row_bytes;
+                tiles[n].src_off_lo = (uint32_t)off;
+                tiles[n].src_off_hi = (uint32_t)(off >> 32);
+                tiles[n].row0 = r - sbase;
+                tiles[n].rows = (short)rows;
+                tiles[n].seg = (short)sg;
+                n++;
+                r += rows;
+            }
+            sbase = send;
+        }
+        s_ntiles = n;
+    }
+    __syncthreads();
+    const int ntiles = s_ntiles;
+
+    if (warp == CW) {
+        // ------------------------------ producer ------------------------------
+        if (lane == 0) {
+            const uint64_t pol = fl_policy_evict_first();
+            int s = 0;
+            uint32_t ph = 1;
+            for (int t = 0; t < ntiles; t++) {
+                fl_mbar_wait(bar0 + 8u * (S + s), ph);
+                const fd_tile tl = tiles[t];
+                const uint32_t bytes = (uint32_t)tl.rows * prm.row_bytes;
+                const uint8_t *src = (const uint8_t *)A.seg_w[tl.seg] + (((uint64_t)tl.src_off_hi << 32) | tl.src_off_lo);
+                fl_mbar_expect_tx(bar0 + 8u * s, bytes);
+                fl_bulk_g2s_hint(fl_smem_u32(stage0 + (size_t)s * prm.stage_bytes), src, bytes, bar0 + 8u * s, pol);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    // ------------------------------ consumers: prologue ------------------------------
+    // Build the q8_0 activation vector in shared memory.  Thread t of the CW*32 consumer threads owns
+    // elements t, t + NT, ...; a warp's 32 lanes therefore always hold one whole 32-element block.
+    const int NT = CW * 32;
+    const int tid = threadIdx.x;                     // consumers are threads [0, NT)
+    {
+        float scale = 1.0f;
+        if (A.pro == FL_PRO_RMSNORM) {
+            double acc = 0.0;
+            for (int e = tid; e < K; e += NT) {
+                const float v = A.x[e];
+                acc += (double)__fmul_rn(v, v);
+            }
+            acc = fl_warp_sum_d(acc);
+            if (lane == 0) red[warp] = acc;
+            asm volatile("bar.sync 15, %0;" ::"r"(NT) : "memory");
+            if (tid == 0) {
+                double t = 0.0;
+                for (int w = 0; w < CW; w++) t += red[w];
+                const float mean = (float)(t / (double)K);
+                ((float *)(red + 16))[0] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, 1e-6f)));
+            }
+            asm volatile("bar.sync 15, %0;" ::"r"(NT) : "memory");
+            scale = ((float *)(red + 16))[0];
+        }
+        for (int e = tid; e < K; e += NT) {           // K is a multiple of 32, NT too: whole warps stay together
+            float v;
+            if (A.pro == FL_PRO_RMSNORM) {
+                v = __fmul_rn(A.gamma[e], __fmul_rn(A.x[e], scale));
+                if (A.normed_out && blockIdx.x == 0) A.normed_out[e] = v;
+            } else if (A.pro == FL_PRO_SILUMUL) {
+                const uint16_t h = __half_as_ushort(__float2half_rn(A.x[e]));
+                v = __fmul_rn(__half2float(__ushort_as_half(A.silu_tab[h])), A.b[e]);
+            } else {
+                v = A.x[e];
+            }
+            const float amax = fl_warp_max(fabsf(v));
+            const float d = __fdiv_rn(amax, 127.f);
+            const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
+            int q = __float2int_rn(__fmul_rn(v, id));
+            q = max(-128, min(127, q));
+            const int sum = fl_warp_sum_i(q);
+            fl_block_q8_0 *yb = ysm + (e >> 5);
+            yb->qs[lane] = (int8_t)q;
+            if (lane == 0) {
+                yb->d = d;
+                yb->s = __fmul_rn(d, (float)sum);
+            }
+        }
+        asm volatile("bar.sync 15, %0;" ::"r"(NT) : "memory");
+    }
+
+    const int tg = warp / WPG;
+    const int wl = warp - tg * WPG;
+    const int p = wl % kparts, g = wl / kparts;
+    const int b0 = p * prm.P;
+    const int b1 = min(prm.nb, b0 + prm.P);
+
+    fd_yprep yp[FD_NBL];
+    bool valid[FD_NBL];
+#pragma unroll
+    for (int j = 0; j < FD_NBL; j++) {
+        const int ib = b0 + lane + 32 * j;
+        valid[j] = (j < NFULL) || ib < b1;
+        if (valid[j]) {
+            fd_prep_y<TYPE>(ysm + ib, yp[j]);
+        } else {
+            yp[j].d = 0.f; yp[j].s = 0.f; yp[j].c = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { yp[j].ye[q] = 0; yp[j].yo[q] = 0; }
+        }
+    }
+
+    // ------------------------------ consumers: main loop ------------------------------
+    const bool staged = (kparts > 1) || (A.epi == FL_EPI_QKV);      // results go through smem + a tile-group barrier
+    const int n_past = (A.epi == FL_EPI_QKV) ? *A.n_past : 0;
+    int s = tg % S;
+    uint32_t ph = (uint32_t)(tg / S) & 1u;
+    const int s_step = TG % S, u_step = TG / S;
+    for (int t = tg; t < ntiles; t += TG) {
+        fl_mbar_wait(bar0 + 8u * s, ph);
+        const fd_tile tl = tiles[t];
+        const uint8_t *tile = stage0 + (size_t)s * prm.stage_bytes;
+        const int rows = tl.rows;
+        float *dseg = A.seg_dst[tl.seg];
+        for (int rr = g; rr < rows; rr += G) {
+            const uint8_t *wrow = tile + (size_t)rr * prm.row_bytes + (size_t)(b0 + lane) * BB;
+            float acc = 0.0f, accm = 0.0f;
+#pragma unroll
+            for (int j = 0; j < FD_NBL; j++) {
+                if (j < NFULL) fd_block<TYPE>(wrow + (size_t)(32 * j) * BB, yp[j], acc, accm);
+                else if (valid[j]) fd_block<TYPE>(wrow + (size_t)(32 * j) * BB, yp[j], acc, accm);
+            }
+            float tot = fl_warp_sum(acc);
+            if (TYPE == FL_TYPE_Q4_1) tot = __fadd_rn(tot, fl_warp_sum(accm));
+            if (lane == 0) {
+                if (staged) rowbuf[((size_t)s * R + rr) * kparts + p] = tot;
+                else {
+                    const int row = tl.row0 + rr;
+                    dseg[row] = (A.epi == FL_EPI_RESADD) ? __fadd_rn(tot, A.res[row]) : tot;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));
+        if (staged) {
+            asm volatile("bar.sync %0, %1;" ::"r"(tg + 1), "r"(WPG * 32) : "memory");
+            const int tloc = (int)threadIdx.x - tg * WPG * 32;
+            if (A.epi == FL_EPI_QKV) {
+                if (tloc < rows / 2) {                                   // one thread per adjacent row pair
+                    const float *p0 = rowbuf + ((size_t)s * R + 2 * tloc) * kparts;
+                    float x0 = p0[0], x1 = p0[kparts];
+                    for (int q = 1; q < kparts; q++) { x0 = __fadd_rn(x0, p0[q]); x1 = __fadd_rn(x1, p0[kparts + q]); }
+                    const int row = tl.row0 + 2 * tloc;                  // even
+                    if (tl.seg < 2) {
+                        const int ip = (row % A.head_dim) >> 1;
+                        const float2 cs = ((const float2 *)A.rope_cs)[(size_t)n_past * (A.head_dim >> 1) + ip];
+                        const float y0 = __fmaf_rn(x0, cs.x, -__fmul_rn(x1, cs.y));
+                        const float y1 = __fmaf_rn(x0, cs.y, __fmul_rn(x1, cs.x));
+                        float *o = (tl.seg == 0) ? (dseg + row) : (A.kcache + (size_t)n_past * A.n_embd + row);
+                        o[0] = y0; o[1] = y1;
+                    } else {
+                        A.vcache[(size_t)row * A.n_ctx + n_past] = x0;
+                        A.vcache[(size_t)(row + 1) * A.n_ctx + n_past] = x1;
+                    }
+                }
+            } else if (tloc < rows) {
+                const float *pp = rowbuf + ((size_t)s * R + tloc) * kparts;
+                float tot = pp[0];
+                for (int q = 1; q < kparts; q++) tot = __fadd_rn(tot, pp[q]);
+                const int row = tl.row0 + tloc;
+                dseg[row] = (A.epi == FL_EPI_RESADD) ? __fadd_rn(tot, A.res[row]) : tot;
+            }
+        }
+        s += s_step; ph ^= (uint32_t)(u_step & 1);
+        if (s >= S) { s -= S; ph ^= 1u; }
+    }
+}
+
+// =================================================================================================
+// attention for one new token: one CTA per head
+// =================================================================================================
+struct fd_attn_params {
+    const float *q;        // [n_embd] rope'd query
+    const float *kcache;   // layer base: [pos][n_embd]
+    const float *vcache;   // layer base: [n_embd][n_ctx]
+    float *out;            // [n_embd]
+    const int *n_past;
+    int n_embd, n_ctx, head_dim;
+    float scale;
+    const uint16_t *exp_tab;
+};
+
+__global__ void __launch_bounds__(256) k_attn_decode(const fd_attn_params P) {
+    extern __shared__ float sc[];                   // [n_ctx] scores / probabilities
+    __shared__ double redd[8];
+    __shared__ float redf[8];
+    const int h = blockIdx.x, hd = P.head_dim;
+    const int n_pos = *P.n_past + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const float *q = P.q + (size_t)h * hd;
+
+    // scores_j = scale * <K_j, q>   (ggml_mul_mat K,Q then ggml_scale; the mask is a no-op for N = 1)
+    for (int j = warp; j < n_pos; j += nw) {
+        const float *k = P.kcache + (size_t)j * P.n_embd + (size_t)h * hd;
+        float acc = 0.f;
+        for (int e = lane; e < hd; e += 32) acc = __fmaf_rn(k[e], q[e], acc);
+        acc = fl_warp_sum(acc);
+        if (lane == 0) sc[j] = __fmul_rn(acc, P.scale);
+    }
+    __syncthreads();
+    // soft_max with the fp16 exp table (reference lib/ggml.c:8521-8589)
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < n_pos; j += blockDim.x) mx = fmaxf(mx, sc[j]);
+    mx = fl_warp_max(mx);
+    if (lane == 0) redf[warp] = mx;
+    __syncthreads();
+    mx = redf[0];
+    for (int w = 1; w < nw; w++) mx = fmaxf(mx, redf[w]);
+    double sum = 0.0;
+    for (int j = threadIdx.x; j < n_pos; j += blockDim.x) {
+        const uint16_t hh = __half_as_ushort(__float2half_rn(__fsub_rn(sc[j], mx)));
+        const float e = __half2float(__ushort_as_half(P.exp_tab[hh]));
+        sc[j] = e;
+        sum += (double)e;
+    }
+    sum = fl_warp_sum_d(sum);
+    if (lane == 0) redd[warp] = sum;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < nw; w++) tot += redd[w];
+    const float inv = (float)(1.0 / tot);
+    for (int j = threadIdx.x; j < n_pos; j += blockDim.x) sc[j] = __fmul_rn(sc[j], inv);
+    __syncthreads();
+    // out_d = sum_j p_j * V[d][j]   (ggml_mul_mat V, soft_max)
+    for (int d = warp; d < hd; d += nw) {
+        const float *v = P.vcache + ((size_t)h * hd + d) * P.n_ctx;
+        float acc = 0.f;
+        for (int j = lane; j < n_pos; j += 32) acc = __fmaf_rn(v[j], sc[j], acc);
+        acc = fl_warp_sum(acc);
+        if (lane == 0) P.out[(size_t)h * hd + d] = acc;
+    }
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+static int g_sm = 0, g_smem_optin = 0;
+static int fd_query() {
+    if (g_sm) return 0;
+    int dev = 0;
+    FL_CUDA_OK(cudaGetDevice(&dev));
+    FL_CUDA_OK(cudaDeviceGetAttribute(&g_sm, cudaDevAttrMultiProcessorCount, dev));
+    FL_CUDA_OK(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return 0;
+}
+
+typedef void (*fd_kernel_t)(const fd_params);
+static fd_kernel_t fd_kernel(int type, int nfull) {
+    if (type == FL_TYPE_Q4_0) {
+        switch (nfull) {
+            case 4: return k_mv_fused<FL_TYPE_Q4_0, 4>;
+            case 3: return k_mv_fused<FL_TYPE_Q4_0, 3>;
+            case 2: return k_mv_fused<FL_TYPE_Q4_0, 2>;
+            case 1: return k_mv_fused<FL_TYPE_Q4_0, 1>;
+            default: return k_mv_fused<FL_TYPE_Q4_0, 0>;
+        }
+    }
+    switch (nfull) {
+        case 4: return k_mv_fused<FL_TYPE_Q4_1, 4>;
+        case 3: return k_mv_fused<FL_TYPE_Q4_1, 3>;
+        case 2: return k_mv_fused<FL_TYPE_Q4_1, 2>;
+        case 1: return k_mv_fused<FL_TYPE_Q4_1, 1>;
+        default: return k_mv_fused<FL_TYPE_Q4_1, 0>;
+    }
+}
+
+int flk_mv_fused_supported(int type, int K, int mtot) {
+    if (type != FL_TYPE_Q4_0 && type != FL_TYPE_Q4_1) return 0;
+    if (K <= 0 || K % 64 != 0) return 0;
+    const size_t row_bytes = (size_t)(K / 32) * fl_block_bytes(type);
+    if (row_bytes % 16 != 0) return 0;
+    if ((K / 32 + 127) / 128 > 8) return 0;
+    if (fd_query() != 0) return 0;
+    return mtot >= 2 && mtot % 2 == 0;
+}
+
+int flk_mv_fused(cudaStream_t st, const fl_mv_args *args) {
+    if (fd_query() != 0) return -1;
+    const fl_mv_args &a = *args;
+    FL_REQUIRE(a.nseg >= 1 && a.nseg <= 3, "mv_fused: nseg=%d", a.nseg);
+    int mtot = 0;
+    for (int i = 0; i < a.nseg; i++) {
+        FL_REQUIRE(a.seg_rows[i] > 0 && a.seg_rows[i] % 2 == 0 && ((uintptr_t)a.seg_w[i] & 15) == 0, "mv_fused: bad segment %d", i);
+        mtot += a.seg_rows[i];
+    }
+    FL_REQUIRE(flk_mv_fused_supported(a.type, a.K, mtot), "mv_fused: unsupported shape type=%d K=%d M=%d", a.type, a.K, mtot);
+    fd_params p;
+    p.a = a;
+    p.mtot = mtot;
+    const int bb = fl_block_bytes(a.type);
+    const int nb = a.K / 32;
+    const size_t row_bytes = (size_t)nb * bb;
+    const int kparts = (nb + 127) / 128;
+    const int P = (nb + kparts - 1) / kparts;
+    const int last = nb - (kparts - 1) * P;
+    int nfull = std::min(P, last) / 32;
+    if (nfull > FD_NBL) nfull = FD_NBL;
+    static int tile_target = -1;
+    if (tile_target < 0) {
+        const char *e = getenv("FASTLLAMA_B200_RING_TILE_KB");
+        tile_target = (e ? atoi(e) : 16) * 1024;
+    }
+    const int Gmax = std::max(1, 16 / kparts);
+    int G = Gmax, TG = 1;
+    for (int tgc = 1; tgc <= 4; tgc *= 2) {
+        const int gc = std::max(1, Gmax / tgc);
+        G = gc; TG = tgc;
+        if ((size_t)gc * row_bytes <= (size_t)tile_target || gc == 1) break;
+    }
+    int R = G;
+    if (R % 2) { R = (R > 1) ? R - 1 : 2; G = std::min(G, R); }      // even tiles keep rope pairs together
+    const size_t stage_bytes = (size_t)R * row_bytes;
+    const size_t y_bytes = (size_t)nb * 40;
+    int S = 16;
+    size_t off_tiles = 0, off_y = 0, off_red = 0, off_rowbuf = 0, off = 0;
+    for (;; S--) {
+        FL_REQUIRE(S >= 2, "mv_fused: shape does not fit shared memory (K=%d)", a.K);
+        off_tiles = ((size_t)(2 * S) * 8 + 127) & ~(size_t)127;
+        off_y = (off_tiles + FD_MAX_TILES * sizeof(fd_tile) + 127) & ~(size_t)127;
+        off_red = (off_y + y_bytes + 127) & ~(size_t)127;
+        off_rowbuf = off_red + 17 * sizeof(double) + 8;
+        off_rowbuf = (off_rowbuf + 127) & ~(size_t)127;
+        off = off_rowbuf + (size_t)S * R * kparts * sizeof(float);
+        off = (off + 127) & ~(size_t)127;
+        if (off + (size_t)S * stage_bytes <= (size_t)g_smem_optin) break;
+    }
+    if (TG > S) TG = S;
+    const int CW = kparts * G * TG;
+    FL_REQUIRE((CW + 1) * 32 <= FD_MAX_THREADS, "mv_fused: too many warps");
+    const int max_tiles_cta = (mtot / g_sm + 2 + R - 1) / R + a.nseg + 1;
+    FL_REQUIRE(max_tiles_cta <= FD_MAX_TILES, "mv_fused: %d tiles per CTA exceed the tile table", max_tiles_cta);
+    p.nb = nb; p.row_bytes = (uint32_t)row_bytes; p.R = R; p.S = S; p.kparts = kparts; p.G = G; p.TG = TG; p.P = P;
+    p.stage_bytes = (uint32_t)stage_bytes;
+    p.off_tiles = (uint32_t)off_tiles; p.off_y = (uint32_t)off_y; p.off_red = (uint32_t)off_red;
+    p.off_rowbuf = (uint32_t)off_rowbuf; p.off_stage0 = (uint32_t)off;
+    const size_t smem_bytes = off + (size_t)S * stage_bytes;
+    fd_kernel_t kern = fd_kernel(a.type, nfull);
+    static bool attr_set[2][FD_NBL + 1] = {{false}};
+    const int ti = a.type == FL_TYPE_Q4_0 ? 0 : 1;
+    if (!attr_set[ti][nfull]) {
+        FL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+        attr_set[ti][nfull] = true;
+    }
+    kern<<<g_sm, (CW + 1) * 32, smem_bytes, st>>>(p);
+    fl_count_launch();
+    FL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int flk_attn_decode(cudaStream_t st, const float *q, const float *kcache, const float *vcache, float *out, const int *n_past,
+                    int n_embd, int n_head, int n_ctx, float scale, const uint16_t *exp_tab) {
+    fd_attn_params P;
+    P.q = q; P.kcache = kcache; P.vcache = vcache; P.out = out; P.n_past = n_past;
+    P.n_embd = n_embd; P.n_ctx = n_ctx; P.head_dim = n_embd / n_head; P.scale = scale; P.exp_tab = exp_tab;
+    const size_t smem = (size_t)n_ctx * sizeof(float);
+    FL_REQUIRE(smem <= 200 * 1024, "attn_decode: n_ctx=%d too large for the score buffer", n_ctx);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && attr < smem) {
+        FL_CUDA_OK(cudaFuncSetAttribute(k_attn_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    k_attn_decode<<<n_head, 256, smem, st>>>(P);
+    fl_count_launch();
+    FL_CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "fl_common.cuh"
+#include "fl_decode.h"
 #include "fl_kernels.h"
 
 // ---------------------------------------------------------------------------------------------
@@ -308,6 +309,58 @@ extern "C" int fl_dev_cpy_f32(const fl_view *src, const fl_view *dst) {
 extern "C" int fl_dev_mul_mat_f32(const fl_view *src0, const fl_view *src1, const fl_view *dst) {
     FL_NEED_INIT();
     return flk_mul_mat_f32(g.stream, *src0, *src1, *dst);
+}
+
+// ---- fused decode step ------------------------------------------------------------------------
+extern "C" int fl_dev_mv_fused_supported(int type, int K, int mtot) { return flk_mv_fused_supported(type, K, mtot); }
+extern "C" int fl_dev_rope_table(int n_dims, int n_pos) {
+    FL_NEED_INIT();
+    return ensure_rope(n_dims, n_pos);
+}
+extern "C" int fl_dev_mv_fused(const fl_mv_args *args) {
+    FL_NEED_INIT();
+    fl_mv_args a = *args;
+    a.silu_tab = g.tab_silu;
+    if (a.epi == FL_EPI_QKV) {
+        FL_REQUIRE(g.rope_cs && g.rope_dims == a.head_dim && g.rope_pos >= a.n_ctx,
+                   "fl_dev_mv_fused: call fl_dev_rope_table(head_dim, n_ctx) first (table must not move under a captured graph)");
+        a.rope_cs = g.rope_cs;
+    }
+    return flk_mv_fused(g.stream, &a);
+}
+extern "C" int fl_dev_attn_decode(const float *q, const float *kcache, const float *vcache, float *out, const int *n_past,
+                                  int n_embd, int n_head, int n_ctx, float scale) {
+    FL_NEED_INIT();
+    return flk_attn_decode(g.stream, q, kcache, vcache, out, n_past, n_embd, n_head, n_ctx, scale, g.tab_exp);
+}
+extern "C" int fl_graph_begin_capture(void) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+    return 0;
+}
+extern "C" int fl_graph_end_capture(void **graph_exec_out) {
+    FL_NEED_INIT();
+    cudaGraph_t graph = nullptr;
+    FL_CUDA_OK(cudaStreamEndCapture(g.stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        fl_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        return -1;
+    }
+    *graph_exec_out = (void *)exec;
+    return 0;
+}
+extern "C" int fl_graph_launch(void *graph_exec) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaGraphLaunch((cudaGraphExec_t)graph_exec, g.stream));
+    fl_count_launch();
+    return 0;
+}
+extern "C" int fl_graph_destroy(void *graph_exec) {
+    if (graph_exec) FL_CUDA_OK(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return 0;
 }
 
 extern "C" void *fl_event_create(void) {

@@ -877,6 +877,312 @@ void exec_node(ggml_tensor *node, const ggml_context *cctx) {
 inline bool in_ctx(const ggml_context *c, const void *p) {
     return c && (const char *)p >= c->mem_buffer && (const char *)p < c->mem_buffer + c->mem_size;
 }
+
+// ================================================================================================
+// 3b. the fused decode plan
+//
+// Model::eval with one token always emits the same 37-node layer (reference lib/llama.cpp:310-455;
+// node order = depth-first post-order of ggml_build_forward_expand).  When a graph matches that
+// template exactly it is lowered to 5 kernels per layer (fl_cuda.h "fused decode step") and the
+// whole token step is captured once into a CUDA graph that is replayed for every later token: all
+// device addresses are the same from token to token (the compute arena is re-built identically), only
+// n_past and the token id change, and both are read from device memory.  Anything that does not
+// match falls through to the node-by-node executor (still on the GPU).
+// ================================================================================================
+struct LayerPlan {
+    fl_mv_args qkv, wo, w13, w2;
+    const float *q, *kcache, *vcache;
+    float *att;
+};
+struct DecodePlan {
+    int n_layer = 0, n_embd = 0, n_head = 0, n_ctx = 0, n_past = 0;
+    float scale = 0.f;
+    // embedding gather
+    int emb_type = 0, emb_K = 0;
+    const void *emb_w = nullptr;
+    size_t emb_stride = 0;
+    const int32_t *emb_ids = nullptr;
+    float *emb_dst = nullptr;
+    std::vector<LayerPlan> layers;
+    fl_mv_args head;
+};
+// Private device workspace of the decode step.  The compute arena cannot be used for intermediates:
+// its layout shifts from token to token (the K*Q score tensor grows with n_past), and the captured
+// graph needs addresses that never move.
+struct DecodeWs {
+    int n_embd = 0, n_ff = 0, n_vocab = 0;
+    float *xa = nullptr, *xb = nullptr, *q = nullptr, *att = nullptr, *ff = nullptr, *m1 = nullptr, *m3 = nullptr, *emb = nullptr, *logits = nullptr;
+    int32_t *d_tok = nullptr;
+};
+struct DecodeState {
+    DecodePlan plan;            // the plan the captured graph was built from
+    DecodeWs ws;
+    void *graph = nullptr;
+    int *d_npast = nullptr;
+    int *h_scalars = nullptr;   // pinned: [0] n_past, [1] token id
+    bool enabled = true, use_graph = true, inited = false;
+};
+struct DecodeOutputs { void *logits_host = nullptr; size_t logits_bytes = 0; void *emb_host = nullptr; size_t emb_bytes = 0; int32_t token = 0; };
+DecodeState g_dec;
+
+struct Cur {
+    ggml_cgraph *g;
+    int i;
+    bool ok;
+    ggml_tensor *next(ggml_op op) {
+        if (!ok || i >= g->n_nodes || g->nodes[i]->op != op) { ok = false; return nullptr; }
+        return g->nodes[i++];
+    }
+};
+#define PM(cond) do { if (!(cond)) return false; } while (0)
+
+inline bool is_qw(const ggml_tensor *w) {
+    return w && w->op == GGML_OP_NONE && (w->type == GGML_TYPE_Q4_0 || w->type == GGML_TYPE_Q4_1) && w->ne[2] == 1 && w->ne[3] == 1 &&
+           w->nb[0] == k_tsize[w->type] && w->nb[1] == (size_t)(w->ne[0] / 32) * k_tsize[w->type];
+}
+inline bool is_vec(const ggml_tensor *t, int64_t n) {
+    return t && t->type == GGML_TYPE_F32 && t->ne[0] == n && t->ne[1] == 1 && t->ne[2] == 1 && t->ne[3] == 1 && t->nb[0] == 4;
+}
+template <typename T> inline T *dp(const ggml_tensor *t, const ggml_context *c) { return (T *)dev_ptr(t->data, ggml_nbytes(t), c); }
+
+void mv_base(fl_mv_args &a, int type, int K) {
+    memset(&a, 0, sizeof(a));
+    a.type = type;
+    a.K = K;
+}
+
+void ensure_ws(DecodeWs &w, int n_embd, int n_ff, int n_vocab) {
+    if (w.xa && w.n_embd == n_embd && w.n_ff == n_ff && w.n_vocab == n_vocab) return;
+    if (w.xa) { FLC(fl_sync()); FLC(fl_dev_free(w.xa)); }
+    const size_t total = (size_t)n_embd * 6 + (size_t)n_ff * 2 + (size_t)n_vocab + 64;
+    float *base = (float *)fl_dev_malloc(total * sizeof(float));
+    if (!base) B200_FAIL("decode workspace: %s", fl_last_error());
+    w.xa = base; w.xb = w.xa + n_embd; w.q = w.xb + n_embd; w.att = w.q + n_embd; w.ff = w.att + n_embd; w.emb = w.ff + n_embd;
+    w.m1 = w.emb + n_embd; w.m3 = w.m1 + n_ff; w.logits = w.m3 + n_ff; w.d_tok = (int32_t *)(w.logits + n_vocab);
+    w.n_embd = n_embd; w.n_ff = n_ff; w.n_vocab = n_vocab;
+}
+
+bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, DecodeWs &W, DecodeOutputs &O) {
+    PM(g->n_nodes >= 4 + 37 && (g->n_nodes - 4) % 37 == 0);
+    Cur c{g, 0, true};
+    ggml_tensor *n0 = c.next(GGML_OP_GET_ROWS);
+    PM(n0 && is_qw(n0->src0) && n0->src1 && n0->src1->type == GGML_TYPE_I32 && ggml_nelements(n0->src1) == 1);
+    const int n_embd = (int)n0->src0->ne[0];
+    PM(is_vec(n0, n_embd));
+    P.n_embd = n_embd;
+    P.n_layer = (g->n_nodes - 4) / 37;
+    P.emb_type = (int)n0->src0->type; P.emb_K = n_embd; P.emb_stride = n0->src0->nb[1];
+    P.emb_w = dp<const void>(n0->src0, ctx);
+    O.token = *(const int32_t *)n0->src1->data;
+    P.layers.resize(P.n_layer);
+    ggml_tensor *x = n0;
+    int n_past = -1, n_head = -1, n_ctx = -1;
+    float *xin = nullptr, *xout = nullptr;     // residual stream ping-pong in the workspace
+    for (int il = 0; il < P.n_layer; il++) {
+        LayerPlan &L = P.layers[il];
+        ggml_tensor *a = c.next(GGML_OP_RMS_NORM), *b = c.next(GGML_OP_MUL);
+        PM(c.ok && a->src0 == x && b->src1 == a && is_vec(b->src0, n_embd) && b->src0->op == GGML_OP_NONE);
+        // K
+        ggml_tensor *mk = c.next(GGML_OP_MUL_MAT), *rsk = c.next(GGML_OP_RESHAPE), *rk = c.next(GGML_OP_ROPE), *vk = c.next(GGML_OP_VIEW),
+                    *ck = c.next(GGML_OP_CPY);
+        PM(c.ok && is_qw(mk->src0) && mk->src1 == b && rsk->src0 == mk && rk->src0 == rsk && ck->src0 == rk && ck->src1 == vk);
+        const int hd = (int)rsk->ne[0];
+        PM(hd > 0 && n_embd % hd == 0 && rsk->ne[1] == n_embd / hd && rsk->ne[2] == 1);
+        const int32_t *rp = (const int32_t *)rk->src1->data;
+        PM(rp[1] == hd && rp[2] == 0 && hd % 2 == 0);
+        if (il == 0) { n_past = rp[0]; n_head = n_embd / hd; }
+        PM(rp[0] == n_past && vk->type == GGML_TYPE_F32 && vk->src0 && vk->src0->op == GGML_OP_NONE);
+        // V
+        ggml_tensor *mvv = c.next(GGML_OP_MUL_MAT), *rsv = c.next(GGML_OP_RESHAPE), *tv = c.next(GGML_OP_TRANSPOSE), *vv = c.next(GGML_OP_VIEW),
+                    *cv = c.next(GGML_OP_CPY);
+        PM(c.ok && is_qw(mvv->src0) && mvv->src1 == b && rsv->src0 == mvv && tv->src0 == rsv && cv->src0 == tv && cv->src1 == vv);
+        PM(vv->type == GGML_TYPE_F32 && vv->ne[0] == 1 && vv->ne[1] == n_embd && vv->nb[1] % 4 == 0);
+        const int nctx_l = (int)(vv->nb[1] / 4);
+        if (il == 0) n_ctx = nctx_l;
+        PM(nctx_l == n_ctx && n_past < n_ctx);
+        // cache views used by attention
+        ggml_tensor *Vv = c.next(GGML_OP_VIEW), *Kv = c.next(GGML_OP_VIEW), *Kr = c.next(GGML_OP_RESHAPE), *Kp = c.next(GGML_OP_PERMUTE);
+        PM(c.ok && Kr->src0 == Kv && Kp->src0 == Kr && Vv->src0 == vv->src0 && Kv->src0 == vk->src0);
+        PM(Kv->ne[0] == (int64_t)(n_past + 1) * n_embd && Vv->ne[0] == n_past + 1 && Vv->ne[1] == hd && Vv->ne[2] == n_head &&
+           Vv->nb[1] == (size_t)n_ctx * 4 && Vv->nb[2] == (size_t)n_ctx * 4 * hd);
+        // the slots written this step must be position n_past of this layer's cache
+        PM((char *)vk->data == (char *)Kv->data + (size_t)n_past * n_embd * 4 && (char *)vv->data == (char *)Vv->data + (size_t)n_past * 4);
+        // Q
+        ggml_tensor *mq = c.next(GGML_OP_MUL_MAT), *rsq = c.next(GGML_OP_RESHAPE), *rq = c.next(GGML_OP_ROPE), *pq = c.next(GGML_OP_PERMUTE);
+        PM(c.ok && is_qw(mq->src0) && mq->src1 == b && rsq->src0 == mq && rq->src0 == rsq && pq->src0 == rq);
+        const int32_t *rpq = (const int32_t *)rq->src1->data;
+        PM(rpq[0] == n_past && rpq[1] == hd && rpq[2] == 0);
+        // attention
+        ggml_tensor *kq = c.next(GGML_OP_MUL_MAT), *sc = c.next(GGML_OP_SCALE), *mask = c.next(GGML_OP_DIAG_MASK_INF), *sm = c.next(GGML_OP_SOFT_MAX),
+                    *kqv = c.next(GGML_OP_MUL_MAT), *pm = c.next(GGML_OP_PERMUTE), *att = c.next(GGML_OP_CPY);
+        PM(c.ok && kq->src0 == Kp && kq->src1 == pq && sc->src0 == kq && mask->src0 == sc && sm->src0 == mask && kqv->src0 == Vv && kqv->src1 == sm &&
+           pm->src0 == kqv && att->src0 == pm && is_vec(att, n_embd) && ggml_nelements(sc->src1) == 1 && sc->src1->op == GGML_OP_NONE);
+        PM(*(const int32_t *)mask->src1->data == n_past);
+        const float scale = *(const float *)sc->src1->data;
+        if (il == 0) P.scale = scale;
+        PM(scale == P.scale);
+        // output projection + residual
+        ggml_tensor *mo = c.next(GGML_OP_MUL_MAT), *ff = c.next(GGML_OP_ADD);
+        PM(c.ok && is_qw(mo->src0) && mo->src1 == att && ff->src0 == mo && ff->src1 == x);
+        // feed-forward
+        ggml_tensor *cn = c.next(GGML_OP_RMS_NORM), *d = c.next(GGML_OP_MUL), *m1 = c.next(GGML_OP_MUL_MAT), *s1 = c.next(GGML_OP_SILU),
+                    *m3 = c.next(GGML_OP_MUL_MAT), *h = c.next(GGML_OP_MUL), *m2 = c.next(GGML_OP_MUL_MAT), *xo = c.next(GGML_OP_ADD);
+        PM(c.ok && cn->src0 == ff && d->src1 == cn && is_vec(d->src0, n_embd) && d->src0->op == GGML_OP_NONE && is_qw(m1->src0) && m1->src1 == d &&
+           s1->src0 == m1 && is_qw(m3->src0) && m3->src1 == d && h->src0 == s1 && h->src1 == m3 && is_qw(m2->src0) && m2->src1 == h &&
+           xo->src0 == m2 && xo->src1 == ff);
+        const ggml_tensor *wq = mq->src0, *wk = mk->src0, *wv = mvv->src0, *wo = mo->src0, *w1 = m1->src0, *w3 = m3->src0, *w2 = m2->src0;
+        const int n_ff = (int)w1->ne[1];
+        PM(wq->type == wk->type && wq->type == wv->type && w1->type == w3->type);
+        PM(wq->ne[0] == n_embd && wk->ne[0] == n_embd && wv->ne[0] == n_embd && wq->ne[1] == n_embd && wk->ne[1] == n_embd && wv->ne[1] == n_embd);
+        PM(wo->ne[0] == n_embd && wo->ne[1] == n_embd && w1->ne[0] == n_embd && w3->ne[0] == n_embd && w3->ne[1] == n_ff && w2->ne[0] == n_ff &&
+           w2->ne[1] == n_embd);
+        PM(fl_dev_mv_fused_supported((int)wq->type, n_embd, 3 * n_embd) && fl_dev_mv_fused_supported((int)wo->type, n_embd, n_embd) &&
+           fl_dev_mv_fused_supported((int)w1->type, n_embd, 2 * n_ff) && fl_dev_mv_fused_supported((int)w2->type, n_ff, n_embd));
+
+        if (il == 0) {
+            ensure_ws(W, n_embd, n_ff, (int)g->nodes[g->n_nodes - 1]->ne[0]);
+            P.emb_ids = W.d_tok; P.emb_dst = W.xa;
+            xin = W.xa; xout = W.xb;
+        }
+        PM(W.n_ff == n_ff);
+        L.q = W.q;
+        L.kcache = dp<const float>(Kv, ctx);
+        L.vcache = dp<const float>(Vv, ctx);
+        L.att = W.att;
+        // wq|wk|wv: rms_norm prologue, rope + cache-store epilogue
+        mv_base(L.qkv, (int)wq->type, n_embd);
+        L.qkv.nseg = 3;
+        L.qkv.seg_w[0] = dp<const void>(wq, ctx); L.qkv.seg_w[1] = dp<const void>(wk, ctx); L.qkv.seg_w[2] = dp<const void>(wv, ctx);
+        L.qkv.seg_rows[0] = L.qkv.seg_rows[1] = L.qkv.seg_rows[2] = n_embd;
+        L.qkv.seg_dst[0] = (float *)L.q;
+        L.qkv.pro = FL_PRO_RMSNORM; L.qkv.x = xin; L.qkv.gamma = dp<const float>(b->src0, ctx);
+        L.qkv.epi = FL_EPI_QKV; L.qkv.n_ctx = n_ctx; L.qkv.n_embd = n_embd; L.qkv.head_dim = hd;
+        L.qkv.kcache = (float *)L.kcache; L.qkv.vcache = (float *)L.vcache;
+        // wo: plain prologue, residual epilogue
+        mv_base(L.wo, (int)wo->type, n_embd);
+        L.wo.nseg = 1; L.wo.seg_w[0] = dp<const void>(wo, ctx); L.wo.seg_rows[0] = n_embd; L.wo.seg_dst[0] = W.ff;
+        L.wo.pro = FL_PRO_PLAIN; L.wo.x = L.att; L.wo.epi = FL_EPI_RESADD; L.wo.res = xin;
+        // w1|w3: rms_norm prologue
+        mv_base(L.w13, (int)w1->type, n_embd);
+        L.w13.nseg = 2; L.w13.seg_w[0] = dp<const void>(w1, ctx); L.w13.seg_w[1] = dp<const void>(w3, ctx);
+        L.w13.seg_rows[0] = L.w13.seg_rows[1] = n_ff; L.w13.seg_dst[0] = W.m1; L.w13.seg_dst[1] = W.m3;
+        L.w13.pro = FL_PRO_RMSNORM; L.w13.x = W.ff; L.w13.gamma = dp<const float>(d->src0, ctx); L.w13.epi = FL_EPI_STORE;
+        // w2: silu*mul prologue, residual epilogue
+        mv_base(L.w2, (int)w2->type, n_ff);
+        L.w2.nseg = 1; L.w2.seg_w[0] = dp<const void>(w2, ctx); L.w2.seg_rows[0] = n_embd; L.w2.seg_dst[0] = xout;
+        L.w2.pro = FL_PRO_SILUMUL; L.w2.x = L.w13.seg_dst[0]; L.w2.b = L.w13.seg_dst[1]; L.w2.epi = FL_EPI_RESADD; L.w2.res = L.w13.x;
+        x = xo;
+        std::swap(xin, xout);
+    }
+    ggml_tensor *e = c.next(GGML_OP_RMS_NORM), *f = c.next(GGML_OP_MUL), *lg = c.next(GGML_OP_MUL_MAT);
+    PM(c.ok && c.i == g->n_nodes && e->src0 == x && f->src1 == e && is_vec(f->src0, n_embd) && is_qw(lg->src0) && lg->src1 == f &&
+       lg->src0->ne[0] == n_embd && lg->src0->ne[1] % 2 == 0 && fl_dev_mv_fused_supported((int)lg->src0->type, n_embd, (int)lg->src0->ne[1]));
+    mv_base(P.head, (int)lg->src0->type, n_embd);
+    P.head.nseg = 1; P.head.seg_w[0] = dp<const void>(lg->src0, ctx); P.head.seg_rows[0] = (int)lg->src0->ne[1]; P.head.seg_dst[0] = W.logits;
+    PM(W.n_vocab == (int)lg->src0->ne[1] && is_vec(lg, W.n_vocab) && is_vec(f, n_embd));
+    P.head.pro = FL_PRO_RMSNORM; P.head.x = xin; P.head.gamma = dp<const float>(f->src0, ctx); P.head.normed_out = W.emb;
+    O.logits_host = lg->data; O.logits_bytes = (size_t)W.n_vocab * 4; O.emb_host = f->data; O.emb_bytes = (size_t)n_embd * 4;
+    P.head.epi = FL_EPI_STORE;
+    P.n_head = n_head; P.n_ctx = n_ctx; P.n_past = n_past;
+    return n_past >= 0;
+}
+
+bool same_mv(const fl_mv_args &a, const fl_mv_args &b) { return memcmp(&a, &b, sizeof(a)) == 0; }
+bool same_plan(const DecodePlan &a, const DecodePlan &b) {
+    if (a.n_layer != b.n_layer || a.n_embd != b.n_embd || a.n_head != b.n_head || a.n_ctx != b.n_ctx || a.scale != b.scale ||
+        a.emb_type != b.emb_type || a.emb_w != b.emb_w || a.emb_stride != b.emb_stride || a.emb_ids != b.emb_ids || a.emb_dst != b.emb_dst ||
+        !same_mv(a.head, b.head))
+        return false;
+    for (int i = 0; i < a.n_layer; i++) {
+        const LayerPlan &x = a.layers[i], &y = b.layers[i];
+        if (!same_mv(x.qkv, y.qkv) || !same_mv(x.wo, y.wo) || !same_mv(x.w13, y.w13) || !same_mv(x.w2, y.w2) || x.q != y.q || x.kcache != y.kcache ||
+            x.vcache != y.vcache || x.att != y.att)
+            return false;
+    }
+    return true;
+}
+
+void profiled_mv(const fl_mv_args &a) {
+    if (!g_profile) { FLC(fl_dev_mv_fused(&a)); return; }
+    FLC(fl_event_record(g_pev0));
+    FLC(fl_dev_mv_fused(&a));
+    FLC(fl_event_record(g_pev1));
+    FLC(fl_event_sync(g_pev1));
+    float ms = 0.f;
+    FLC(fl_event_elapsed_ms(g_pev0, g_pev1, &ms));
+    int M = 0;
+    for (int i = 0; i < a.nseg; i++) M += a.seg_rows[i];
+    ggml_b200_kernel_stat *e = nullptr;
+    for (auto &k : g_kstats) if (k.type == a.type && k.M == M && k.K == a.K && k.N == 1) e = &k;
+    if (!e) {
+        g_kstats.push_back(ggml_b200_kernel_stat{a.type, M, a.K, 1, 0, 0.0, (double)M * (a.K / 32) * (double)k_tsize[a.type] + (double)(a.K / 32) * 40.0 + 4.0 * M});
+        e = &g_kstats.back();
+    }
+    e->launches++;
+    e->total_ms += ms;
+}
+
+void issue_decode(const DecodePlan &P, const int *d_npast) {
+    FLC(fl_dev_dequantize_rows(P.emb_type, P.emb_w, P.emb_stride, P.emb_K, P.emb_ids, 1, P.emb_dst, (size_t)P.emb_K));
+    for (const LayerPlan &Lc : P.layers) {
+        fl_mv_args qkv = Lc.qkv;
+        qkv.n_past = d_npast;
+        profiled_mv(qkv);
+        FLC(fl_dev_attn_decode(Lc.q, Lc.kcache, Lc.vcache, Lc.att, d_npast, P.n_embd, P.n_head, P.n_ctx, P.scale));
+        profiled_mv(Lc.wo);
+        profiled_mv(Lc.w13);
+        profiled_mv(Lc.w2);
+    }
+    profiled_mv(P.head);
+}
+
+// returns true when the graph was executed through the fused plan
+bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, void *ev0, void *ev1) {
+    DecodeState &D = g_dec;
+    if (!D.inited) {
+        D.inited = true;
+        D.enabled = getenv("FASTLLAMA_B200_NO_FUSED") == nullptr;
+        D.use_graph = getenv("FASTLLAMA_B200_NO_GRAPH") == nullptr;
+    }
+    if (!D.enabled) return false;
+    DecodePlan P;
+    if (!match_decode(ctx, g, P, D.ws, O)) return false;
+    if (!D.d_npast) {
+        D.d_npast = (int *)fl_dev_malloc(64);
+        D.h_scalars = (int *)fl_host_alloc_pinned(64);
+        if (!D.d_npast || !D.h_scalars) B200_FAIL("decode plan: %s", fl_last_error());
+    }
+    FLC(fl_dev_rope_table(P.n_embd / P.n_head, P.n_ctx));
+    FLC(fl_sync());                                   // the pinned scalars of the previous step have been consumed
+    D.h_scalars[0] = P.n_past;
+    D.h_scalars[1] = O.token;
+    FLC(fl_h2d(D.d_npast, &D.h_scalars[0], sizeof(int)));
+    FLC(fl_h2d(D.ws.d_tok, &D.h_scalars[1], sizeof(int)));
+    if (g_profile || !D.use_graph) {
+        FLC(fl_event_record(ev0));
+        issue_decode(P, D.d_npast);
+        FLC(fl_event_record(ev1));
+        return true;
+    }
+    if (!D.graph || !same_plan(P, D.plan)) {
+        if (D.graph) { FLC(fl_sync()); FLC(fl_graph_destroy(D.graph)); D.graph = nullptr; }
+        // one eager pass first: sets kernel attributes, and gives this token's result
+        FLC(fl_event_record(ev0));
+        issue_decode(P, D.d_npast);
+        FLC(fl_event_record(ev1));
+        FLC(fl_graph_begin_capture());
+        issue_decode(P, D.d_npast);
+        FLC(fl_graph_end_capture(&D.graph));
+        D.plan = P;
+        if (g_verbose) fprintf(stderr, "[ggml_b200] decode plan captured: %d layers, n_embd %d, n_ctx %d\n", P.n_layer, P.n_embd, P.n_ctx);
+        return true;       // the eager pass already produced this token (capture does not execute)
+    }
+    FLC(fl_event_record(ev0));
+    FLC(fl_graph_launch(D.graph));
+    FLC(fl_event_record(ev1));
+    g_stats.graph_replays++;
+    return true;
+}
 }  // namespace
 
 extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph *g) {
@@ -889,67 +1195,76 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
     g->work = nullptr;
     g->work_size = 0;
 
-    // Leafs.  Weights / KV cache live in persistent arenas (uploaded once by dev_ptr).  Constants the
-    // host wrote into the compute arena while building the graph are uploaded per graph, but only
-    // those a device op reads as DATA (token ids); rope / mask / scale parameters are read on the
-    // host at dispatch, so ~130 tiny copies per 7B token are avoided.
-    {
-        const ggml_tensor *done[16];
-        int n_done = 0;
-        auto upload_leaf = [&](const ggml_tensor *t) {
-            if (!t || t->op != GGML_OP_NONE || !t->data || !in_ctx(ctx, t->data)) return;
-            for (int i = 0; i < n_done; i++) if (done[i] == t) return;
-            const size_t nb = ggml_nbytes(t);
-            FLC(fl_h2d(dev_ptr(t->data, nb, ctx), t->data, nb));
-            if (n_done < 16) done[n_done++] = t;
-        };
-        for (int i = 0; i < g->n_nodes; i++) {
-            const ggml_tensor *n = g->nodes[i];
-            const bool param_only = n->op == GGML_OP_SCALE || n->op == GGML_OP_DIAG_MASK_INF || n->op == GGML_OP_ROPE;
-            upload_leaf(n->src0);
-            if (!param_only) upload_leaf(n->src1);
-        }
-    }
-
-    FLC(fl_event_record(ev0));
-    for (int i = 0; i < g->n_nodes; i++) exec_node(g->nodes[i], ctx);
-    FLC(fl_event_record(ev1));
-
-    // results the caller may read on the host (reference lib/llama.cpp:476-489): graph sinks that
-    // live in the compute arena (the logits) and the input of the last mul_mat (the embeddings).
-    std::vector<char> consumed((size_t)g->n_nodes, 0);
-    {
-        const GraphEpoch *ge = lookup_epoch(g);
-        const bool by_stamp = ge && ge->clean && ge->epoch == g_epoch;
-        std::unordered_map<const ggml_tensor *, int> index;
-        if (!by_stamp)
-            for (int i = 0; i < g->n_nodes; i++) index[g->nodes[i]] = i;
-        auto mark = [&](const ggml_tensor *s) {
-            if (!s) return;
-            if (by_stamp) {
-                const Stamp *st = (const Stamp *)s->padding;
-                if (st->epoch == ge->epoch && st->index >= 0 && st->index < g->n_nodes && g->nodes[st->index] == s) consumed[st->index] = 1;
-            } else {
-                auto it = index.find(s);
-                if (it != index.end()) consumed[it->second] = 1;
+    DecodeOutputs dout;
+    if (run_decode_plan(ctx, g, dout, ev0, ev1)) {
+        // fused decode step: the two results the caller reads (reference lib/llama.cpp:476-489) come
+        // straight from the private workspace
+        FLC(fl_d2h(dout.logits_host, g_dec.ws.logits, dout.logits_bytes));
+        FLC(fl_d2h(dout.emb_host, g_dec.ws.emb, dout.emb_bytes));
+        FLC(fl_sync());
+    } else {
+        // Leafs.  Weights / KV cache live in persistent arenas (uploaded once by dev_ptr).  Constants the
+        // host wrote into the compute arena while building the graph are uploaded per graph, but only
+        // those a device op reads as DATA (token ids); rope / mask / scale parameters are read on the
+        // host at dispatch, so ~130 tiny copies per 7B token are avoided.
+        {
+            const ggml_tensor *done[16];
+            int n_done = 0;
+            auto upload_leaf = [&](const ggml_tensor *t) {
+                if (!t || t->op != GGML_OP_NONE || !t->data || !in_ctx(ctx, t->data)) return;
+                for (int i = 0; i < n_done; i++) if (done[i] == t) return;
+                const size_t nb = ggml_nbytes(t);
+                FLC(fl_h2d(dev_ptr(t->data, nb, ctx), t->data, nb));
+                if (n_done < 16) done[n_done++] = t;
+            };
+            for (int i = 0; i < g->n_nodes; i++) {
+                const ggml_tensor *n = g->nodes[i];
+                const bool param_only = n->op == GGML_OP_SCALE || n->op == GGML_OP_DIAG_MASK_INF || n->op == GGML_OP_ROPE;
+                upload_leaf(n->src0);
+                if (!param_only) upload_leaf(n->src1);
             }
-        };
-        for (int i = 0; i < g->n_nodes; i++) {
-            mark(g->nodes[i]->src0); mark(g->nodes[i]->src1);
-            for (int k = 0; k < GGML_MAX_OPT; k++) mark(g->nodes[i]->opt[k]);
         }
+
+        FLC(fl_event_record(ev0));
+        for (int i = 0; i < g->n_nodes; i++) exec_node(g->nodes[i], ctx);
+        FLC(fl_event_record(ev1));
+
+        // results the caller may read on the host (reference lib/llama.cpp:476-489): graph sinks that
+        // live in the compute arena (the logits) and the input of the last mul_mat (the embeddings).
+        std::vector<char> consumed((size_t)g->n_nodes, 0);
+        {
+            const GraphEpoch *ge = lookup_epoch(g);
+            const bool by_stamp = ge && ge->clean && ge->epoch == g_epoch;
+            std::unordered_map<const ggml_tensor *, int> index;
+            if (!by_stamp)
+                for (int i = 0; i < g->n_nodes; i++) index[g->nodes[i]] = i;
+            auto mark = [&](const ggml_tensor *s) {
+                if (!s) return;
+                if (by_stamp) {
+                    const Stamp *st = (const Stamp *)s->padding;
+                    if (st->epoch == ge->epoch && st->index >= 0 && st->index < g->n_nodes && g->nodes[st->index] == s) consumed[st->index] = 1;
+                } else {
+                    auto it = index.find(s);
+                    if (it != index.end()) consumed[it->second] = 1;
+                }
+            };
+            for (int i = 0; i < g->n_nodes; i++) {
+                mark(g->nodes[i]->src0); mark(g->nodes[i]->src1);
+                for (int k = 0; k < GGML_MAX_OPT; k++) mark(g->nodes[i]->opt[k]);
+            }
+        }
+        const ggml_tensor *last_mm = nullptr;
+        for (int i = g->n_nodes - 1; i >= 0 && !last_mm; i--)
+            if (g->nodes[i]->op == GGML_OP_MUL_MAT) last_mm = g->nodes[i];
+        for (int i = 0; i < g->n_nodes; i++) {
+            ggml_tensor *t = g->nodes[i];
+            const bool want = sync_all || !consumed[i] || (last_mm && t == last_mm->src1);
+            if (!want || !in_ctx(ctx, t->data) || !is_contiguous(t)) continue;
+            const size_t nb = ggml_nbytes(t);
+            FLC(fl_d2h(t->data, dev_ptr(t->data, nb, ctx), nb));
+        }
+        FLC(fl_sync());
     }
-    const ggml_tensor *last_mm = nullptr;
-    for (int i = g->n_nodes - 1; i >= 0 && !last_mm; i--)
-        if (g->nodes[i]->op == GGML_OP_MUL_MAT) last_mm = g->nodes[i];
-    for (int i = 0; i < g->n_nodes; i++) {
-        ggml_tensor *t = g->nodes[i];
-        const bool want = sync_all || !consumed[i] || (last_mm && t == last_mm->src1);
-        if (!want || !in_ctx(ctx, t->data) || !is_contiguous(t)) continue;
-        const size_t nb = ggml_nbytes(t);
-        FLC(fl_d2h(t->data, dev_ptr(t->data, nb, ctx), nb));
-    }
-    FLC(fl_sync());
 
     float ms = 0.f;
     FLC(fl_event_elapsed_ms(ev0, ev1, &ms));

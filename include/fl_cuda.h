@@ -128,6 +128,45 @@ int fl_dev_rope(const fl_view *t, int n_past, int n_dims, int mode);        /* i
 int fl_dev_cpy_f32(const fl_view *src, const fl_view *dst);
 int fl_dev_mul_mat_f32(const fl_view *src0, const fl_view *src1, const fl_view *dst);
 
+/* ---- fused decode step (N = 1) ------------------------------------------------------------------
+ * fl_dev_mv_fused: up to three weight matrices that share one input, one launch.  The prologue builds
+ * the q8_0 activations from f32 inside the kernel (replacing rms_norm / mul / silu / quantize_row_q8_0
+ * launches, reference lib/ggml.c:7378-7434, :3207-3215, :1299-1441); the epilogue replaces the
+ * ggml_add after wo / w2 or the rope + KV-cache copies after wq|wk|wv (reference lib/llama.cpp:328-343).
+ * All pointers are device pointers.  n_past is read on the device (CUDA-graph replay). */
+enum { FL_PRO_PLAIN = 0, FL_PRO_RMSNORM = 1, FL_PRO_SILUMUL = 2 };
+enum { FL_EPI_STORE = 0, FL_EPI_RESADD = 1, FL_EPI_QKV = 2 };
+typedef struct fl_mv_args {
+    int type, K, nseg;
+    const void *seg_w[3];        /* weight matrices: seg_rows[i] rows of K/32 blocks, contiguous rows */
+    int seg_rows[3];
+    float *seg_dst[3];           /* f32 outputs (EPI_QKV: only seg_dst[0] = q buffer is used) */
+    int pro;
+    const float *x;              /* PRO_PLAIN / PRO_RMSNORM input; PRO_SILUMUL: the silu argument */
+    const float *gamma;          /* PRO_RMSNORM: norm weight */
+    const float *b;              /* PRO_SILUMUL: the multiplier */
+    float *normed_out;           /* PRO_RMSNORM: optional copy of gamma * rms_norm(x) (the "embeddings") */
+    const uint16_t *silu_tab;    /* filled in by the library */
+    int epi;
+    const float *res;            /* EPI_RESADD */
+    const int *n_past;           /* EPI_QKV ... */
+    int n_ctx, n_embd, head_dim;
+    const void *rope_cs;         /* filled in by the library (cos/sin table) */
+    float *kcache, *vcache;      /* this layer's K [pos][n_embd] and V [n_embd][n_ctx] cache */
+} fl_mv_args;
+int fl_dev_mv_fused_supported(int type, int K, int mtot);
+int fl_dev_mv_fused(const fl_mv_args *args);
+/* attention of one new token over the cached positions 0..n_past (reference lib/llama.cpp:346-398, N = 1) */
+int fl_dev_attn_decode(const float *q, const float *kcache, const float *vcache, float *out, const int *n_past, int n_embd,
+                       int n_head, int n_ctx, float scale);
+int fl_dev_rope_table(int n_dims, int n_pos);    /* make sure the cos/sin table covers n_pos positions */
+
+/* CUDA-graph capture of everything issued on the library stream between begin and end */
+int fl_graph_begin_capture(void);
+int fl_graph_end_capture(void **graph_exec_out);
+int fl_graph_launch(void *graph_exec);
+int fl_graph_destroy(void *graph_exec);
+
 /* Tooling: counter-based N(0, std^2) fill (element i depends on (seed, i) only) used to create
  * synthetic model files on the device; not part of the hot path. */
 int fl_dev_fill_normal(float *p_dev, size_t n, uint64_t seed, float std);

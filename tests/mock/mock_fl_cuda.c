@@ -104,7 +104,11 @@ int fl_dev_mul_mat_q(int type, const void *W, size_t wrs, int M, int K, const vo
         }
     return 0;
 }
+typedef struct mock_graph_fwd mock_graph_fwd;
+static int mock_capturing(void);
+static void mock_record_deq(int type, const void *W, size_t wrs, int K, const int32_t *ids, int n, float *dst, size_t drs);
 int fl_dev_dequantize_rows(int type, const void *W, size_t wrs, int K, const int32_t *ids, int n, float *dst, size_t drs) {
+    if (mock_capturing()) { mock_record_deq(type, W, wrs, K, ids, n, dst, drs); return 0; }
     g_launches++;
     for (int i = 0; i < n; i++) {
         const void *wr = (const char *)W + (size_t)(ids ? ids[i] : i) * wrs;
@@ -204,4 +208,93 @@ int fl_dev_mul_mat_f32(const fl_view *a, const fl_view *b, const fl_view *d) {
         *(float *)at(d, i0, i1, i2, i3) = acc;
     }
     return 0;
+}
+
+/* ---- fused decode step + graph capture (recorded and replayed, like a CUDA graph) ---------------- */
+enum { OP_MV = 1, OP_ATTN = 2, OP_DEQ = 3 };
+typedef struct {
+    int kind;
+    fl_mv_args mv;
+    struct { const float *q, *k, *v; float *out; const int *n_past; int n_embd, n_head, n_ctx; float scale; } at;
+    struct { int type; const void *W; size_t wrs; int K; const int32_t *ids; int n; float *dst; size_t drs; } dq;
+} mock_op;
+typedef struct { mock_op *ops; int n, cap; } mock_graph;
+static mock_graph *g_capture = NULL;
+
+static void record(const mock_op *op) {
+    if (g_capture->n == g_capture->cap) { g_capture->cap = g_capture->cap ? 2 * g_capture->cap : 64; g_capture->ops = realloc(g_capture->ops, sizeof(mock_op) * g_capture->cap); }
+    g_capture->ops[g_capture->n++] = *op;
+}
+static void run_mv(const fl_mv_args *a) {
+    const int K = a->K, nb = K / 32, bb = a->type == 2 ? 20 : 24;
+    float *v = malloc(sizeof(float) * K);
+    if (a->pro == FL_PRO_RMSNORM) {
+        double sum = 0; for (int i = 0; i < K; i++) sum += (double)(a->x[i] * a->x[i]);
+        float mean = (float)(sum / (double)K), sc = 1.0f / sqrtf(mean + 1e-6f);
+        for (int i = 0; i < K; i++) { v[i] = a->gamma[i] * (a->x[i] * sc); if (a->normed_out) a->normed_out[i] = v[i]; }
+    } else if (a->pro == FL_PRO_SILUMUL) {
+        for (int i = 0; i < K; i++) v[i] = h2f(tab_silu[f2h(a->x[i])]) * a->b[i];
+    } else memcpy(v, a->x, sizeof(float) * K);
+    void *q8 = malloc((size_t)nb * 40);
+    orc_quantize_row_q8_0(v, q8, K);
+    const int n_past = a->epi == FL_EPI_QKV ? *a->n_past : 0;
+    for (int sg = 0; sg < a->nseg; sg++) {
+        float *tmp = malloc(sizeof(float) * a->seg_rows[sg]);
+        for (int r = 0; r < a->seg_rows[sg]; r++) {
+            const void *wr = (const char *)a->seg_w[sg] + (size_t)r * nb * bb;
+            if (a->type == 2) orc_vec_dot_q4_0_q8_0(K, tmp + r, wr, q8); else orc_vec_dot_q4_1_q8_0(K, tmp + r, wr, q8);
+        }
+        if (a->epi == FL_EPI_QKV) {
+            const int hd = a->head_dim; const float ts = powf(10000.0f, -2.0f / hd);
+            for (int r = 0; r < a->seg_rows[sg]; r += 2) {
+                float x0 = tmp[r], x1 = tmp[r + 1];
+                if (sg < 2) {
+                    float theta = (float)n_past; for (int i = 0; i < (r % hd) / 2; i++) theta *= ts;
+                    float c = cosf(theta), s = sinf(theta), y0 = x0 * c - x1 * s, y1 = x0 * s + x1 * c;
+                    float *o = sg == 0 ? a->seg_dst[0] + r : a->kcache + (size_t)n_past * a->n_embd + r;
+                    o[0] = y0; o[1] = y1;
+                } else { a->vcache[(size_t)r * a->n_ctx + n_past] = x0; a->vcache[(size_t)(r + 1) * a->n_ctx + n_past] = x1; }
+            }
+        } else for (int r = 0; r < a->seg_rows[sg]; r++) a->seg_dst[sg][r] = a->epi == FL_EPI_RESADD ? tmp[r] + a->res[r] : tmp[r];
+        free(tmp);
+    }
+    free(q8); free(v);
+}
+static void run_attn(const mock_op *o) {
+    const int hd = o->at.n_embd / o->at.n_head, n_pos = *o->at.n_past + 1;
+    float *p = malloc(sizeof(float) * n_pos);
+    for (int h = 0; h < o->at.n_head; h++) {
+        float mx = -INFINITY; double sum = 0;
+        for (int j = 0; j < n_pos; j++) { float acc = 0; for (int e = 0; e < hd; e++) acc += o->at.k[(size_t)j * o->at.n_embd + h * hd + e] * o->at.q[h * hd + e]; p[j] = acc * o->at.scale; if (p[j] > mx) mx = p[j]; }
+        for (int j = 0; j < n_pos; j++) { float v = h2f(tab_exp[f2h(p[j] - mx)]); sum += v; p[j] = v; }
+        float inv = (float)(1.0 / sum);
+        for (int j = 0; j < n_pos; j++) p[j] *= inv;
+        for (int d = 0; d < hd; d++) { float acc = 0; for (int j = 0; j < n_pos; j++) acc += o->at.v[((size_t)h * hd + d) * o->at.n_ctx + j] * p[j]; o->at.out[h * hd + d] = acc; }
+    }
+    free(p);
+}
+static void run_op(const mock_op *o) {
+    g_launches++;
+    if (o->kind == OP_MV) run_mv(&o->mv);
+    else if (o->kind == OP_ATTN) run_attn(o);
+    else for (int i = 0; i < o->dq.n; i++) {
+        const void *wr = (const char *)o->dq.W + (size_t)(o->dq.ids ? o->dq.ids[i] : i) * o->dq.wrs;
+        if (o->dq.type == 2) orc_dequantize_row_q4_0(wr, o->dq.dst + (size_t)i * o->dq.drs, o->dq.K); else orc_dequantize_row_q4_1(wr, o->dq.dst + (size_t)i * o->dq.drs, o->dq.K);
+    }
+}
+int fl_dev_mv_fused_supported(int type, int K, int mtot) { return (type == 2 || type == 3) && K % 64 == 0 && mtot >= 2 && mtot % 2 == 0; }
+int fl_dev_rope_table(int n_dims, int n_pos) { (void)n_dims; (void)n_pos; return 0; }
+int fl_dev_mv_fused(const fl_mv_args *a) { mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_MV; o.mv = *a; if (g_capture) record(&o); else run_op(&o); return 0; }
+int fl_dev_attn_decode(const float *q, const float *k, const float *v, float *out, const int *n_past, int n_embd, int n_head, int n_ctx, float scale) {
+    mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_ATTN; o.at.q = q; o.at.k = k; o.at.v = v; o.at.out = out; o.at.n_past = n_past; o.at.n_embd = n_embd; o.at.n_head = n_head; o.at.n_ctx = n_ctx; o.at.scale = scale;
+    if (g_capture) record(&o); else run_op(&o); return 0;
+}
+int fl_graph_begin_capture(void) { g_capture = calloc(1, sizeof(mock_graph)); return 0; }
+int fl_graph_end_capture(void **out) { *out = g_capture; g_capture = NULL; return 0; }
+int fl_graph_launch(void *ge) { mock_graph *g = ge; for (int i = 0; i < g->n; i++) run_op(&g->ops[i]); return 0; }
+int fl_graph_destroy(void *ge) { mock_graph *g = ge; if (g) { free(g->ops); free(g); } return 0; }
+
+static int mock_capturing(void) { return g_capture != NULL; }
+static void mock_record_deq(int type, const void *W, size_t wrs, int K, const int32_t *ids, int n, float *dst, size_t drs) {
+    mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_DEQ; o.dq.type = type; o.dq.W = W; o.dq.wrs = wrs; o.dq.K = K; o.dq.ids = ids; o.dq.n = n; o.dq.dst = dst; o.dq.drs = drs; record(&o);
 }
