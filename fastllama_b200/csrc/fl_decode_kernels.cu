@@ -175,17 +175,24 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
     }
 
     // ------------------------------ consumers: prologue ------------------------------
-    // Build the q8_0 activation vector in shared memory.  Thread t of the CW*32 consumer threads owns
-    // elements t, t + NT, ...; a warp's 32 lanes therefore always hold one whole 32-element block.
+    // Build the q8_0 activation vector in shared memory.  Each thread owns float4 groups i, i + NT, ...
+    // (K/4 groups); 8 consecutive lanes hold one 32-element block, so amax / sum are 3-step shuffles.
+    // Loads go through the read-only path (__ldg) and are issued two iterations ahead of their use.
     const int NT = CW * 32;
     const int tid = threadIdx.x;                     // consumers are threads [0, NT)
     {
+        const int nvec = K >> 2;
+        const float4 *x4 = (const float4 *)A.x;
         float scale = 1.0f;
         if (A.pro == FL_PRO_RMSNORM) {
             double acc = 0.0;
-            for (int e = tid; e < K; e += NT) {
-                const float v = A.x[e];
-                acc += (double)__fmul_rn(v, v);
+#pragma unroll 4
+            for (int i = tid; i < nvec; i += NT) {
+                const float4 v = __ldg(x4 + i);
+                acc += (double)__fmul_rn(v.x, v.x);
+                acc += (double)__fmul_rn(v.y, v.y);
+                acc += (double)__fmul_rn(v.z, v.z);
+                acc += (double)__fmul_rn(v.w, v.w);
             }
             acc = fl_warp_sum_d(acc);
             if (lane == 0) red[warp] = acc;
@@ -199,29 +206,60 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
             asm volatile("bar.sync 15, %0;" ::"r"(NT) : "memory");
             scale = ((float *)(red + 16))[0];
         }
-        for (int e = tid; e < K; e += NT) {           // K is a multiple of 32, NT too: whole warps stay together
-            float v;
-            if (A.pro == FL_PRO_RMSNORM) {
-                v = __fmul_rn(A.gamma[e], __fmul_rn(A.x[e], scale));
-                if (A.normed_out && blockIdx.x == 0) A.normed_out[e] = v;
-            } else if (A.pro == FL_PRO_SILUMUL) {
-                const uint16_t h = __half_as_ushort(__float2half_rn(A.x[e]));
-                v = __fmul_rn(__half2float(__ushort_as_half(A.silu_tab[h])), A.b[e]);
-            } else {
-                v = A.x[e];
+        const float4 *g4 = (const float4 *)A.gamma, *b4 = (const float4 *)A.b;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // software pipeline: the loads of group i + NT are in flight while group i is quantised
+        int i = warp * 32 + lane;                    // == tid; whole warps advance together (uniform trip count)
+        float4 xv = (i < nvec) ? __ldg(x4 + i) : zero4;
+        float4 ov = zero4;
+        if (A.pro == FL_PRO_RMSNORM) ov = (i < nvec) ? __ldg(g4 + i) : zero4;
+        else if (A.pro == FL_PRO_SILUMUL) ov = (i < nvec) ? __ldg(b4 + i) : zero4;
+        for (int base = warp * 32; base < nvec; base += NT) {
+            const int inext = i + NT;
+            float4 xn = zero4, on = zero4;
+            if (base + NT < nvec) {
+                xn = (inext < nvec) ? __ldg(x4 + inext) : zero4;
+                if (A.pro == FL_PRO_RMSNORM) on = (inext < nvec) ? __ldg(g4 + inext) : zero4;
+                else if (A.pro == FL_PRO_SILUMUL) on = (inext < nvec) ? __ldg(b4 + inext) : zero4;
             }
-            const float amax = fl_warp_max(fabsf(v));
+            float v[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float o[4] = {ov.x, ov.y, ov.z, ov.w};
+            if (A.pro == FL_PRO_RMSNORM) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) v[c] = __fmul_rn(o[c], __fmul_rn(v[c], scale));
+                if (A.normed_out && blockIdx.x == 0 && i < nvec) ((float4 *)A.normed_out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+            } else if (A.pro == FL_PRO_SILUMUL) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const uint16_t h = __half_as_ushort(__float2half_rn(v[c]));
+                    v[c] = __fmul_rn(__half2float(__ushort_as_half(__ldg(A.silu_tab + h))), o[c]);
+                }
+            }
+            float amax = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
             const float d = __fdiv_rn(amax, 127.f);
             const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
-            int q = __float2int_rn(__fmul_rn(v, id));
-            q = max(-128, min(127, q));
-            const int sum = fl_warp_sum_i(q);
-            fl_block_q8_0 *yb = ysm + (e >> 5);
-            yb->qs[lane] = (int8_t)q;
-            if (lane == 0) {
-                yb->d = d;
-                yb->s = __fmul_rn(d, (float)sum);
+            int q[4], sum = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                q[c] = max(-128, min(127, __float2int_rn(__fmul_rn(v[c], id))));
+                sum += q[c];
             }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+            if (i < nvec) {
+                fl_block_q8_0 *yb = ysm + (i >> 3);
+                const uint32_t packed = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[1] & 0xFF) << 8) | ((uint32_t)(q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
+                ((uint32_t *)yb->qs)[i & 7] = packed;
+                if ((i & 7) == 0) {
+                    yb->d = d;
+                    yb->s = __fmul_rn(d, (float)sum);
+                }
+            }
+            xv = xn; ov = on; i = inext;
         }
         asm volatile("bar.sync 15, %0;" ::"r"(NT) : "memory");
     }
@@ -469,7 +507,7 @@ int flk_mv_fused(cudaStream_t st, const fl_mv_args *args) {
         off_rowbuf = (off_rowbuf + 127) & ~(size_t)127;
         off = off_rowbuf + (size_t)S * R * kparts * sizeof(float);
         off = (off + 127) & ~(size_t)127;
-        if (off + (size_t)S * stage_bytes <= (size_t)g_smem_optin) break;
+        if (off + (size_t)S * stage_bytes <= (size_t)g_smem_optin - 1024) break;       // 1 KB left for static shared memory
     }
     if (TG > S) TG = S;
     const int CW = kparts * G * TG;
@@ -485,7 +523,9 @@ int flk_mv_fused(cudaStream_t st, const fl_mv_args *args) {
     static bool attr_set[2][FD_NBL + 1] = {{false}};
     const int ti = a.type == FL_TYPE_Q4_0 ? 0 : 1;
     if (!attr_set[ti][nfull]) {
-        FL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+        cudaFuncAttributes fa;
+        FL_CUDA_OK(cudaFuncGetAttributes(&fa, kern));
+        FL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin - (int)fa.sharedSizeBytes));
         attr_set[ti][nfull] = true;
     }
     kern<<<g_sm, (CW + 1) * 32, smem_bytes, st>>>(p);

@@ -46,11 +46,11 @@ def make_weights(hp: HParams, wtype: int, quantize, seed: int = 0) -> dict:
     for i in range(hp.n_layer):
         vec(f"layers.{i}.attention_norm.weight", hp.n_embd)
         for w in ("wq", "wk", "wv", "wo"):
-            mat(f"layers.{i}.attention.{w}.weight", hp.n_embd, hp.n_embd, 0.08)
+            mat(f"layers.{i}.attention.{w}.weight", hp.n_embd, hp.n_embd, 0.04)
         vec(f"layers.{i}.ffn_norm.weight", hp.n_embd)
-        mat(f"layers.{i}.feed_forward.w1.weight", hp.n_embd, hp.n_ff, 0.08)
-        mat(f"layers.{i}.feed_forward.w2.weight", hp.n_ff, hp.n_embd, 0.08)
-        mat(f"layers.{i}.feed_forward.w3.weight", hp.n_embd, hp.n_ff, 0.08)
+        mat(f"layers.{i}.feed_forward.w1.weight", hp.n_embd, hp.n_ff, 0.04)
+        mat(f"layers.{i}.feed_forward.w2.weight", hp.n_ff, hp.n_embd, 0.04)
+        mat(f"layers.{i}.feed_forward.w3.weight", hp.n_embd, hp.n_ff, 0.04)
     return out
 
 
