@@ -83,14 +83,6 @@ __device__ __forceinline__ void fd_block(const uint8_t *blk, const fd_yprep &yp,
 
 #define FD_NBL 4
 #define FD_MAX_THREADS 576
-#define FD_MAX_TILES 96
-#define FD_MAX_VEC_PER_THREAD 24      // K <= 512 * 24 = 12288 ... larger K uses more passes (handled by loop)
-
-struct fd_tile {
-    uint32_t src_off_lo, src_off_hi;   // byte offset from seg W base
-    int row0;                          // first row, relative to its segment
-    short rows, seg;
-};
 
 // device-side copy of the launch description (fl_mv_args) plus the ring geometry
 struct fd_params {
@@ -99,73 +91,91 @@ struct fd_params {
     uint32_t row_bytes;
     int R, S, kparts, G, TG, P;
     uint32_t stage_bytes;
-    uint32_t off_tiles, off_y, off_red, off_rowbuf, off_stage0;
+    uint32_t off_y, off_red, off_rowbuf, off_cnt, off_stage0;
     int mtot;
 };
+
+// The CTA's slice [r0, r1) of the concatenated row space, cut per matrix ("segment") into tiles of
+// at most R rows that never straddle a matrix.  Everything is closed-form, so the producer can start
+// issuing copies a few cycles after launch and nobody builds a table.
+struct fd_slice {
+    int f0, f1, f2;          // per segment: first owned row, relative to the segment
+    int n0, n1, n2;          // rows owned
+    int t0, t1;              // cumulative tile counts after segment 0 and 1
+    int ntiles;
+};
+__device__ __forceinline__ void fd_seg_span(int r0, int r1, int sbase, int rows_sg, int &first, int &n) {
+    const int lo = max(r0, sbase), hi = min(r1, sbase + rows_sg);
+    first = lo - sbase;
+    n = max(0, hi - lo);
+}
+__device__ __forceinline__ fd_slice fd_make_slice(const fl_mv_args &A, int mtot, int R) {
+    fd_slice sl;
+    const int half = mtot / 2;             // even split points keep rope pairs in one CTA
+    const int r0 = 2 * (int)(((long)half * blockIdx.x) / gridDim.x);
+    const int r1 = 2 * (int)(((long)half * (blockIdx.x + 1)) / gridDim.x);
+    const int m0 = A.seg_rows[0], m1 = A.nseg > 1 ? A.seg_rows[1] : 0, m2 = A.nseg > 2 ? A.seg_rows[2] : 0;
+    fd_seg_span(r0, r1, 0, m0, sl.f0, sl.n0);
+    fd_seg_span(r0, r1, m0, m1, sl.f1, sl.n1);
+    fd_seg_span(r0, r1, m0 + m1, m2, sl.f2, sl.n2);
+    sl.t0 = (sl.n0 + R - 1) / R;
+    sl.t1 = sl.t0 + (sl.n1 + R - 1) / R;
+    sl.ntiles = sl.t1 + (sl.n2 + R - 1) / R;
+    return sl;
+}
+__device__ __forceinline__ void fd_tile_of(const fd_slice &sl, int R, int t, int &seg, int &row0, int &rows) {
+    seg = (t < sl.t0) ? 0 : (t < sl.t1) ? 1 : 2;
+    const int j = t - (seg == 0 ? 0 : seg == 1 ? sl.t0 : sl.t1);
+    const int first = seg == 0 ? sl.f0 : seg == 1 ? sl.f1 : sl.f2;
+    const int n = seg == 0 ? sl.n0 : seg == 1 ? sl.n1 : sl.n2;
+    row0 = first + j * R;
+    rows = min(R, n - j * R);
+}
 
 template <int TYPE, int NFULL>
 __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params prm) {
     constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = (uint64_t *)smem;
-    fd_tile *tiles = (fd_tile *)(smem + prm.off_tiles);
     fl_block_q8_0 *ysm = (fl_block_q8_0 *)(smem + prm.off_y);
     double *red = (double *)(smem + prm.off_red);            // [16] block-reduce scratch + [1] scale slot
-    float *rowbuf = (float *)(smem + prm.off_rowbuf);        // [S][R][kparts]
+    float *rowbuf = (float *)(smem + prm.off_rowbuf);        // [S][R][kparts] per-part row sums
+    int *cnt = (int *)(smem + prm.off_cnt);                  // [S][R] arrival counters of the combine groups
     uint8_t *stage0 = smem + prm.off_stage0;
-    __shared__ int s_ntiles;
 
     const fl_mv_args &A = prm.a;
     const int S = prm.S, R = prm.R, kparts = prm.kparts, G = prm.G, TG = prm.TG;
     const int WPG = kparts * G, CW = WPG * TG;
+    const int NT = CW * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K = prm.nb * 32;
-
-    // this CTA's slice of the concatenated row space, kept even so rope pairs never split
-    const int half = prm.mtot / 2;
-    const int r0 = 2 * (int)(((long)half * blockIdx.x) / gridDim.x);
-    const int r1 = 2 * (int)(((long)half * (blockIdx.x + 1)) / gridDim.x);
-
+    const fd_slice sl = fd_make_slice(A, prm.mtot, R);
+    const int ntiles = sl.ntiles;
     const uint32_t bar0 = fl_smem_u32(bars);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; s++) {
-            fl_mbar_init(bar0 + 8u * s, 1);
-            fl_mbar_init(bar0 + 8u * (S + s), WPG);
-        }
-        fl_mbar_fence_init();
-        // tile table: tiles never straddle a matrix
-        int n = 0, r = r0, sbase = 0;
-        for (int sg = 0; sg < A.nseg && r < r1; sg++) {
-            const int send = sbase + A.seg_rows[sg];
-            while (r < r1 && r < send && n < FD_MAX_TILES) {
-                const int rows = min(R, min(r1, send) - r);
-                const uint64_t off = (uint64_t)(r - sbase) * prm.row_bytes;
-                tiles[n].src_off_lo = (uint32_t)off;
-                tiles[n].src_off_hi = (uint32_t)(off >> 32);
-                tiles[n].row0 = r - sbase;
-                tiles[n].rows = (short)rows;
-                tiles[n].seg = (short)sg;
-                n++;
-                r += rows;
-            }
-            sbase = send;
-        }
-        s_ntiles = n;
-    }
-    __syncthreads();
-    const int ntiles = s_ntiles;
 
     if (warp == CW) {
         // ------------------------------ producer ------------------------------
+        // Initialises the mbarriers itself and starts streaming weights immediately: the weight stream
+        // does not depend on anything the consumers compute in their prologue.
+        if (lane == 0) {
+            for (int s = 0; s < S; s++) {
+                fl_mbar_init(bar0 + 8u * s, 1);
+                fl_mbar_init(bar0 + 8u * (S + s), WPG);
+            }
+            fl_mbar_fence_init();
+        }
+        __syncwarp();
+        asm volatile("bar.arrive 14, %0;" ::"r"(NT + 32) : "memory");      // consumers wait on 14 before touching the mbarriers
         if (lane == 0) {
             const uint64_t pol = fl_policy_evict_first();
             int s = 0;
             uint32_t ph = 1;
             for (int t = 0; t < ntiles; t++) {
+                int seg, row0, rows;
+                fd_tile_of(sl, R, t, seg, row0, rows);
                 fl_mbar_wait(bar0 + 8u * (S + s), ph);
-                const fd_tile tl = tiles[t];
-                const uint32_t bytes = (uint32_t)tl.rows * prm.row_bytes;
-                const uint8_t *src = (const uint8_t *)A.seg_w[tl.seg] + (((uint64_t)tl.src_off_hi << 32) | tl.src_off_lo);
+                const uint32_t bytes = (uint32_t)rows * prm.row_bytes;
+                const uint8_t *src = (const uint8_t *)A.seg_w[seg] + (size_t)row0 * prm.row_bytes;
                 fl_mbar_expect_tx(bar0 + 8u * s, bytes);
                 fl_bulk_g2s_hint(fl_smem_u32(stage0 + (size_t)s * prm.stage_bytes), src, bytes, bar0 + 8u * s, pol);
                 if (++s == S) { s = 0; ph ^= 1u; }
@@ -174,12 +184,13 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
         return;
     }
 
+    const int tid = threadIdx.x;                     // consumers are threads [0, NT)
+    for (int i = tid; i < S * R; i += NT) cnt[i] = 0;
+
     // ------------------------------ consumers: prologue ------------------------------
     // Build the q8_0 activation vector in shared memory.  Each thread owns float4 groups i, i + NT, ...
     // (K/4 groups); 8 consecutive lanes hold one 32-element block, so amax / sum are 3-step shuffles.
     // Loads go through the read-only path (__ldg) and are issued two iterations ahead of their use.
-    const int NT = CW * 32;
-    const int tid = threadIdx.x;                     // consumers are threads [0, NT)
     {
         const int nvec = K >> 2;
         const float4 *x4 = (const float4 *)A.x;
@@ -286,17 +297,23 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
     }
 
     // ------------------------------ consumers: main loop ------------------------------
-    const bool staged = (kparts > 1) || (A.epi == FL_EPI_QKV);      // results go through smem + a tile-group barrier
-    const int n_past = (A.epi == FL_EPI_QKV) ? *A.n_past : 0;
+    // Results that need more than one warp (K split over `kparts` warps, or a rope pair computed by two
+    // warps) are combined by whichever warp arrives last at a per-group counter, always summing the
+    // parts in index order -- deterministic, and no barrier in the loop.
+    asm volatile("bar.sync 14, %0;" ::"r"(NT + 32) : "memory");          // mbarriers are initialised
+    const bool pair = (A.epi == FL_EPI_QKV);
+    const bool staged = (kparts > 1) || pair;
+    const int target = pair ? 2 * kparts : kparts;
+    const int n_past = pair ? *A.n_past : 0;
     int s = tg % S;
     uint32_t ph = (uint32_t)(tg / S) & 1u;
     const int s_step = TG % S, u_step = TG / S;
     for (int t = tg; t < ntiles; t += TG) {
+        int seg, row0, rows;
+        fd_tile_of(sl, R, t, seg, row0, rows);
         fl_mbar_wait(bar0 + 8u * s, ph);
-        const fd_tile tl = tiles[t];
         const uint8_t *tile = stage0 + (size_t)s * prm.stage_bytes;
-        const int rows = tl.rows;
-        float *dseg = A.seg_dst[tl.seg];
+        float *dseg = A.seg_dst[seg];
         for (int rr = g; rr < rows; rr += G) {
             const uint8_t *wrow = tile + (size_t)rr * prm.row_bytes + (size_t)(b0 + lane) * BB;
             float acc = 0.0f, accm = 0.0f;
@@ -308,44 +325,45 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
             float tot = fl_warp_sum(acc);
             if (TYPE == FL_TYPE_Q4_1) tot = __fadd_rn(tot, fl_warp_sum(accm));
             if (lane == 0) {
-                if (staged) rowbuf[((size_t)s * R + rr) * kparts + p] = tot;
-                else {
-                    const int row = tl.row0 + rr;
+                const int row = row0 + rr;
+                if (!staged) {
                     dseg[row] = (A.epi == FL_EPI_RESADD) ? __fadd_rn(tot, A.res[row]) : tot;
+                } else {
+                    volatile float *rb = rowbuf + (size_t)s * R * kparts;
+                    rb[rr * kparts + p] = tot;
+                    __threadfence_block();
+                    const int gid = pair ? (rr >> 1) : rr;
+                    const int old = atomicAdd(&cnt[s * R + gid], 1);
+                    if (old == target - 1) {                                  // last arriver combines
+                        cnt[s * R + gid] = 0;
+                        __threadfence_block();
+                        if (pair) {
+                            const int ra = gid << 1;
+                            float x0 = rb[ra * kparts], x1 = rb[(ra + 1) * kparts];
+                            for (int q = 1; q < kparts; q++) { x0 = __fadd_rn(x0, rb[ra * kparts + q]); x1 = __fadd_rn(x1, rb[(ra + 1) * kparts + q]); }
+                            const int r2 = row0 + ra;                            // even row of the pair
+                            if (seg < 2) {
+                                const int ip = (r2 % A.head_dim) >> 1;
+                                const float2 cs = ((const float2 *)A.rope_cs)[(size_t)n_past * (A.head_dim >> 1) + ip];
+                                const float y0 = __fmaf_rn(x0, cs.x, -__fmul_rn(x1, cs.y));
+                                const float y1 = __fmaf_rn(x0, cs.y, __fmul_rn(x1, cs.x));
+                                float *o = (seg == 0) ? (dseg + r2) : (A.kcache + (size_t)n_past * A.n_embd + r2);
+                                o[0] = y0; o[1] = y1;
+                            } else {
+                                A.vcache[(size_t)r2 * A.n_ctx + n_past] = x0;
+                                A.vcache[(size_t)(r2 + 1) * A.n_ctx + n_past] = x1;
+                            }
+                        } else {
+                            float tsum = rb[rr * kparts];
+                            for (int q = 1; q < kparts; q++) tsum = __fadd_rn(tsum, rb[rr * kparts + q]);
+                            dseg[row] = (A.epi == FL_EPI_RESADD) ? __fadd_rn(tsum, A.res[row]) : tsum;
+                        }
+                    }
                 }
             }
         }
         __syncwarp();
         if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));
-        if (staged) {
-            asm volatile("bar.sync %0, %1;" ::"r"(tg + 1), "r"(WPG * 32) : "memory");
-            const int tloc = (int)threadIdx.x - tg * WPG * 32;
-            if (A.epi == FL_EPI_QKV) {
-                if (tloc < rows / 2) {                                   // one thread per adjacent row pair
-                    const float *p0 = rowbuf + ((size_t)s * R + 2 * tloc) * kparts;
-                    float x0 = p0[0], x1 = p0[kparts];
-                    for (int q = 1; q < kparts; q++) { x0 = __fadd_rn(x0, p0[q]); x1 = __fadd_rn(x1, p0[kparts + q]); }
-                    const int row = tl.row0 + 2 * tloc;                  // even
-                    if (tl.seg < 2) {
-                        const int ip = (row % A.head_dim) >> 1;
-                        const float2 cs = ((const float2 *)A.rope_cs)[(size_t)n_past * (A.head_dim >> 1) + ip];
-                        const float y0 = __fmaf_rn(x0, cs.x, -__fmul_rn(x1, cs.y));
-                        const float y1 = __fmaf_rn(x0, cs.y, __fmul_rn(x1, cs.x));
-                        float *o = (tl.seg == 0) ? (dseg + row) : (A.kcache + (size_t)n_past * A.n_embd + row);
-                        o[0] = y0; o[1] = y1;
-                    } else {
-                        A.vcache[(size_t)row * A.n_ctx + n_past] = x0;
-                        A.vcache[(size_t)(row + 1) * A.n_ctx + n_past] = x1;
-                    }
-                }
-            } else if (tloc < rows) {
-                const float *pp = rowbuf + ((size_t)s * R + tloc) * kparts;
-                float tot = pp[0];
-                for (int q = 1; q < kparts; q++) tot = __fadd_rn(tot, pp[q]);
-                const int row = tl.row0 + tloc;
-                dseg[row] = (A.epi == FL_EPI_RESADD) ? __fadd_rn(tot, A.res[row]) : tot;
-            }
-        }
         s += s_step; ph ^= (uint32_t)(u_step & 1);
         if (s >= S) { s -= S; ph ^= 1u; }
     }
@@ -454,7 +472,7 @@ int flk_mv_fused_supported(int type, int K, int mtot) {
     if (K <= 0 || K % 64 != 0) return 0;
     const size_t row_bytes = (size_t)(K / 32) * fl_block_bytes(type);
     if (row_bytes % 16 != 0) return 0;
-    if ((K / 32 + 127) / 128 > 8) return 0;
+    if (K / 32 > 8 * 128) return 0;
     if (fd_query() != 0) return 0;
     return mtot >= 2 && mtot % 2 == 0;
 }
@@ -475,9 +493,11 @@ int flk_mv_fused(cudaStream_t st, const fl_mv_args *args) {
     const int bb = fl_block_bytes(a.type);
     const int nb = a.K / 32;
     const size_t row_bytes = (size_t)nb * bb;
-    const int kparts = (nb + 127) / 128;
+    int kparts = 1;
+    while (kparts * 128 < nb) kparts *= 2;                      // power of two so that 16 consumer warps divide evenly
     const int P = (nb + kparts - 1) / kparts;
     const int last = nb - (kparts - 1) * P;
+    FL_REQUIRE(last > 0, "mv_fused: K=%d splits badly", a.K);
     int nfull = std::min(P, last) / 32;
     if (nfull > FD_NBL) nfull = FD_NBL;
     static int tile_target = -1;
@@ -497,27 +517,23 @@ int flk_mv_fused(cudaStream_t st, const fl_mv_args *args) {
     const size_t stage_bytes = (size_t)R * row_bytes;
     const size_t y_bytes = (size_t)nb * 40;
     int S = 16;
-    size_t off_tiles = 0, off_y = 0, off_red = 0, off_rowbuf = 0, off = 0;
+    size_t off_y = 0, off_red = 0, off_rowbuf = 0, off_cnt = 0, off = 0;
     for (;; S--) {
         FL_REQUIRE(S >= 2, "mv_fused: shape does not fit shared memory (K=%d)", a.K);
-        off_tiles = ((size_t)(2 * S) * 8 + 127) & ~(size_t)127;
-        off_y = (off_tiles + FD_MAX_TILES * sizeof(fd_tile) + 127) & ~(size_t)127;
+        off_y = ((size_t)(2 * S) * 8 + 127) & ~(size_t)127;
         off_red = (off_y + y_bytes + 127) & ~(size_t)127;
-        off_rowbuf = off_red + 17 * sizeof(double) + 8;
-        off_rowbuf = (off_rowbuf + 127) & ~(size_t)127;
-        off = off_rowbuf + (size_t)S * R * kparts * sizeof(float);
-        off = (off + 127) & ~(size_t)127;
+        off_rowbuf = (off_red + 17 * sizeof(double) + 8 + 127) & ~(size_t)127;
+        off_cnt = (off_rowbuf + (size_t)S * R * kparts * sizeof(float) + 127) & ~(size_t)127;
+        off = (off_cnt + (size_t)S * R * sizeof(int) + 127) & ~(size_t)127;
         if (off + (size_t)S * stage_bytes <= (size_t)g_smem_optin - 1024) break;       // 1 KB left for static shared memory
     }
     if (TG > S) TG = S;
     const int CW = kparts * G * TG;
     FL_REQUIRE((CW + 1) * 32 <= FD_MAX_THREADS, "mv_fused: too many warps");
-    const int max_tiles_cta = (mtot / g_sm + 2 + R - 1) / R + a.nseg + 1;
-    FL_REQUIRE(max_tiles_cta <= FD_MAX_TILES, "mv_fused: %d tiles per CTA exceed the tile table", max_tiles_cta);
     p.nb = nb; p.row_bytes = (uint32_t)row_bytes; p.R = R; p.S = S; p.kparts = kparts; p.G = G; p.TG = TG; p.P = P;
     p.stage_bytes = (uint32_t)stage_bytes;
-    p.off_tiles = (uint32_t)off_tiles; p.off_y = (uint32_t)off_y; p.off_red = (uint32_t)off_red;
-    p.off_rowbuf = (uint32_t)off_rowbuf; p.off_stage0 = (uint32_t)off;
+    p.off_y = (uint32_t)off_y; p.off_red = (uint32_t)off_red;
+    p.off_rowbuf = (uint32_t)off_rowbuf; p.off_cnt = (uint32_t)off_cnt; p.off_stage0 = (uint32_t)off;
     const size_t smem_bytes = off + (size_t)S * stage_bytes;
     fd_kernel_t kern = fd_kernel(a.type, nfull);
     static bool attr_set[2][FD_NBL + 1] = {{false}};

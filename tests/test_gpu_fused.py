@@ -46,7 +46,7 @@ def rope_ref(v, pos, hd):
 
 
 @pytest.mark.parametrize("t", [GGML_TYPE_Q4_0, GGML_TYPE_Q4_1])
-@pytest.mark.parametrize("k,rows", [(64, (2,)), (256, (6, 10)), (4096, (4096,)), (4096, (11008, 11008)), (11008, (4096,)), (5120, (5120, 5120, 5120))])
+@pytest.mark.parametrize("k,rows", [(128, (2,)), (256, (6, 10)), (4096, (4096,)), (4096, (11008, 11008)), (11008, (4096,)), (5120, (5120, 5120, 5120))])
 @pytest.mark.parametrize("pro", [0, 1, 2])
 def test_mv_fused_prologues_and_segments(fl, oracle, t, k, rows, pro):
     from fastllama_b200.cuda_abi import EPI_RESADD, EPI_STORE, FlMvArgs
