@@ -152,6 +152,10 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
     const fd_slice sl = fd_make_slice(A, prm.mtot, R);
     const int ntiles = sl.ntiles;
     const uint32_t bar0 = fl_smem_u32(bars);
+    // Programmatic dependent launch: let the next kernel of the stream start as soon as SMs free up
+    // (its producer streams its own weights while we finish); nothing below reads or writes an
+    // activation before griddepcontrol.wait, which returns only when the previous kernel has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == CW) {
         // ------------------------------ producer ------------------------------
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
 
     const int tid = threadIdx.x;                     // consumers are threads [0, NT)
     for (int i = tid; i < S * R; i += NT) cnt[i] = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the producer warp never waits: weights depend on nothing
 
     // ------------------------------ consumers: prologue ------------------------------
     // Build the q8_0 activation vector in shared memory.  Each thread owns float4 groups i, i + NT, ...
@@ -383,22 +388,38 @@ struct fd_attn_params {
     const uint16_t *exp_tab;
 };
 
+// The KV cache of a layer was last touched one token ago and has long left L2 (4 GB of weights went
+// through since), so this kernel is bound by DRAM round trips, not bytes: every phase is written to
+// have many independent loads in flight (4 positions per warp iteration for the scores, one output
+// dimension per thread with 4 independent float4 streams for P*V).
 __global__ void __launch_bounds__(256) k_attn_decode(const fd_attn_params P) {
     extern __shared__ float sc[];                   // [n_ctx] scores / probabilities
     __shared__ double redd[8];
     __shared__ float redf[8];
+    __shared__ float part[256];
     const int h = blockIdx.x, hd = P.head_dim;
-    const int n_pos = *P.n_past + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");              // q / K / V of this step come from the previous kernel
+    const int n_pos = *P.n_past + 1;
     const float *q = P.q + (size_t)h * hd;
 
     // scores_j = scale * <K_j, q>   (ggml_mul_mat K,Q then ggml_scale; the mask is a no-op for N = 1)
-    for (int j = warp; j < n_pos; j += nw) {
-        const float *k = P.kcache + (size_t)j * P.n_embd + (size_t)h * hd;
-        float acc = 0.f;
-        for (int e = lane; e < hd; e += 32) acc = __fmaf_rn(k[e], q[e], acc);
-        acc = fl_warp_sum(acc);
-        if (lane == 0) sc[j] = __fmul_rn(acc, P.scale);
+    for (int j0 = warp * 4; j0 < n_pos; j0 += nw * 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int e = lane; e < hd; e += 32) {
+            const float qe = q[e];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = min(j0 + u, n_pos - 1);                 // clamp: loads stay in range, result discarded below
+                acc[u] = __fmaf_rn(P.kcache[(size_t)j * P.n_embd + (size_t)h * hd + e], qe, acc[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float a = fl_warp_sum(acc[u]);
+            if (lane == 0 && j0 + u < n_pos) sc[j0 + u] = __fmul_rn(a, P.scale);
+        }
     }
     __syncthreads();
     // soft_max with the fp16 exp table (reference lib/ggml.c:8521-8589)
@@ -424,13 +445,30 @@ __global__ void __launch_bounds__(256) k_attn_decode(const fd_attn_params P) {
     const float inv = (float)(1.0 / tot);
     for (int j = threadIdx.x; j < n_pos; j += blockDim.x) sc[j] = __fmul_rn(sc[j], inv);
     __syncthreads();
-    // out_d = sum_j p_j * V[d][j]   (ggml_mul_mat V, soft_max)
-    for (int d = warp; d < hd; d += nw) {
+    // out_d = sum_j p_j * V[d][j]   (ggml_mul_mat V, soft_max): thread (d, half) walks its row of V
+    const int npt = blockDim.x / hd;                               // threads per output dimension (2 for head_dim 128)
+    if (npt >= 1 && (int)threadIdx.x < npt * hd) {
+        const int d = threadIdx.x % hd, sub = threadIdx.x / hd;
         const float *v = P.vcache + ((size_t)h * hd + d) * P.n_ctx;
-        float acc = 0.f;
-        for (int j = lane; j < n_pos; j += 32) acc = __fmaf_rn(v[j], sc[j], acc);
-        acc = fl_warp_sum(acc);
-        if (lane == 0) P.out[(size_t)h * hd + d] = acc;
+        const int n4 = n_pos >> 2;                                  // whole float4 groups (rows are 16-B aligned: n_ctx % 4 == 0)
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int i = sub; i < n4; i += npt) {
+            const float4 vv = *(const float4 *)(v + 4 * i);
+            a0 = __fmaf_rn(vv.x, sc[4 * i + 0], a0);
+            a1 = __fmaf_rn(vv.y, sc[4 * i + 1], a1);
+            a2 = __fmaf_rn(vv.z, sc[4 * i + 2], a2);
+            a3 = __fmaf_rn(vv.w, sc[4 * i + 3], a3);
+        }
+        float acc = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+        if (sub == 0)
+            for (int j = 4 * n4; j < n_pos; j++) acc = __fmaf_rn(v[j], sc[j], acc);
+        part[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < hd) {
+        float acc = part[threadIdx.x];
+        for (int u = 1; u < npt; u++) acc = __fadd_rn(acc, part[threadIdx.x + u * hd]);
+        P.out[(size_t)h * hd + threadIdx.x] = acc;
     }
 }
 
@@ -445,6 +483,12 @@ static int fd_query() {
     FL_CUDA_OK(cudaDeviceGetAttribute(&g_sm, cudaDevAttrMultiProcessorCount, dev));
     FL_CUDA_OK(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     return 0;
+}
+
+static bool fd_use_pdl() {
+    static int v = -1;
+    if (v < 0) v = getenv("FASTLLAMA_B200_NO_PDL") ? 0 : 1;
+    return v != 0;
 }
 
 typedef void (*fd_kernel_t)(const fd_params);
@@ -544,7 +588,17 @@ int flk_mv_fused(cudaStream_t st, const fl_mv_args *args) {
         FL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin - (int)fa.sharedSizeBytes));
         attr_set[ti][nfull] = true;
     }
-    kern<<<g_sm, (CW + 1) * 32, smem_bytes, st>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g_sm);
+    cfg.blockDim = dim3((CW + 1) * 32);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = fd_use_pdl() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
     fl_count_launch();
     FL_CUDA_OK(cudaGetLastError());
     return 0;
@@ -562,7 +616,18 @@ int flk_attn_decode(cudaStream_t st, const float *q, const float *kcache, const 
         FL_CUDA_OK(cudaFuncSetAttribute(k_attn_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    k_attn_decode<<<n_head, 256, smem, st>>>(P);
+    FL_REQUIRE(n_ctx % 4 == 0 && P.head_dim <= 256, "attn_decode: n_ctx must be a multiple of 4 and head_dim <= 256");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_head);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute lattr[1];
+    lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lattr[0].val.programmaticStreamSerializationAllowed = fd_use_pdl() ? 1 : 0;
+    cfg.attrs = lattr;
+    cfg.numAttrs = 1;
+    FL_CUDA_OK(cudaLaunchKernelEx(&cfg, k_attn_decode, P));
     fl_count_launch();
     FL_CUDA_OK(cudaGetLastError());
     return 0;
