@@ -333,9 +333,13 @@ extern "C" int fl_dev_attn_decode(const float *q, const float *kcache, const flo
     FL_NEED_INIT();
     return flk_attn_decode(g.stream, q, kcache, vcache, out, n_past, n_embd, n_head, n_ctx, scale, g.tab_exp);
 }
+// a captured graph remembers how many of our kernels it holds, so replays keep fl_launch_count honest
+struct fl_graph_handle { cudaGraphExec_t exec; uint64_t kernels; };
+static uint64_t g_capture_start = 0;
 extern "C" int fl_graph_begin_capture(void) {
     FL_NEED_INIT();
     FL_CUDA_OK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+    g_capture_start = g.launches;
     return 0;
 }
 extern "C" int fl_graph_end_capture(void **graph_exec_out) {
@@ -349,17 +353,24 @@ extern "C" int fl_graph_end_capture(void **graph_exec_out) {
         fl_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
         return -1;
     }
-    *graph_exec_out = (void *)exec;
+    fl_graph_handle *h = new fl_graph_handle{exec, g.launches - g_capture_start};
+    g.launches = g_capture_start;                 // recorded, not executed
+    *graph_exec_out = (void *)h;
     return 0;
 }
 extern "C" int fl_graph_launch(void *graph_exec) {
     FL_NEED_INIT();
-    FL_CUDA_OK(cudaGraphLaunch((cudaGraphExec_t)graph_exec, g.stream));
-    fl_count_launch();
+    fl_graph_handle *h = (fl_graph_handle *)graph_exec;
+    FL_CUDA_OK(cudaGraphLaunch(h->exec, g.stream));
+    g.launches += h->kernels;
     return 0;
 }
 extern "C" int fl_graph_destroy(void *graph_exec) {
-    if (graph_exec) FL_CUDA_OK(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    fl_graph_handle *h = (fl_graph_handle *)graph_exec;
+    if (h) {
+        FL_CUDA_OK(cudaGraphExecDestroy(h->exec));
+        delete h;
+    }
     return 0;
 }
 
