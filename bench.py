@@ -185,6 +185,18 @@ def main():
 
     fl = FlCuda()                                     # fails loudly without the CUDA library / a B200
     props = fl.device_props()
+    tp = world > 1 and not os.environ.get("FASTLLAMA_BENCH_REPLICAS")
+    if tp:
+        # tensor parallelism: one NCCL communicator over all ranks; rank 0's unique id travels by torch.distributed
+        import torch
+
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            raw = C.create_string_buffer(128)
+            fl.check(fl.lib.fl_comm_unique_id(raw))
+            idbuf = torch.tensor(list(raw.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idbuf, 0)
+        fl.check(fl.lib.fl_comm_init(rank, world, bytes(idbuf.cpu().numpy().tobytes())))
     if rank == 0:
         path = ensure_model(args.size, wtype, args.wtype)
     if dist:
@@ -259,7 +271,8 @@ def main():
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        wall, device_s, total_tokens = float(mx[0]), float(mx[1]), float(sm[2])
+        wall, device_s = float(mx[0]), float(mx[1])
+        total_tokens = float(n_tok) if tp else float(sm[2])        # tensor parallel: every rank decodes the SAME stream
     else:
         total_tokens = float(n_tok)
     if rank != 0:
@@ -284,10 +297,12 @@ def main():
     e2e = total_tokens / wall if wall > 0 else 0.0
     line = {
         "metric": "tokens/sec LLaMA-7B q4_0 decode (n_batch=1, greedy)", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": n_tok,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * device_s / n_tok if n_tok else None, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1000.0 * device_s / n_tok if n_tok else None, "higher_is_better": True,
+        "scaling": "strong" if (world > 1 and tp) else "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"LLaMA-{args.size} {args.wtype} greedy decode, n_batch=1, n_ctx=512, synthetic random weights N(0,0.02^2) seed 0",
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (tensor-parallel sharding not in this round)",
+                   "parallelism": "1 GPU" if world == 1 else (f"tp{world}: wq/wk/wv/w1/w3/output row-split, wo/w2 K-split, 2 NCCL all-reduces of n_embd fp32 per layer + 1 logits all-gather, in the CUDA graph"
+                                                               if tp else f"{world} independent replicas"),
                    "l2": "inputs (4.13 GB of weights per token) are 33x larger than L2; no flush needed",
                    "algorithmic_bytes_per_token": algo, "device": props["name"]},
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 32000 * 4 + 4096 * 4,

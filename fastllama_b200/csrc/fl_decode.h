@@ -7,4 +7,4 @@
 int flk_mv_fused_supported(int type, int K, int mtot);
 int flk_mv_fused(cudaStream_t st, const fl_mv_args *args);
 int flk_attn_decode(cudaStream_t st, const float *q, const float *kcache, const float *vcache, float *out, const int *n_past,
-                    int n_embd, int n_head, int n_ctx, float scale, const uint16_t *exp_tab);
+                    int k_row_stride, int n_head, int head_dim, int n_ctx, float scale, const uint16_t *exp_tab);

@@ -199,12 +199,14 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
     {
         const int nvec = K >> 2;
         const float4 *x4 = (const float4 *)A.x;
+        const float4 *xa4 = (const float4 *)A.xadd;          // optional residual add in front of everything
         float scale = 1.0f;
         if (A.pro == FL_PRO_RMSNORM) {
             double acc = 0.0;
 #pragma unroll 4
             for (int i = tid; i < nvec; i += NT) {
-                const float4 v = __ldg(x4 + i);
+                float4 v = __ldcg(x4 + i);
+                if (xa4) { const float4 w = __ldcg(xa4 + i); v.x = __fadd_rn(v.x, w.x); v.y = __fadd_rn(v.y, w.y); v.z = __fadd_rn(v.z, w.z); v.w = __fadd_rn(v.w, w.w); }
                 acc += (double)__fmul_rn(v.x, v.x);
                 acc += (double)__fmul_rn(v.y, v.y);
                 acc += (double)__fmul_rn(v.z, v.z);
@@ -226,7 +228,12 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         // software pipeline: the loads of group i + NT are in flight while group i is quantised
         int i = warp * 32 + lane;                    // == tid; whole warps advance together (uniform trip count)
-        float4 xv = (i < nvec) ? __ldg(x4 + i) : zero4;
+        auto load_x = [&](int idx) -> float4 {
+            float4 v = __ldcg(x4 + idx);
+            if (xa4) { const float4 w = __ldcg(xa4 + idx); v.x = __fadd_rn(v.x, w.x); v.y = __fadd_rn(v.y, w.y); v.z = __fadd_rn(v.z, w.z); v.w = __fadd_rn(v.w, w.w); }
+            return v;
+        };
+        float4 xv = (i < nvec) ? load_x(i) : zero4;
         float4 ov = zero4;
         if (A.pro == FL_PRO_RMSNORM) ov = (i < nvec) ? __ldg(g4 + i) : zero4;
         else if (A.pro == FL_PRO_SILUMUL) ov = (i < nvec) ? __ldg(b4 + i) : zero4;
@@ -234,12 +241,13 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
             const int inext = i + NT;
             float4 xn = zero4, on = zero4;
             if (base + NT < nvec) {
-                xn = (inext < nvec) ? __ldg(x4 + inext) : zero4;
+                xn = (inext < nvec) ? load_x(inext) : zero4;
                 if (A.pro == FL_PRO_RMSNORM) on = (inext < nvec) ? __ldg(g4 + inext) : zero4;
                 else if (A.pro == FL_PRO_SILUMUL) on = (inext < nvec) ? __ldg(b4 + inext) : zero4;
             }
             float v[4] = {xv.x, xv.y, xv.z, xv.w};
             const float o[4] = {ov.x, ov.y, ov.z, ov.w};
+            if (A.sum_out && blockIdx.x == 0 && i < nvec) ((float4 *)A.sum_out)[i] = xv;
             if (A.pro == FL_PRO_RMSNORM) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) v[c] = __fmul_rn(o[c], __fmul_rn(v[c], scale));
@@ -514,7 +522,7 @@ static fd_kernel_t fd_kernel(int type, int nfull) {
 
 int flk_mv_fused_supported(int type, int K, int mtot) {
     if (type != FL_TYPE_Q4_0 && type != FL_TYPE_Q4_1) return 0;
-    if (K <= 0 || K % 64 != 0) return 0;
+    if (K <= 0 || K % 32 != 0) return 0;
     const size_t row_bytes = (size_t)(K / 32) * fl_block_bytes(type);
     if (row_bytes % 16 != 0) return 0;
     if (K / 32 > 8 * 128) return 0;
@@ -531,13 +539,18 @@ int flk_mv_fused(cudaStream_t st, const fl_mv_args *args) {
         FL_REQUIRE(a.seg_rows[i] > 0 && a.seg_rows[i] % 2 == 0 && ((uintptr_t)a.seg_w[i] & 15) == 0, "mv_fused: bad segment %d", i);
         mtot += a.seg_rows[i];
     }
-    FL_REQUIRE(flk_mv_fused_supported(a.type, a.K, mtot), "mv_fused: unsupported shape type=%d K=%d M=%d", a.type, a.K, mtot);
+    FL_REQUIRE((a.type == FL_TYPE_Q4_0 || a.type == FL_TYPE_Q4_1) && a.K > 0 && a.K % 32 == 0 && mtot >= 2, "mv_fused: unsupported shape type=%d K=%d M=%d", a.type, a.K, mtot);
+    FL_REQUIRE(a.row_stride_bytes ? (a.row_stride_bytes % 16 == 0 && a.row_stride_bytes >= (size_t)(a.K / 32) * fl_block_bytes(a.type))
+                                  : flk_mv_fused_supported(a.type, a.K, mtot),
+               "mv_fused: rows of K=%d (stride %zu) are not 16-byte multiples", a.K, a.row_stride_bytes);
+    FL_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.xadd & 15) == 0 && ((uintptr_t)a.gamma & 15) == 0 && ((uintptr_t)a.b & 15) == 0 &&
+               ((uintptr_t)a.sum_out & 15) == 0 && ((uintptr_t)a.normed_out & 15) == 0, "mv_fused: activation vectors must be 16-byte aligned");
     fd_params p;
     p.a = a;
     p.mtot = mtot;
     const int bb = fl_block_bytes(a.type);
     const int nb = a.K / 32;
-    const size_t row_bytes = (size_t)nb * bb;
+    const size_t row_bytes = a.row_stride_bytes ? a.row_stride_bytes : (size_t)nb * bb;
     int kparts = 1;
     while (kparts * 128 < nb) kparts *= 2;                      // power of two so that 16 consumer warps divide evenly
     const int P = (nb + kparts - 1) / kparts;
@@ -606,10 +619,10 @@ int flk_mv_fused(cudaStream_t st, const fl_mv_args *args) {
 }
 
 int flk_attn_decode(cudaStream_t st, const float *q, const float *kcache, const float *vcache, float *out, const int *n_past,
-                    int n_embd, int n_head, int n_ctx, float scale, const uint16_t *exp_tab) {
+                    int n_embd, int n_head, int head_dim, int n_ctx, float scale, const uint16_t *exp_tab) {
     fd_attn_params P;
     P.q = q; P.kcache = kcache; P.vcache = vcache; P.out = out; P.n_past = n_past;
-    P.n_embd = n_embd; P.n_ctx = n_ctx; P.head_dim = n_embd / n_head; P.scale = scale; P.exp_tab = exp_tab;
+    P.n_embd = n_embd; P.n_ctx = n_ctx; P.head_dim = head_dim; P.scale = scale; P.exp_tab = exp_tab;
     const size_t smem = (size_t)n_ctx * sizeof(float);
     FL_REQUIRE(smem <= 200 * 1024, "attn_decode: n_ctx=%d too large for the score buffer", n_ctx);
     static size_t attr = 0;

@@ -2,6 +2,7 @@
 // include/fl_cuda.h.  No CPU compute path exists here: every entry point either runs the sm_100a
 // kernels or fails loudly.
 #include <cuda_fp16.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -329,10 +330,102 @@ extern "C" int fl_dev_mv_fused(const fl_mv_args *args) {
     return flk_mv_fused(g.stream, &a);
 }
 extern "C" int fl_dev_attn_decode(const float *q, const float *kcache, const float *vcache, float *out, const int *n_past,
-                                  int n_embd, int n_head, int n_ctx, float scale) {
+                                  int k_row_stride, int n_head, int head_dim, int n_ctx, float scale) {
     FL_NEED_INIT();
-    return flk_attn_decode(g.stream, q, kcache, vcache, out, n_past, n_embd, n_head, n_ctx, scale, g.tab_exp);
+    return flk_attn_decode(g.stream, q, kcache, vcache, out, n_past, k_row_stride, n_head, head_dim, n_ctx, scale, g.tab_exp);
 }
+// ---- tensor parallelism: K-slice packing + NCCL through dlopen ------------------------------------
+__global__ void k_pack_cols(const uint32_t *__restrict__ W, size_t src_stride_w, int M, size_t src_off_w, int words, uint32_t *__restrict__ dst,
+                            size_t dst_stride_w) {
+    const long total = (long)M * words;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long m = i / words, w = i % words;
+        dst[m * dst_stride_w + w] = W[m * src_stride_w + src_off_w + w];
+    }
+}
+extern "C" int fl_dev_pack_cols(int type, const void *W, size_t wrs, int M, int blk0, int nblk, void *dst, size_t drs) {
+    FL_NEED_INIT();
+    const int bb = fl_block_bytes(type);
+    FL_REQUIRE(bb > 0 && wrs % 4 == 0 && drs % 4 == 0 && drs >= (size_t)nblk * bb, "fl_dev_pack_cols: bad arguments");
+    const int words = nblk * bb / 4;
+    k_pack_cols<<<flk_sm_count() * 8, 256, 0, g.stream>>>((const uint32_t *)W, wrs / 4, M, (size_t)blk0 * bb / 4, words, (uint32_t *)dst, drs / 4);
+    fl_count_launch();
+    FL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+struct NcclId { char internal[128]; };
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    void *comm = nullptr;
+    int rank = 0, world = 1;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.lib) return 0;
+    // the soname resolves to whatever libnccl.so.2 the process already has (torch's bundled one under torchrun) or the system's
+    g_nccl.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    FL_REQUIRE(g_nccl.lib != nullptr, "cannot dlopen libnccl.so.2: %s", dlerror());
+    *(void **)&g_nccl.GetUniqueId = dlsym(g_nccl.lib, "ncclGetUniqueId");
+    *(void **)&g_nccl.CommInitRank = dlsym(g_nccl.lib, "ncclCommInitRank");
+    *(void **)&g_nccl.AllReduce = dlsym(g_nccl.lib, "ncclAllReduce");
+    *(void **)&g_nccl.AllGather = dlsym(g_nccl.lib, "ncclAllGather");
+    *(void **)&g_nccl.GetErrorString = dlsym(g_nccl.lib, "ncclGetErrorString");
+    FL_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.AllGather, "libnccl.so.2 lacks the expected symbols");
+    return 0;
+}
+#define FL_NCCL_OK(expr)                                                                                  \
+    do {                                                                                                  \
+        int _r = (expr);                                                                                  \
+        if (_r != 0) {                                                                                    \
+            fl_set_error("%s -> nccl error %d (%s)", #expr, _r, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
+            return -1;                                                                                    \
+        }                                                                                                 \
+    } while (0)
+extern "C" int fl_comm_unique_id(void *out128) {
+    if (nccl_load()) return -1;
+    FL_NCCL_OK(g_nccl.GetUniqueId(out128));
+    return 0;
+}
+extern "C" int fl_comm_init(int rank, int world, const void *id128) {
+    FL_NEED_INIT();
+    if (world <= 1) { g_nccl.rank = 0; g_nccl.world = 1; return 0; }
+    if (nccl_load()) return -1;
+    NcclId id;
+    memcpy(&id, id128, sizeof(id));
+    FL_NCCL_OK(g_nccl.CommInitRank(&g_nccl.comm, world, id, rank));
+    g_nccl.rank = rank;
+    g_nccl.world = world;
+    return 0;
+}
+extern "C" int fl_comm_rank(void) { return g_nccl.rank; }
+extern "C" int fl_comm_world(void) { return g_nccl.world; }
+extern "C" int fl_comm_allreduce_f32(float *buf, size_t n) {
+    FL_NEED_INIT();
+    if (g_nccl.world <= 1) return 0;
+    FL_NCCL_OK(g_nccl.AllReduce(buf, buf, n, /*ncclFloat32*/ 7, /*ncclSum*/ 0, g_nccl.comm, g.stream));
+    fl_count_launch();
+    return 0;
+}
+extern "C" int fl_comm_allgather_f32(const float *send, float *recv, size_t n_per_rank) {
+    FL_NEED_INIT();
+    if (g_nccl.world <= 1) {
+        if (send != recv) FL_CUDA_OK(cudaMemcpyAsync(recv, send, n_per_rank * sizeof(float), cudaMemcpyDeviceToDevice, g.stream));
+        return 0;
+    }
+    FL_NCCL_OK(g_nccl.AllGather(send, recv, n_per_rank, /*ncclFloat32*/ 7, g_nccl.comm, g.stream));
+    fl_count_launch();
+    return 0;
+}
+
 // a captured graph remembers how many of our kernels it holds, so replays keep fl_launch_count honest
 struct fl_graph_handle { cudaGraphExec_t exec; uint64_t kernels; };
 static uint64_t g_capture_start = 0;

@@ -893,6 +893,7 @@ struct LayerPlan {
     fl_mv_args qkv, wo, w13, w2;
     const float *q, *kcache, *vcache;
     float *att;
+    float *part1 = nullptr, *part2 = nullptr;   // tensor-parallel: partial sums of the K-split wo / w2, all-reduced in place
 };
 struct DecodePlan {
     int n_layer = 0, n_embd = 0, n_head = 0, n_ctx = 0, n_past = 0;
@@ -905,6 +906,9 @@ struct DecodePlan {
     float *emb_dst = nullptr;
     std::vector<LayerPlan> layers;
     fl_mv_args head;
+    int world = 1, heads_local = 0;             // tensor-parallel degree and heads per rank
+    float *logits_local = nullptr, *logits_all = nullptr;
+    int vocab_local = 0;
 };
 // Private device workspace of the decode step.  The compute arena cannot be used for intermediates:
 // its layout shifts from token to token (the K*Q score tensor grows with n_past), and the captured
@@ -912,6 +916,7 @@ struct DecodePlan {
 struct DecodeWs {
     int n_embd = 0, n_ff = 0, n_vocab = 0;
     float *xa = nullptr, *xb = nullptr, *q = nullptr, *att = nullptr, *ff = nullptr, *m1 = nullptr, *m3 = nullptr, *emb = nullptr, *logits = nullptr;
+    float *part1 = nullptr, *part2 = nullptr, *logits_local = nullptr;
     int32_t *d_tok = nullptr;
 };
 struct DecodeState {
@@ -921,6 +926,7 @@ struct DecodeState {
     int *d_npast = nullptr;
     int *h_scalars = nullptr;   // pinned: [0] n_past, [1] token id
     bool enabled = true, use_graph = true, inited = false;
+    bool tp_kv_sharded = false;   // tensor-parallel decode steps have written only this rank's heads into the KV cache
 };
 struct DecodeOutputs { void *logits_host = nullptr; size_t logits_bytes = 0; void *emb_host = nullptr; size_t emb_bytes = 0; int32_t token = 0; };
 DecodeState g_dec;
@@ -954,15 +960,33 @@ void mv_base(fl_mv_args &a, int type, int K) {
 void ensure_ws(DecodeWs &w, int n_embd, int n_ff, int n_vocab) {
     if (w.xa && w.n_embd == n_embd && w.n_ff == n_ff && w.n_vocab == n_vocab) return;
     if (w.xa) { FLC(fl_sync()); FLC(fl_dev_free(w.xa)); }
-    const size_t total = (size_t)n_embd * 6 + (size_t)n_ff * 2 + (size_t)n_vocab + 64;
+    const size_t total = (size_t)n_embd * 8 + (size_t)n_ff * 2 + (size_t)n_vocab * 2 + 64;
     float *base = (float *)fl_dev_malloc(total * sizeof(float));
     if (!base) B200_FAIL("decode workspace: %s", fl_last_error());
     w.xa = base; w.xb = w.xa + n_embd; w.q = w.xb + n_embd; w.att = w.q + n_embd; w.ff = w.att + n_embd; w.emb = w.ff + n_embd;
-    w.m1 = w.emb + n_embd; w.m3 = w.m1 + n_ff; w.logits = w.m3 + n_ff; w.d_tok = (int32_t *)(w.logits + n_vocab);
+    w.part1 = w.emb + n_embd; w.part2 = w.part1 + n_embd;
+    w.m1 = w.part2 + n_embd; w.m3 = w.m1 + n_ff; w.logits = w.m3 + n_ff; w.logits_local = w.logits + n_vocab;
+    w.d_tok = (int32_t *)(w.logits_local + n_vocab);
     w.n_embd = n_embd; w.n_ff = n_ff; w.n_vocab = n_vocab;
 }
 
+// K-split shards of wo / w2 (tensor parallelism): blocks [blk0, blk0 + nblk) of every row, packed once
+// into a private matrix with a 16-byte-multiple row stride so each tile is still one bulk copy
+std::unordered_map<const void *, void *> g_packed;
+const void *packed_shard(const ggml_tensor *w, const void *w_dev, int blk0, int nblk, size_t &stride_out) {
+    const size_t bb = k_tsize[w->type];
+    stride_out = ((size_t)nblk * bb + 15) & ~(size_t)15;
+    auto it = g_packed.find(w_dev);
+    if (it != g_packed.end()) return it->second;
+    void *dst = fl_dev_malloc(stride_out * (size_t)w->ne[1] + 256);
+    if (!dst) B200_FAIL("tensor-parallel shard: %s", fl_last_error());
+    FLC(fl_dev_pack_cols((int)w->type, w_dev, w->nb[1], (int)w->ne[1], blk0, nblk, dst, stride_out));
+    g_packed[w_dev] = dst;
+    return dst;
+}
+
 bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, DecodeWs &W, DecodeOutputs &O) {
+    const int world = fl_comm_world(), rank = fl_comm_rank();
     PM(g->n_nodes >= 4 + 37 && (g->n_nodes - 4) % 37 == 0);
     Cur c{g, 0, true};
     ggml_tensor *n0 = c.next(GGML_OP_GET_ROWS);
@@ -1071,6 +1095,30 @@ bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, Decode
         mv_base(L.w2, (int)w2->type, n_ff);
         L.w2.nseg = 1; L.w2.seg_w[0] = dp<const void>(w2, ctx); L.w2.seg_rows[0] = n_embd; L.w2.seg_dst[0] = xout;
         L.w2.pro = FL_PRO_SILUMUL; L.w2.x = L.w13.seg_dst[0]; L.w2.b = L.w13.seg_dst[1]; L.w2.epi = FL_EPI_RESADD; L.w2.res = L.w13.x;
+        if (world > 1) {
+            // ---- tensor-parallel wiring: wq/wk/wv/w1/w3 row-split by heads / n_ff slices, wo/w2 K-split,
+            // fp32 all-reduce of n_embd after wo and after w2; the residual adds move into the next prologue (xadd).
+            PM(n_head % world == 0 && n_ff % (32 * world) == 0 && (n_embd / world) % 32 == 0);
+            const int nl = n_embd / world, fl = n_ff / world;
+            const size_t rb_e = (size_t)(n_embd / 32) * k_tsize[wq->type];          // dense row bytes, K = n_embd
+            L.part1 = W.part1; L.part2 = W.part2;
+            L.kcache += (size_t)rank * nl; L.vcache += (size_t)rank * nl * n_ctx;   // this rank's heads
+            for (int i = 0; i < 3; i++) { L.qkv.seg_w[i] = (const char *)L.qkv.seg_w[i] + (size_t)rank * nl * rb_e; L.qkv.seg_rows[i] = nl; }
+            L.qkv.kcache = (float *)L.kcache; L.qkv.vcache = (float *)L.vcache;
+            if (il == 0) { L.qkv.x = W.xa; }
+            else { L.qkv.x = W.part2; L.qkv.xadd = W.ff; L.qkv.sum_out = W.xa; }    // x_l = w2 partial sum + ff of the previous layer
+            size_t st = 0;
+            mv_base(L.wo, (int)wo->type, nl);
+            L.wo.nseg = 1; L.wo.seg_w[0] = packed_shard(wo, dp<const void>(wo, ctx), rank * (nl / 32), nl / 32, st); L.wo.row_stride_bytes = st;
+            L.wo.seg_rows[0] = n_embd; L.wo.seg_dst[0] = W.part1; L.wo.pro = FL_PRO_PLAIN; L.wo.x = W.att; L.wo.epi = FL_EPI_STORE;
+            const size_t rb1 = (size_t)(n_embd / 32) * k_tsize[w1->type];
+            L.w13.seg_w[0] = (const char *)L.w13.seg_w[0] + (size_t)rank * fl * rb1; L.w13.seg_w[1] = (const char *)L.w13.seg_w[1] + (size_t)rank * fl * rb1;
+            L.w13.seg_rows[0] = L.w13.seg_rows[1] = fl;
+            L.w13.x = W.part1; L.w13.xadd = W.xa; L.w13.sum_out = W.ff;              // ff = wo partial sum + x
+            mv_base(L.w2, (int)w2->type, fl);
+            L.w2.nseg = 1; L.w2.seg_w[0] = packed_shard(w2, dp<const void>(w2, ctx), rank * (fl / 32), fl / 32, st); L.w2.row_stride_bytes = st;
+            L.w2.seg_rows[0] = n_embd; L.w2.seg_dst[0] = W.part2; L.w2.pro = FL_PRO_SILUMUL; L.w2.x = W.m1; L.w2.b = W.m3; L.w2.epi = FL_EPI_STORE;
+        }
         x = xo;
         std::swap(xin, xout);
     }
@@ -1082,6 +1130,15 @@ bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, Decode
     PM(W.n_vocab == (int)lg->src0->ne[1] && is_vec(lg, W.n_vocab) && is_vec(f, n_embd));
     P.head.pro = FL_PRO_RMSNORM; P.head.x = xin; P.head.gamma = dp<const float>(f->src0, ctx); P.head.normed_out = W.emb;
     O.logits_host = lg->data; O.logits_bytes = (size_t)W.n_vocab * 4; O.emb_host = f->data; O.emb_bytes = (size_t)n_embd * 4;
+    P.world = world; P.heads_local = n_head / world;
+    if (world > 1) {
+        PM(W.n_vocab % (2 * world) == 0);
+        const int vl = W.n_vocab / world;
+        const size_t rbv = (size_t)(n_embd / 32) * k_tsize[lg->src0->type];
+        P.head.seg_w[0] = (const char *)P.head.seg_w[0] + (size_t)rank * vl * rbv; P.head.seg_rows[0] = vl; P.head.seg_dst[0] = W.logits_local;
+        P.head.x = W.part2; P.head.xadd = W.ff;                                    // final residual add of the last layer
+        P.vocab_local = vl; P.logits_local = W.logits_local; P.logits_all = W.logits;
+    }
     P.head.epi = FL_EPI_STORE;
     P.n_head = n_head; P.n_ctx = n_ctx; P.n_past = n_past;
     return n_past >= 0;
@@ -1091,7 +1148,7 @@ bool same_mv(const fl_mv_args &a, const fl_mv_args &b) { return memcmp(&a, &b, s
 bool same_plan(const DecodePlan &a, const DecodePlan &b) {
     if (a.n_layer != b.n_layer || a.n_embd != b.n_embd || a.n_head != b.n_head || a.n_ctx != b.n_ctx || a.scale != b.scale ||
         a.emb_type != b.emb_type || a.emb_w != b.emb_w || a.emb_stride != b.emb_stride || a.emb_ids != b.emb_ids || a.emb_dst != b.emb_dst ||
-        !same_mv(a.head, b.head))
+        !same_mv(a.head, b.head) || a.world != b.world)
         return false;
     for (int i = 0; i < a.n_layer; i++) {
         const LayerPlan &x = a.layers[i], &y = b.layers[i];
@@ -1124,16 +1181,20 @@ void profiled_mv(const fl_mv_args &a) {
 
 void issue_decode(const DecodePlan &P, const int *d_npast) {
     FLC(fl_dev_dequantize_rows(P.emb_type, P.emb_w, P.emb_stride, P.emb_K, P.emb_ids, 1, P.emb_dst, (size_t)P.emb_K));
+    const int hd = P.n_embd / P.n_head;
     for (const LayerPlan &Lc : P.layers) {
         fl_mv_args qkv = Lc.qkv;
         qkv.n_past = d_npast;
         profiled_mv(qkv);
-        FLC(fl_dev_attn_decode(Lc.q, Lc.kcache, Lc.vcache, Lc.att, d_npast, P.n_embd, P.n_head, P.n_ctx, P.scale));
+        FLC(fl_dev_attn_decode(Lc.q, Lc.kcache, Lc.vcache, Lc.att, d_npast, P.n_embd, P.heads_local, hd, P.n_ctx, P.scale));
         profiled_mv(Lc.wo);
+        if (P.world > 1) FLC(fl_comm_allreduce_f32(Lc.part1, (size_t)P.n_embd));
         profiled_mv(Lc.w13);
         profiled_mv(Lc.w2);
+        if (P.world > 1) FLC(fl_comm_allreduce_f32(Lc.part2, (size_t)P.n_embd));
     }
     profiled_mv(P.head);
+    if (P.world > 1) FLC(fl_comm_allgather_f32(P.logits_local, P.logits_all, (size_t)P.vocab_local));
 }
 
 // returns true when the graph was executed through the fused plan
@@ -1197,6 +1258,7 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
 
     DecodeOutputs dout;
     if (run_decode_plan(ctx, g, dout, ev0, ev1)) {
+        if (fl_comm_world() > 1) g_dec.tp_kv_sharded = true;
         // fused decode step: the two results the caller reads (reference lib/llama.cpp:476-489) come
         // straight from the private workspace
         FLC(fl_d2h(dout.logits_host, g_dec.ws.logits, dout.logits_bytes));
@@ -1225,6 +1287,11 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
             }
         }
 
+        if (g_dec.tp_kv_sharded)
+            for (int i = 0; i < g->n_nodes; i++)
+                if (g->nodes[i]->op == GGML_OP_SOFT_MAX)
+                    B200_FAIL("tensor-parallel mode: a replicated (multi-token) attention eval after sharded decode steps would read KV-cache "
+                              "entries of other ranks' heads; the KV all-gather for that case is not implemented");
         FLC(fl_event_record(ev0));
         for (int i = 0; i < g->n_nodes; i++) exec_node(g->nodes[i], ctx);
         FLC(fl_event_record(ev1));

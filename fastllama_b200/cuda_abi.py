@@ -40,7 +40,8 @@ EPI_STORE, EPI_RESADD, EPI_QKV = 0, 1, 2
 class FlMvArgs(C.Structure):          # struct fl_mv_args, include/fl_cuda.h
     _fields_ = [("type", C.c_int), ("K", C.c_int), ("nseg", C.c_int), ("seg_w", C.c_void_p * 3), ("seg_rows", C.c_int * 3),
                 ("seg_dst", C.c_void_p * 3), ("pro", C.c_int), ("x", C.c_void_p), ("gamma", C.c_void_p), ("b", C.c_void_p),
-                ("normed_out", C.c_void_p), ("silu_tab", C.c_void_p), ("epi", C.c_int), ("res", C.c_void_p), ("n_past", C.c_void_p),
+                ("normed_out", C.c_void_p), ("xadd", C.c_void_p), ("sum_out", C.c_void_p), ("row_stride_bytes", C.c_size_t),
+                ("silu_tab", C.c_void_p), ("epi", C.c_int), ("res", C.c_void_p), ("n_past", C.c_void_p),
                 ("n_ctx", C.c_int), ("n_embd", C.c_int), ("head_dim", C.c_int), ("rope_cs", C.c_void_p), ("kcache", C.c_void_p),
                 ("vcache", C.c_void_p)]
 
@@ -87,7 +88,14 @@ SIGNATURES = {
     "fl_dev_mul_mat_f32": (C.c_int, [_VP, _VP, _VP]),
     "fl_dev_mv_fused_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "fl_dev_mv_fused": (C.c_int, [C.POINTER(FlMvArgs)]),
-    "fl_dev_attn_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]),
+    "fl_dev_attn_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
+    "fl_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "fl_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "fl_comm_rank": (C.c_int, []),
+    "fl_comm_world": (C.c_int, []),
+    "fl_comm_allreduce_f32": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "fl_comm_allgather_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fl_dev_pack_cols": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "fl_dev_rope_table": (C.c_int, [C.c_int, C.c_int]),
     "fl_graph_begin_capture": (C.c_int, []),
     "fl_graph_end_capture": (C.c_int, [C.POINTER(C.c_void_p)]),

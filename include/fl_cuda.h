@@ -146,6 +146,10 @@ typedef struct fl_mv_args {
     const float *gamma;          /* PRO_RMSNORM: norm weight */
     const float *b;              /* PRO_SILUMUL: the multiplier */
     float *normed_out;           /* PRO_RMSNORM: optional copy of gamma * rms_norm(x) (the "embeddings") */
+    const float *xadd;           /* optional: the prologue input is x + xadd (the residual add that follows an
+                                    all-reduced partial result in tensor-parallel mode) ... */
+    float *sum_out;              /* ... and x + xadd is also written here (by CTA 0): the new residual stream */
+    size_t row_stride_bytes;     /* 0 = dense rows of K/32 blocks; else the (16-B multiple) stride of packed K-slices */
     const uint16_t *silu_tab;    /* filled in by the library */
     int epi;
     const float *res;            /* EPI_RESADD */
@@ -157,9 +161,22 @@ typedef struct fl_mv_args {
 int fl_dev_mv_fused_supported(int type, int K, int mtot);
 int fl_dev_mv_fused(const fl_mv_args *args);
 /* attention of one new token over the cached positions 0..n_past (reference lib/llama.cpp:346-398, N = 1) */
-int fl_dev_attn_decode(const float *q, const float *kcache, const float *vcache, float *out, const int *n_past, int n_embd,
-                       int n_head, int n_ctx, float scale);
+int fl_dev_attn_decode(const float *q, const float *kcache, const float *vcache, float *out, const int *n_past, int k_row_stride,
+                       int n_head, int head_dim, int n_ctx, float scale);   /* k_row_stride = n_embd of the model (floats per cached position) */
 int fl_dev_rope_table(int n_dims, int n_pos);    /* make sure the cos/sin table covers n_pos positions */
+
+/* ---- tensor parallelism: one process per GPU, NCCL (dlopen'ed libnccl.so.2) on the
+ * library stream; collectives are captured into the decode CUDA graph.  fl_comm_unique_id is called on
+ * rank 0 and its 128 bytes are distributed by the launcher (bench.py uses torch.distributed). */
+int fl_comm_unique_id(void *out128);
+int fl_comm_init(int rank, int world, const void *id128);
+int fl_comm_rank(void);
+int fl_comm_world(void);
+int fl_comm_allreduce_f32(float *buf_dev, size_t n);                                   /* in place, sum */
+int fl_comm_allgather_f32(const float *send_dev, float *recv_dev, size_t n_per_rank);
+/* copy blocks [blk0, blk0 + nblk) of every row of a quantised matrix into a packed matrix whose row
+ * stride is dst_row_stride bytes (the K-split shard of wo / w2) */
+int fl_dev_pack_cols(int type, const void *W, size_t w_row_stride_bytes, int M, int blk0, int nblk, void *dst, size_t dst_row_stride);
 
 /* CUDA-graph capture of everything issued on the library stream between begin and end */
 int fl_graph_begin_capture(void);

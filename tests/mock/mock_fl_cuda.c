@@ -211,12 +211,24 @@ int fl_dev_mul_mat_f32(const fl_view *a, const fl_view *b, const fl_view *d) {
 }
 
 /* ---- fused decode step + graph capture (recorded and replayed, like a CUDA graph) ---------------- */
-enum { OP_MV = 1, OP_ATTN = 2, OP_DEQ = 3 };
+/* ---- tensor-parallel plumbing of the mock: collectives are delegated to a callback the test installs
+ * (torch.distributed / gloo on the "device" buffers, which are host memory here) */
+typedef void (*mock_coll_cb)(int kind, void *send, void *recv, size_t n);   /* kind 0 = allreduce in place, 1 = allgather */
+static mock_coll_cb g_coll = NULL;
+static int g_rank = 0, g_world = 1;
+void fl_mock_set_collective(mock_coll_cb cb, int rank, int world) { g_coll = cb; g_rank = rank; g_world = world; }
+int fl_comm_unique_id(void *out) { memset(out, 0, 128); return 0; }
+int fl_comm_init(int rank, int world, const void *id) { (void)id; g_rank = rank; g_world = world; return 0; }
+int fl_comm_rank(void) { return g_rank; }
+int fl_comm_world(void) { return g_world; }
+
+enum { OP_MV = 1, OP_ATTN = 2, OP_DEQ = 3, OP_ALLREDUCE = 10, OP_ALLGATHER = 11 };
 typedef struct {
     int kind;
     fl_mv_args mv;
-    struct { const float *q, *k, *v; float *out; const int *n_past; int n_embd, n_head, n_ctx; float scale; } at;
+    struct { const float *q, *k, *v; float *out; const int *n_past; int n_embd, n_head, hd, n_ctx; float scale; } at;
     struct { int type; const void *W; size_t wrs; int K; const int32_t *ids; int n; float *dst; size_t drs; } dq;
+    struct { float *send, *recv; size_t n; } co;
 } mock_op;
 typedef struct { mock_op *ops; int n, cap; } mock_graph;
 static mock_graph *g_capture = NULL;
@@ -227,21 +239,25 @@ static void record(const mock_op *op) {
 }
 static void run_mv(const fl_mv_args *a) {
     const int K = a->K, nb = K / 32, bb = a->type == 2 ? 20 : 24;
-    float *v = malloc(sizeof(float) * K);
+    const size_t rstride = a->row_stride_bytes ? a->row_stride_bytes : (size_t)nb * bb;
+    float *v = malloc(sizeof(float) * K), *xin = malloc(sizeof(float) * K);
+    for (int i = 0; i < K; i++) xin[i] = a->xadd ? a->x[i] + a->xadd[i] : a->x[i];
+    if (a->sum_out) memcpy(a->sum_out, xin, sizeof(float) * K);
     if (a->pro == FL_PRO_RMSNORM) {
-        double sum = 0; for (int i = 0; i < K; i++) sum += (double)(a->x[i] * a->x[i]);
+        double sum = 0; for (int i = 0; i < K; i++) sum += (double)(xin[i] * xin[i]);
         float mean = (float)(sum / (double)K), sc = 1.0f / sqrtf(mean + 1e-6f);
-        for (int i = 0; i < K; i++) { v[i] = a->gamma[i] * (a->x[i] * sc); if (a->normed_out) a->normed_out[i] = v[i]; }
+        for (int i = 0; i < K; i++) { v[i] = a->gamma[i] * (xin[i] * sc); if (a->normed_out) a->normed_out[i] = v[i]; }
     } else if (a->pro == FL_PRO_SILUMUL) {
-        for (int i = 0; i < K; i++) v[i] = h2f(tab_silu[f2h(a->x[i])]) * a->b[i];
-    } else memcpy(v, a->x, sizeof(float) * K);
+        for (int i = 0; i < K; i++) v[i] = h2f(tab_silu[f2h(xin[i])]) * a->b[i];
+    } else memcpy(v, xin, sizeof(float) * K);
+    free(xin);
     void *q8 = malloc((size_t)nb * 40);
     orc_quantize_row_q8_0(v, q8, K);
     const int n_past = a->epi == FL_EPI_QKV ? *a->n_past : 0;
     for (int sg = 0; sg < a->nseg; sg++) {
         float *tmp = malloc(sizeof(float) * a->seg_rows[sg]);
         for (int r = 0; r < a->seg_rows[sg]; r++) {
-            const void *wr = (const char *)a->seg_w[sg] + (size_t)r * nb * bb;
+            const void *wr = (const char *)a->seg_w[sg] + (size_t)r * rstride;
             if (a->type == 2) orc_vec_dot_q4_0_q8_0(K, tmp + r, wr, q8); else orc_vec_dot_q4_1_q8_0(K, tmp + r, wr, q8);
         }
         if (a->epi == FL_EPI_QKV) {
@@ -261,7 +277,7 @@ static void run_mv(const fl_mv_args *a) {
     free(q8); free(v);
 }
 static void run_attn(const mock_op *o) {
-    const int hd = o->at.n_embd / o->at.n_head, n_pos = *o->at.n_past + 1;
+    const int hd = o->at.hd, n_pos = *o->at.n_past + 1;
     float *p = malloc(sizeof(float) * n_pos);
     for (int h = 0; h < o->at.n_head; h++) {
         float mx = -INFINITY; double sum = 0;
@@ -277,6 +293,8 @@ static void run_op(const mock_op *o) {
     g_launches++;
     if (o->kind == OP_MV) run_mv(&o->mv);
     else if (o->kind == OP_ATTN) run_attn(o);
+    else if (o->kind == OP_ALLREDUCE) g_coll(0, o->co.send, o->co.recv, o->co.n);
+    else if (o->kind == OP_ALLGATHER) g_coll(1, o->co.send, o->co.recv, o->co.n);
     else for (int i = 0; i < o->dq.n; i++) {
         const void *wr = (const char *)o->dq.W + (size_t)(o->dq.ids ? o->dq.ids[i] : i) * o->dq.wrs;
         if (o->dq.type == 2) orc_dequantize_row_q4_0(wr, o->dq.dst + (size_t)i * o->dq.drs, o->dq.K); else orc_dequantize_row_q4_1(wr, o->dq.dst + (size_t)i * o->dq.drs, o->dq.K);
@@ -285,8 +303,8 @@ static void run_op(const mock_op *o) {
 int fl_dev_mv_fused_supported(int type, int K, int mtot) { return (type == 2 || type == 3) && K % 64 == 0 && mtot >= 2 && mtot % 2 == 0; }
 int fl_dev_rope_table(int n_dims, int n_pos) { (void)n_dims; (void)n_pos; return 0; }
 int fl_dev_mv_fused(const fl_mv_args *a) { mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_MV; o.mv = *a; if (g_capture) record(&o); else run_op(&o); return 0; }
-int fl_dev_attn_decode(const float *q, const float *k, const float *v, float *out, const int *n_past, int n_embd, int n_head, int n_ctx, float scale) {
-    mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_ATTN; o.at.q = q; o.at.k = k; o.at.v = v; o.at.out = out; o.at.n_past = n_past; o.at.n_embd = n_embd; o.at.n_head = n_head; o.at.n_ctx = n_ctx; o.at.scale = scale;
+int fl_dev_attn_decode(const float *q, const float *k, const float *v, float *out, const int *n_past, int n_embd, int n_head, int head_dim, int n_ctx, float scale) {
+    mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_ATTN; o.at.q = q; o.at.k = k; o.at.v = v; o.at.out = out; o.at.n_past = n_past; o.at.n_embd = n_embd; o.at.n_head = n_head; o.at.hd = head_dim; o.at.n_ctx = n_ctx; o.at.scale = scale;
     if (g_capture) record(&o); else run_op(&o); return 0;
 }
 int fl_graph_begin_capture(void) { g_capture = calloc(1, sizeof(mock_graph)); return 0; }
@@ -297,4 +315,21 @@ int fl_graph_destroy(void *ge) { mock_graph *g = ge; if (g) { free(g->ops); free
 static int mock_capturing(void) { return g_capture != NULL; }
 static void mock_record_deq(int type, const void *W, size_t wrs, int K, const int32_t *ids, int n, float *dst, size_t drs) {
     mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_DEQ; o.dq.type = type; o.dq.W = W; o.dq.wrs = wrs; o.dq.K = K; o.dq.ids = ids; o.dq.n = n; o.dq.dst = dst; o.dq.drs = drs; record(&o);
+}
+
+
+int fl_comm_allreduce_f32(float *buf, size_t n) {
+    if (g_world <= 1) return 0;
+    mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_ALLREDUCE; o.co.send = buf; o.co.recv = buf; o.co.n = n;
+    if (g_capture) record(&o); else run_op(&o); return 0;
+}
+int fl_comm_allgather_f32(const float *send, float *recv, size_t n) {
+    if (g_world <= 1) { if (send != recv) memmove(recv, send, n * sizeof(float)); return 0; }
+    mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_ALLGATHER; o.co.send = (float *)send; o.co.recv = recv; o.co.n = n;
+    if (g_capture) record(&o); else run_op(&o); return 0;
+}
+int fl_dev_pack_cols(int type, const void *W, size_t wrs, int M, int blk0, int nblk, void *dst, size_t drs) {
+    const int bb = type == 2 ? 20 : 24;
+    for (int m = 0; m < M; m++) memcpy((char *)dst + (size_t)m * drs, (const char *)W + (size_t)m * wrs + (size_t)blk0 * bb, (size_t)nblk * bb);
+    return 0;
 }

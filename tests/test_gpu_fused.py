@@ -141,7 +141,7 @@ def test_attn_decode(fl, n_embd, n_head, n_ctx, n_past):
     scale = np.float32(1.0 / math.sqrt(hd))
     dq, dk, dv, do = fl.to_device(q), fl.to_device(kc), fl.to_device(vc), fl.alloc(n_embd * 4)
     dnp = fl.to_device(np.array([n_past], dtype=np.int32))
-    fl.check(fl.lib.fl_dev_attn_decode(dq, dk, dv, do, dnp, n_embd, n_head, n_ctx, scale))
+    fl.check(fl.lib.fl_dev_attn_decode(dq, dk, dv, do, dnp, n_embd, n_head, hd, n_ctx, scale))
     got = fl.to_host(do, (n_embd,), np.float32)
     want = np.zeros(n_embd, dtype=np.float32)
     n_pos = n_past + 1
