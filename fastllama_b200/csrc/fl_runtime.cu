@@ -334,6 +334,29 @@ extern "C" int fl_dev_attn_decode(const float *q, const float *kcache, const flo
     FL_NEED_INIT();
     return flk_attn_decode(g.stream, q, kcache, vcache, out, n_past, k_row_stride, n_head, head_dim, n_ctx, scale, g.tab_exp);
 }
+extern "C" int fl_token_plan_create(const fl_token_step *steps, int n_steps, void **plan_out) {
+    FL_NEED_INIT();
+    FL_REQUIRE(steps && n_steps > 0 && plan_out, "fl_token_plan_create: bad arguments");
+    for (int i = 0; i < n_steps; i++)
+        if (steps[i].kind == 0 && steps[i].mv.epi == FL_EPI_QKV)
+            FL_REQUIRE(g.rope_cs && g.rope_dims == steps[i].mv.head_dim && g.rope_pos >= steps[i].mv.n_ctx,
+                       "fl_token_plan_create: call fl_dev_rope_table(head_dim, n_ctx) first");
+    return flk_token_plan_create(steps, n_steps, g.tab_silu, g.tab_exp, g.rope_cs, plan_out);
+}
+extern "C" int fl_token_plan_launch(void *plan) {
+    FL_NEED_INIT();
+    return flk_token_plan_launch(g.stream, plan);
+}
+extern "C" int fl_token_plan_profile(void *plan, unsigned long long *out, size_t max_words, int *n_ctas) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return flk_token_plan_profile(plan, out, max_words, n_ctas);
+}
+extern "C" int fl_token_plan_destroy(void *plan) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return flk_token_plan_destroy(plan);
+}
 // ---- tensor parallelism: K-slice packing + NCCL through dlopen ------------------------------------
 __global__ void k_pack_cols(const uint32_t *__restrict__ W, size_t src_stride_w, int M, size_t src_off_w, int words, uint32_t *__restrict__ dst,
                             size_t dst_stride_w) {

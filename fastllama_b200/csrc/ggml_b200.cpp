@@ -923,9 +923,10 @@ struct DecodeState {
     DecodePlan plan;            // the plan the captured graph was built from
     DecodeWs ws;
     void *graph = nullptr;
+    void *token_plan = nullptr;   // the persistent per-token kernel's program (single-GPU decode)
     int *d_npast = nullptr;
     int *h_scalars = nullptr;   // pinned: [0] n_past, [1] token id
-    bool enabled = true, use_graph = true, inited = false;
+    bool enabled = true, use_graph = true, use_token_kernel = true, inited = false;
     bool tp_kv_sharded = false;   // tensor-parallel decode steps have written only this rank's heads into the KV cache
 };
 struct DecodeOutputs { void *logits_host = nullptr; size_t logits_bytes = 0; void *emb_host = nullptr; size_t emb_bytes = 0; int32_t token = 0; };
@@ -1197,6 +1198,38 @@ void issue_decode(const DecodePlan &P, const int *d_npast) {
     if (P.world > 1) FLC(fl_comm_allgather_f32(P.logits_local, P.logits_all, (size_t)P.vocab_local));
 }
 
+// The same steps as issue_decode, handed to the persistent token kernel (one cooperative launch per token;
+// fl_token_kernel.cu).  Returns nullptr when the shapes are outside what that kernel handles.
+void *make_token_plan(const DecodePlan &P, const int *d_npast) {
+    std::vector<fl_token_step> steps;
+    auto mv = [&](const fl_mv_args &a) { fl_token_step s; memset(&s, 0, sizeof(s)); s.kind = 0; s.mv = a; steps.push_back(s); };
+    const int hd = P.n_embd / P.n_head;
+    for (const LayerPlan &Lc : P.layers) {
+        fl_mv_args qkv = Lc.qkv;
+        qkv.n_past = d_npast;
+        mv(qkv);
+        fl_token_step s;
+        memset(&s, 0, sizeof(s));
+        s.kind = 1; s.q = Lc.q; s.kcache = Lc.kcache; s.vcache = Lc.vcache; s.out = Lc.att; s.n_past = d_npast;
+        s.k_row_stride = P.n_embd; s.n_head = P.heads_local; s.head_dim = hd; s.n_ctx = P.n_ctx; s.scale = P.scale;
+        steps.push_back(s);
+        mv(Lc.wo);
+        mv(Lc.w13);
+        mv(Lc.w2);
+    }
+    mv(P.head);
+    void *plan = nullptr;
+    if (fl_token_plan_create(steps.data(), (int)steps.size(), &plan) != 0) {
+        if (g_verbose) fprintf(stderr, "[ggml_b200] token kernel not used: %s\n", fl_last_error());
+        return nullptr;
+    }
+    return plan;
+}
+void issue_decode_token_kernel(const DecodePlan &P, void *token_plan) {
+    FLC(fl_dev_dequantize_rows(P.emb_type, P.emb_w, P.emb_stride, P.emb_K, P.emb_ids, 1, P.emb_dst, (size_t)P.emb_K));
+    FLC(fl_token_plan_launch(token_plan));
+}
+
 // returns true when the graph was executed through the fused plan
 bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, void *ev0, void *ev1) {
     DecodeState &D = g_dec;
@@ -1204,6 +1237,7 @@ bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, 
         D.inited = true;
         D.enabled = getenv("FASTLLAMA_B200_NO_FUSED") == nullptr;
         D.use_graph = getenv("FASTLLAMA_B200_NO_GRAPH") == nullptr;
+        D.use_token_kernel = getenv("FASTLLAMA_B200_NO_TOKEN_KERNEL") == nullptr;
     }
     if (!D.enabled) return false;
     DecodePlan P;
@@ -1227,15 +1261,18 @@ bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, 
     }
     if (!D.graph || !same_plan(P, D.plan)) {
         if (D.graph) { FLC(fl_sync()); FLC(fl_graph_destroy(D.graph)); D.graph = nullptr; }
+        if (D.token_plan) { FLC(fl_token_plan_destroy(D.token_plan)); D.token_plan = nullptr; }
+        if (D.use_token_kernel && P.world == 1) D.token_plan = make_token_plan(P, D.d_npast);
         // one eager pass first: sets kernel attributes, and gives this token's result
         FLC(fl_event_record(ev0));
-        issue_decode(P, D.d_npast);
+        if (D.token_plan) issue_decode_token_kernel(P, D.token_plan); else issue_decode(P, D.d_npast);
         FLC(fl_event_record(ev1));
         FLC(fl_graph_begin_capture());
-        issue_decode(P, D.d_npast);
+        if (D.token_plan) issue_decode_token_kernel(P, D.token_plan); else issue_decode(P, D.d_npast);
         FLC(fl_graph_end_capture(&D.graph));
         D.plan = P;
-        if (g_verbose) fprintf(stderr, "[ggml_b200] decode plan captured: %d layers, n_embd %d, n_ctx %d\n", P.n_layer, P.n_embd, P.n_ctx);
+        if (g_verbose) fprintf(stderr, "[ggml_b200] decode plan captured: %d layers, n_embd %d, n_ctx %d, %s\n", P.n_layer, P.n_embd, P.n_ctx,
+                               D.token_plan ? "persistent token kernel" : "one kernel per matrix group");
         return true;       // the eager pass already produced this token (capture does not execute)
     }
     FLC(fl_event_record(ev0));

@@ -46,6 +46,12 @@ class FlMvArgs(C.Structure):          # struct fl_mv_args, include/fl_cuda.h
                 ("vcache", C.c_void_p)]
 
 
+class FlTokenStep(C.Structure):       # struct fl_token_step, include/fl_cuda.h
+    _fields_ = [("kind", C.c_int), ("mv", FlMvArgs), ("q", C.c_void_p), ("kcache", C.c_void_p), ("vcache", C.c_void_p),
+                ("out", C.c_void_p), ("n_past", C.c_void_p), ("k_row_stride", C.c_int), ("n_head", C.c_int), ("head_dim", C.c_int),
+                ("n_ctx", C.c_int), ("scale", C.c_float)]
+
+
 SIGNATURES = {
     "fl_init": (C.c_int, [C.c_int]),
     "fl_shutdown": (None, []),
@@ -88,6 +94,10 @@ SIGNATURES = {
     "fl_dev_mul_mat_f32": (C.c_int, [_VP, _VP, _VP]),
     "fl_dev_mv_fused_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "fl_dev_mv_fused": (C.c_int, [C.POINTER(FlMvArgs)]),
+    "fl_token_plan_create": (C.c_int, [C.POINTER(FlTokenStep), C.c_int, C.POINTER(C.c_void_p)]),
+    "fl_token_plan_launch": (C.c_int, [C.c_void_p]),
+    "fl_token_plan_destroy": (C.c_int, [C.c_void_p]),
+    "fl_token_plan_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "fl_dev_attn_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "fl_comm_unique_id": (C.c_int, [C.c_void_p]),
     "fl_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),

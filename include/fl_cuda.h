@@ -165,6 +165,27 @@ int fl_dev_attn_decode(const float *q, const float *kcache, const float *vcache,
                        int n_head, int head_dim, int n_ctx, float scale);   /* k_row_stride = n_embd of the model (floats per cached position) */
 int fl_dev_rope_table(int n_dims, int n_pos);    /* make sure the cos/sin table covers n_pos positions */
 
+/* ---- the whole decode step as one persistent kernel ---------------------------------------------
+ * A token plan is a list of steps, each either an fl_dev_mv_fused call (kind 0) or an
+ * fl_dev_attn_decode call (kind 1) with exactly the arguments above; fl_token_plan_launch runs them in
+ * order inside ONE cooperative launch of one CTA per SM, with grid barriers between steps and the
+ * weight stream prefetched across them.  Results are bit-identical to issuing the steps one by one. */
+typedef struct fl_token_step {
+    int kind;                    /* 0 = matvec (mv), 1 = attention (the fields below) */
+    fl_mv_args mv;
+    const float *q, *kcache, *vcache;
+    float *out;
+    const int *n_past;
+    int k_row_stride, n_head, head_dim, n_ctx;
+    float scale;
+} fl_token_step;
+int fl_token_plan_create(const fl_token_step *steps, int n_steps, void **plan_out);
+int fl_token_plan_launch(void *plan);
+int fl_token_plan_destroy(void *plan);
+/* tooling: with FASTLLAMA_B200_TOKEN_PROF set at create time, the last launch's per-step, per-CTA timestamps
+ * [n_steps][n_ctas][4] in ns: step entered, grid barrier passed, activations quantised, tiles consumed */
+int fl_token_plan_profile(void *plan, unsigned long long *out, size_t max_words, int *n_ctas);
+
 /* ---- tensor parallelism: one process per GPU, NCCL (dlopen'ed libnccl.so.2) on the
  * library stream; collectives are captured into the decode CUDA graph.  fl_comm_unique_id is called on
  * rank 0 and its 128 bytes are distributed by the launcher (bench.py uses torch.distributed). */

@@ -222,13 +222,14 @@ int fl_comm_init(int rank, int world, const void *id) { (void)id; g_rank = rank;
 int fl_comm_rank(void) { return g_rank; }
 int fl_comm_world(void) { return g_world; }
 
-enum { OP_MV = 1, OP_ATTN = 2, OP_DEQ = 3, OP_ALLREDUCE = 10, OP_ALLGATHER = 11 };
+enum { OP_MV = 1, OP_ATTN = 2, OP_DEQ = 3, OP_ALLREDUCE = 10, OP_ALLGATHER = 11, OP_PLAN = 20 };
 typedef struct {
     int kind;
     fl_mv_args mv;
     struct { const float *q, *k, *v; float *out; const int *n_past; int n_embd, n_head, hd, n_ctx; float scale; } at;
     struct { int type; const void *W; size_t wrs; int K; const int32_t *ids; int n; float *dst; size_t drs; } dq;
     struct { float *send, *recv; size_t n; } co;
+    void *plan;
 } mock_op;
 typedef struct { mock_op *ops; int n, cap; } mock_graph;
 static mock_graph *g_capture = NULL;
@@ -291,6 +292,7 @@ static void run_attn(const mock_op *o) {
 }
 static void run_op(const mock_op *o) {
     g_launches++;
+    if (o->kind == OP_PLAN) { const mock_graph *pg = o->plan; for (int i = 0; i < pg->n; i++) { run_op(&pg->ops[i]); g_launches--; } return; }
     if (o->kind == OP_MV) run_mv(&o->mv);
     else if (o->kind == OP_ATTN) run_attn(o);
     else if (o->kind == OP_ALLREDUCE) g_coll(0, o->co.send, o->co.recv, o->co.n);
@@ -307,6 +309,21 @@ int fl_dev_attn_decode(const float *q, const float *k, const float *v, float *ou
     mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_ATTN; o.at.q = q; o.at.k = k; o.at.v = v; o.at.out = out; o.at.n_past = n_past; o.at.n_embd = n_embd; o.at.n_head = n_head; o.at.hd = head_dim; o.at.n_ctx = n_ctx; o.at.scale = scale;
     if (g_capture) record(&o); else run_op(&o); return 0;
 }
+/* the persistent token kernel: the mock runs its steps one after another */
+int fl_token_plan_create(const fl_token_step *steps, int n, void **out) {
+    mock_graph *pg = calloc(1, sizeof(mock_graph));
+    pg->ops = calloc((size_t)n, sizeof(mock_op)); pg->n = pg->cap = n;
+    for (int i = 0; i < n; i++) {
+        mock_op *o = &pg->ops[i];
+        if (steps[i].kind == 0) { o->kind = OP_MV; o->mv = steps[i].mv; }
+        else { o->kind = OP_ATTN; o->at.q = steps[i].q; o->at.k = steps[i].kcache; o->at.v = steps[i].vcache; o->at.out = steps[i].out; o->at.n_past = steps[i].n_past;
+               o->at.n_embd = steps[i].k_row_stride; o->at.n_head = steps[i].n_head; o->at.hd = steps[i].head_dim; o->at.n_ctx = steps[i].n_ctx; o->at.scale = steps[i].scale; }
+    }
+    *out = pg; return 0;
+}
+int fl_token_plan_launch(void *plan) { mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_PLAN; o.plan = plan; if (g_capture) record(&o); else run_op(&o); return 0; }
+int fl_token_plan_profile(void *plan, unsigned long long *out, size_t n, int *c) { (void)plan; (void)out; (void)n; *c = 0; return -1; }
+int fl_token_plan_destroy(void *plan) { mock_graph *pg = plan; if (pg) { free(pg->ops); free(pg); } return 0; }
 int fl_graph_begin_capture(void) { g_capture = calloc(1, sizeof(mock_graph)); return 0; }
 int fl_graph_end_capture(void **out) { *out = g_capture; g_capture = NULL; return 0; }
 int fl_graph_launch(void *ge) { mock_graph *g = ge; for (int i = 0; i < g->n; i++) run_op(&g->ops[i]); return 0; }
