@@ -94,3 +94,64 @@ __device__ __forceinline__ void fd_tile_of(const fd_slice &sl, int R, int t, int
     rows = min(R, n - j * R);
 }
 
+
+// ---- P*V of the decode attention: out[d] = sum_j p_j * V[d][j] -------------------------------------
+// Canonical summation order, shared by k_attn_decode and the token kernel so that both give the same bits
+// however many threads they put on one output dimension: the float4 groups of the V row are dealt round-robin
+// to FD_PV_SUBS subsequences; each subsequence keeps four lane accumulators (by position mod 4) and folds them
+// as (a0+a1)+(a2+a3); subsequence 0 appends the n_pos % 4 tail; the partials are then added in index order.
+#define FD_PV_SUBS 16
+template <int NS>
+__device__ __forceinline__ void fd_pv_partials(const float *v, const float *sc, int n_pos, int sub0, float *out /* [NS] */) {
+    const int n4 = n_pos >> 2;
+    float a[NS][4];
+#pragma unroll
+    for (int u = 0; u < NS; u++) a[u][0] = a[u][1] = a[u][2] = a[u][3] = 0.f;
+    for (int i0 = 0; i0 < n4; i0 += FD_PV_SUBS) {
+        float4 vv[NS];
+#pragma unroll
+        for (int u = 0; u < NS; u++) {
+            const int i = i0 + sub0 + u;
+            vv[u] = (i < n4) ? __ldcg((const float4 *)(v + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < NS; u++) {
+            const int i = i0 + sub0 + u;
+            if (i < n4) {
+                a[u][0] = __fmaf_rn(vv[u].x, sc[4 * i + 0], a[u][0]);
+                a[u][1] = __fmaf_rn(vv[u].y, sc[4 * i + 1], a[u][1]);
+                a[u][2] = __fmaf_rn(vv[u].z, sc[4 * i + 2], a[u][2]);
+                a[u][3] = __fmaf_rn(vv[u].w, sc[4 * i + 3], a[u][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < NS; u++) {
+        float acc = __fadd_rn(__fadd_rn(a[u][0], a[u][1]), __fadd_rn(a[u][2], a[u][3]));
+        if (sub0 + u == 0)
+            for (int j = 4 * n4; j < n_pos; j++) acc = __fmaf_rn(__ldcg(v + j), sc[j], acc);
+        out[u] = acc;
+    }
+}
+// thread handles subsequences [sub0, sub0 + NS) of output dimension `col` (column of the [FD_PV_SUBS][ncols] partial table)
+template <int NS>
+__device__ __forceinline__ void fd_pv_do(const float *v, const float *sc, int n_pos, int sub0, float *part, int ncols, int col) {
+    float o[NS];
+    fd_pv_partials<NS>(v, sc, n_pos, sub0, o);
+#pragma unroll
+    for (int u = 0; u < NS; u++) part[(sub0 + u) * ncols + col] = o[u];
+}
+template <int MAXNS>
+__device__ __forceinline__ void fd_pv_store_partials(const float *v, const float *sc, int n_pos, int sub0, int ns, float *part, int ncols, int col) {
+    if (ns == 1) fd_pv_do<1>(v, sc, n_pos, sub0, part, ncols, col);
+    else if (ns == 2) fd_pv_do<2>(v, sc, n_pos, sub0, part, ncols, col);
+    else if (ns == 4 || MAXNS == 4) fd_pv_do<4>(v, sc, n_pos, sub0, part, ncols, col);
+    else if (ns == 8) fd_pv_do<(MAXNS >= 8 ? 8 : 4)>(v, sc, n_pos, sub0, part, ncols, col);
+    else fd_pv_do<(MAXNS >= 16 ? 16 : 4)>(v, sc, n_pos, sub0, part, ncols, col);
+}
+__device__ __forceinline__ float fd_pv_combine(const float *part, int ncols, int col) {
+    float acc = part[col];
+#pragma unroll
+    for (int u = 1; u < FD_PV_SUBS; u++) acc = __fadd_rn(acc, part[u * ncols + col]);
+    return acc;
+}

@@ -314,10 +314,10 @@ struct fd_attn_params {
 // have many independent loads in flight (4 positions per warp iteration for the scores, one output
 // dimension per thread with 4 independent float4 streams for P*V).
 __global__ void __launch_bounds__(256) k_attn_decode(const fd_attn_params P) {
-    extern __shared__ float sc[];                   // [n_ctx] scores / probabilities
+    extern __shared__ float sc[];                   // [n_ctx] scores / probabilities, then [FD_PV_SUBS][head_dim] partials
     __shared__ double redd[8];
     __shared__ float redf[8];
-    __shared__ float part[256];
+    float *part = sc + P.n_ctx;
     const int h = blockIdx.x, hd = P.head_dim;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -366,31 +366,15 @@ __global__ void __launch_bounds__(256) k_attn_decode(const fd_attn_params P) {
     const float inv = (float)(1.0 / tot);
     for (int j = threadIdx.x; j < n_pos; j += blockDim.x) sc[j] = __fmul_rn(sc[j], inv);
     __syncthreads();
-    // out_d = sum_j p_j * V[d][j]   (ggml_mul_mat V, soft_max): thread (d, half) walks its row of V
+    // out_d = sum_j p_j * V[d][j]   (ggml_mul_mat V, soft_max) in the canonical order of fd_pv_partials
     const int npt = blockDim.x / hd;                               // threads per output dimension (2 for head_dim 128)
-    if (npt >= 1 && (int)threadIdx.x < npt * hd) {
-        const int d = threadIdx.x % hd, sub = threadIdx.x / hd;
-        const float *v = P.vcache + ((size_t)h * hd + d) * P.n_ctx;
-        const int n4 = n_pos >> 2;                                  // whole float4 groups (rows are 16-B aligned: n_ctx % 4 == 0)
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int i = sub; i < n4; i += npt) {
-            const float4 vv = *(const float4 *)(v + 4 * i);
-            a0 = __fmaf_rn(vv.x, sc[4 * i + 0], a0);
-            a1 = __fmaf_rn(vv.y, sc[4 * i + 1], a1);
-            a2 = __fmaf_rn(vv.z, sc[4 * i + 2], a2);
-            a3 = __fmaf_rn(vv.w, sc[4 * i + 3], a3);
-        }
-        float acc = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
-        if (sub == 0)
-            for (int j = 4 * n4; j < n_pos; j++) acc = __fmaf_rn(v[j], sc[j], acc);
-        part[threadIdx.x] = acc;
+    const int ns = FD_PV_SUBS / npt;                               // subsequences per thread
+    if ((int)threadIdx.x < npt * hd) {
+        const int d = threadIdx.x % hd, sub0 = (threadIdx.x / hd) * ns;
+        fd_pv_store_partials<16>(P.vcache + ((size_t)h * hd + d) * P.n_ctx, sc, n_pos, sub0, ns, part, hd, d);
     }
     __syncthreads();
-    if ((int)threadIdx.x < hd) {
-        float acc = part[threadIdx.x];
-        for (int u = 1; u < npt; u++) acc = __fadd_rn(acc, part[threadIdx.x + u * hd]);
-        P.out[(size_t)h * hd + threadIdx.x] = acc;
-    }
+    if ((int)threadIdx.x < hd) P.out[(size_t)h * hd + threadIdx.x] = fd_pv_combine(part, hd, threadIdx.x);
 }
 
 // =================================================================================================
@@ -536,14 +520,15 @@ int flk_attn_decode(cudaStream_t st, const float *q, const float *kcache, const 
     fd_attn_params P;
     P.q = q; P.kcache = kcache; P.vcache = vcache; P.out = out; P.n_past = n_past;
     P.n_embd = n_embd; P.n_ctx = n_ctx; P.head_dim = head_dim; P.scale = scale; P.exp_tab = exp_tab;
-    const size_t smem = (size_t)n_ctx * sizeof(float);
+    const size_t smem = ((size_t)n_ctx + (size_t)FD_PV_SUBS * head_dim) * sizeof(float);
     FL_REQUIRE(smem <= 200 * 1024, "attn_decode: n_ctx=%d too large for the score buffer", n_ctx);
     static size_t attr = 0;
     if (smem > 48 * 1024 && attr < smem) {
         FL_CUDA_OK(cudaFuncSetAttribute(k_attn_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    FL_REQUIRE(n_ctx % 4 == 0 && P.head_dim <= 256, "attn_decode: n_ctx must be a multiple of 4 and head_dim <= 256");
+    FL_REQUIRE(n_ctx % 4 == 0 && head_dim >= 16 && head_dim <= 256 && (head_dim & (head_dim - 1)) == 0,
+               "attn_decode: n_ctx must be a multiple of 4 and head_dim a power of two in [16, 256]");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_head);
     cfg.blockDim = dim3(256);

@@ -8,10 +8,15 @@
 // mbarrier ring, running ahead of the consumers across phase boundaries: while the grid synchronises
 // and the next activation vector is quantised, the next matrices are already landing in shared memory.
 //
-// Each phase does exactly what the corresponding k_mv_fused / k_attn_decode launch does (same prologue,
-// block arithmetic, combine order, epilogue), so results are bit-identical to the multi-kernel path.
+// Work unit = a PAIR of rows handled by one warp (both rows against the same prepared activations):
+//   * default: rows (2u, 2u+1) of a matrix;
+//   * wq|wk|wv: the pair is a rope pair, so rope + KV-cache store need no cross-warp staging;
+//   * w1|w3 ("SwiGLU" phases, detected at plan creation): the pair is (w1 row u, w3 row u) and the
+//     epilogue writes silu(w1.x) * (w3.x) directly, so w2's prologue is a plain quantisation.
+// Per-row arithmetic (block dot, lane mapping, K-slice combine order, epilogues) is exactly that of
+// k_mv_fused / k_attn_decode, so results are bit-identical to the multi-kernel path.
 // Activations move between phases through L2: they are read with ld.global.cg (L1 is not coherent
-// across SMs inside a kernel) and published with __threadfence() before the barrier arrive.
+// across SMs inside a kernel) and published by a gpu-scope release before the barrier arrive.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -27,20 +32,24 @@
 #define TK_NT (TK_CW * 32)
 #define TK_TG 4                  // tile groups; ring slot s always belongs to group s % 4 (S is a multiple of 4)
 #define TK_WPG 4                 // warps per tile group = kparts * G
-#define TK_RMAX 4
+#define TK_GMAX 4                // units (row pairs) per tile at most
 #define TK_THREADS (TK_NT + 32)
+#define TK_PRO_G 4               // float4 groups a thread keeps in registers in the single-pass prologues
 
 enum { TK_PH_MATVEC = 0, TK_PH_ATTN = 1 };
 
 struct tk_phase {
     int kind;
-    int nb, kparts, G, R, P, nfull, mtot;
+    int nb, kparts, G, lgG, P, nfull;
+    int swiglu;                  // pair = (seg 0 row u, seg 1 row u); epilogue writes silu(a) * b to seg_dst[0][u]
+    int units[3];                // pairs per segment (swiglu: one segment of seg_rows[0] pairs)
     uint32_t row_bytes;
     fl_mv_args a;
     // attention
     const float *q, *kcache, *vcache;
     float *out;
     int k_row_stride, n_head, head_dim, n_ctx;
+    int head_split;              // CTAs per head (each owns head_dim / head_split output dimensions)
     float scale;
 };
 
@@ -51,6 +60,7 @@ struct tk_params {
     const uint16_t *exp_tab;
     unsigned long long *prof;      // optional: [n_phases][gridDim.x][4] globaltimer stamps of thread 0
     int S;
+    uint32_t grid_magic, grid_shift, s_magic, s_shift;  // n / d == umulhi(n, magic) >> shift (magic 0: d is a power of two, n >> shift); exact for n < 2^31
     uint32_t slot_bytes;
     uint32_t off_y, off_red, off_rowbuf, off_cnt, off_sc, off_stage0;
 };
@@ -62,36 +72,167 @@ __device__ __forceinline__ unsigned long long tk_now() {
 }
 __device__ __forceinline__ void tk_bar_consumers(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TK_NT) : "memory"); }
 
+// Grid barrier: CTA barrier, then one thread publishes the CTA's writes with a gpu-scope release increment
+// and spins on an acquire load; the second CTA barrier hands the acquired view to the other threads, which
+// read shared activations with ld.global.cg only.
 __device__ __forceinline__ void tk_grid_sync(unsigned *bar, unsigned target) {
-    tk_bar_consumers(13);                               // every consumer warp of this CTA has finished the phase
+    tk_bar_consumers(13);
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned v;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
         } while (v < target);
-        __threadfence();
     }
     tk_bar_consumers(13);
 }
 
-// ---- prologue: q8_0 activations of the phase into shared memory (same arithmetic as k_mv_fused) ----
-__device__ __forceinline__ void tk_prologue(const fl_mv_args &A, int K, fl_block_q8_0 *ysm, double *red, int warp, int lane, int tid) {
+// ---- the CTA's slice of a phase, in units (row pairs), cut into tiles of at most G units ------------
+struct tk_slice {
+    int f0, f1, f2, n0, n1, n2, t0, t1, ntiles;
+};
+__device__ __forceinline__ uint32_t tk_div(uint32_t n, uint32_t magic, uint32_t shift) { return (magic ? __umulhi(n, magic) : n) >> shift; }
+// lgG = log2 of the units per tile (1, 2 or 4 units)
+__device__ __forceinline__ tk_slice tk_make_slice_u(int m0, int m1, int m2, int lgG, uint32_t grid_magic, uint32_t grid_shift) {
+    tk_slice sl;
+    const unsigned U = (unsigned)(m0 + m1 + m2);            // U * gridDim.x < 2^32 (checked at plan creation)
+    const int u0 = (int)tk_div(U * blockIdx.x, grid_magic, grid_shift);
+    const int u1 = (int)tk_div(U * (blockIdx.x + 1), grid_magic, grid_shift);
+    const int rnd = (1 << lgG) - 1;
+    fd_seg_span(u0, u1, 0, m0, sl.f0, sl.n0);
+    fd_seg_span(u0, u1, m0, m1, sl.f1, sl.n1);
+    fd_seg_span(u0, u1, m0 + m1, m2, sl.f2, sl.n2);
+    sl.t0 = (sl.n0 + rnd) >> lgG;
+    sl.t1 = sl.t0 + ((sl.n1 + rnd) >> lgG);
+    sl.ntiles = sl.t1 + ((sl.n2 + rnd) >> lgG);
+    return sl;
+}
+__device__ __forceinline__ void tk_tile_of(const tk_slice &sl, int G, int t, int &seg, int &unit0, int &nunits) {
+    seg = (t < sl.t0) ? 0 : (t < sl.t1) ? 1 : 2;
+    const int j = t - (seg == 0 ? 0 : seg == 1 ? sl.t0 : sl.t1);
+    const int first = seg == 0 ? sl.f0 : seg == 1 ? sl.f1 : sl.f2;
+    const int n = seg == 0 ? sl.n0 : seg == 1 ? sl.n1 : sl.n2;
+    unit0 = first + j * G;
+    nunits = min(G, n - j * G);
+}
+
+// ---- prologues: q8_0 activations of the phase into shared memory (same arithmetic as k_mv_fused) ----
+// One float4 group -> quantised quarter of a block; 8 consecutive lanes hold one 32-element block.
+__device__ __forceinline__ void tk_quant_group(float v[4], int i, int nvec, fl_block_q8_0 *ysm) {
+    float amax = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+    const float d = __fdiv_rn(amax, 127.f);
+    const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
+    int q[4], sum = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        q[c] = max(-128, min(127, __float2int_rn(__fmul_rn(v[c], id))));
+        sum += q[c];
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    if (i < nvec) {
+        fl_block_q8_0 *yb = ysm + (i >> 3);
+        const uint32_t packed = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[1] & 0xFF) << 8) | ((uint32_t)(q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
+        ((uint32_t *)yb->qs)[i & 7] = packed;
+        if ((i & 7) == 0) {
+            yb->d = d;
+            yb->s = __fmul_rn(d, (float)sum);
+        }
+    }
+}
+__device__ __forceinline__ float4 tk_load_x(const float4 *x4, const float4 *xa4, int idx) {
+    float4 v = __ldcg(x4 + idx);
+    if (xa4) { const float4 w = __ldcg(xa4 + idx); v.x = __fadd_rn(v.x, w.x); v.y = __fadd_rn(v.y, w.y); v.z = __fadd_rn(v.z, w.z); v.w = __fadd_rn(v.w, w.w); }
+    return v;
+}
+
+// Single pass: all of a thread's loads are issued before anything is consumed (one L2 round trip), the
+// rms_norm reduction runs on the registers, and the values are quantised from the registers.
+// Requires nvec <= TK_PRO_G * TK_NT for PRO_RMSNORM (K <= 8192); PRO_PLAIN loops over chunks.
+__device__ __forceinline__ void tk_prologue_fast(const fl_mv_args &A, int K, fl_block_q8_0 *ysm, double *red, int warp, int lane, int tid) {
     const int nvec = K >> 2;
     const float4 *x4 = (const float4 *)A.x;
     const float4 *xa4 = (const float4 *)A.xadd;
-    auto load_x = [&](int idx) -> float4 {
-        float4 v = __ldcg(x4 + idx);
-        if (xa4) { const float4 w = __ldcg(xa4 + idx); v.x = __fadd_rn(v.x, w.x); v.y = __fadd_rn(v.y, w.y); v.z = __fadd_rn(v.z, w.z); v.w = __fadd_rn(v.w, w.w); }
-        return v;
-    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (A.pro == FL_PRO_RMSNORM) {
+        const float4 *g4 = (const float4 *)A.gamma;
+        float4 xr[TK_PRO_G], gr[TK_PRO_G];
+#pragma unroll
+        for (int g = 0; g < TK_PRO_G; g++) {
+            const int i = tid + g * TK_NT;
+            xr[g] = (i < nvec) ? tk_load_x(x4, xa4, i) : zero4;
+            gr[g] = (i < nvec) ? __ldg(g4 + i) : zero4;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int g = 0; g < TK_PRO_G; g++) {
+            acc += (double)__fmul_rn(xr[g].x, xr[g].x);
+            acc += (double)__fmul_rn(xr[g].y, xr[g].y);
+            acc += (double)__fmul_rn(xr[g].z, xr[g].z);
+            acc += (double)__fmul_rn(xr[g].w, xr[g].w);
+        }
+        acc = fl_warp_sum_d(acc);
+        if (lane == 0) red[warp] = acc;
+        tk_bar_consumers(15);
+        if (warp == 0) {                                             // the double division is ~100 instructions: one warp, not sixteen
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < TK_CW; w++) t += red[w];
+            const float mean = (float)(t / (double)K);
+            if (lane == 0) ((float *)(red + 16))[0] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, 1e-6f)));
+        }
+        tk_bar_consumers(15);
+        const float scale = ((float *)(red + 16))[0];
+#pragma unroll
+        for (int g = 0; g < TK_PRO_G; g++) {
+            const int i = tid + g * TK_NT;
+            if (g * TK_NT < nvec) {                                  // warp-uniform
+                float v[4] = {xr[g].x, xr[g].y, xr[g].z, xr[g].w};
+                const float o[4] = {gr[g].x, gr[g].y, gr[g].z, gr[g].w};
+                if (A.sum_out && blockIdx.x == 0 && i < nvec) ((float4 *)A.sum_out)[i] = xr[g];
+#pragma unroll
+                for (int c = 0; c < 4; c++) v[c] = __fmul_rn(o[c], __fmul_rn(v[c], scale));
+                if (A.normed_out && blockIdx.x == 0 && i < nvec) ((float4 *)A.normed_out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+                tk_quant_group(v, i, nvec, ysm);
+            }
+        }
+    } else {   // FL_PRO_PLAIN
+        for (int base = 0; base < nvec; base += TK_PRO_G * TK_NT) {
+            float4 xr[TK_PRO_G];
+#pragma unroll
+            for (int g = 0; g < TK_PRO_G; g++) {
+                const int i = base + tid + g * TK_NT;
+                xr[g] = (i < nvec) ? tk_load_x(x4, xa4, i) : zero4;
+            }
+#pragma unroll
+            for (int g = 0; g < TK_PRO_G; g++) {
+                const int i = base + tid + g * TK_NT;
+                if (base + g * TK_NT < nvec) {
+                    float v[4] = {xr[g].x, xr[g].y, xr[g].z, xr[g].w};
+                    if (A.sum_out && blockIdx.x == 0 && i < nvec) ((float4 *)A.sum_out)[i] = xr[g];
+                    tk_quant_group(v, i, nvec, ysm);
+                }
+            }
+        }
+    }
+    tk_bar_consumers(15);
+}
+
+// General path (any K, PRO_SILUMUL): two passes with software-pipelined loads, as in k_mv_fused.
+__device__ __noinline__ void tk_prologue_general(const fl_mv_args &A, int K, fl_block_q8_0 *ysm, double *red, int warp, int lane, int tid) {
+    const int nvec = K >> 2;
+    const float4 *x4 = (const float4 *)A.x;
+    const float4 *xa4 = (const float4 *)A.xadd;
     float scale = 1.0f;
     if (A.pro == FL_PRO_RMSNORM) {
         double acc = 0.0;
 #pragma unroll 4
         for (int i = tid; i < nvec; i += TK_NT) {
-            const float4 v = load_x(i);
+            const float4 v = tk_load_x(x4, xa4, i);
             acc += (double)__fmul_rn(v.x, v.x);
             acc += (double)__fmul_rn(v.y, v.y);
             acc += (double)__fmul_rn(v.z, v.z);
@@ -100,19 +241,15 @@ __device__ __forceinline__ void tk_prologue(const fl_mv_args &A, int K, fl_block
         acc = fl_warp_sum_d(acc);
         if (lane == 0) red[warp] = acc;
         tk_bar_consumers(15);
-        if (tid == 0) {
-            double t = 0.0;
-            for (int w = 0; w < TK_CW; w++) t += red[w];
-            const float mean = (float)(t / (double)K);
-            ((float *)(red + 16))[0] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, 1e-6f)));
-        }
-        tk_bar_consumers(15);
-        scale = ((float *)(red + 16))[0];
+        double t = 0.0;
+        for (int w = 0; w < TK_CW; w++) t += red[w];
+        const float mean = (float)(t / (double)K);
+        scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, 1e-6f)));
     }
     const float4 *g4 = (const float4 *)A.gamma, *b4 = (const float4 *)A.b;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int i = warp * 32 + lane;
-    float4 xv = (i < nvec) ? load_x(i) : zero4;
+    int i = tid;
+    float4 xv = (i < nvec) ? tk_load_x(x4, xa4, i) : zero4;
     float4 ov = zero4;
     if (A.pro == FL_PRO_RMSNORM) ov = (i < nvec) ? __ldg(g4 + i) : zero4;
     else if (A.pro == FL_PRO_SILUMUL) ov = (i < nvec) ? __ldcg(b4 + i) : zero4;
@@ -120,7 +257,7 @@ __device__ __forceinline__ void tk_prologue(const fl_mv_args &A, int K, fl_block
         const int inext = i + TK_NT;
         float4 xn = zero4, on = zero4;
         if (base + TK_NT < nvec) {
-            xn = (inext < nvec) ? load_x(inext) : zero4;
+            xn = (inext < nvec) ? tk_load_x(x4, xa4, inext) : zero4;
             if (A.pro == FL_PRO_RMSNORM) on = (inext < nvec) ? __ldg(g4 + inext) : zero4;
             else if (A.pro == FL_PRO_SILUMUL) on = (inext < nvec) ? __ldcg(b4 + inext) : zero4;
         }
@@ -138,46 +275,57 @@ __device__ __forceinline__ void tk_prologue(const fl_mv_args &A, int K, fl_block
                 v[c] = __fmul_rn(__half2float(__ushort_as_half(__ldg(A.silu_tab + h))), o[c]);
             }
         }
-        float amax = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-        const float d = __fdiv_rn(amax, 127.f);
-        const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
-        int q[4], sum = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            q[c] = max(-128, min(127, __float2int_rn(__fmul_rn(v[c], id))));
-            sum += q[c];
-        }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-        if (i < nvec) {
-            fl_block_q8_0 *yb = ysm + (i >> 3);
-            const uint32_t packed = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[1] & 0xFF) << 8) | ((uint32_t)(q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
-            ((uint32_t *)yb->qs)[i & 7] = packed;
-            if ((i & 7) == 0) {
-                yb->d = d;
-                yb->s = __fmul_rn(d, (float)sum);
-            }
-        }
+        tk_quant_group(v, i, nvec, ysm);
         xv = xn; ov = on; i = inext;
     }
     tk_bar_consumers(15);
 }
 
+// ---- epilogue of one unit (lane 0 of the warp that holds the complete sums a, b) --------------------
+__device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, float a, float b, int n_past) {
+    const fl_mv_args &A = ph.a;
+    if (ph.swiglu) {
+        const uint16_t h = __half_as_ushort(__float2half_rn(a));
+        A.seg_dst[0][u] = __fmul_rn(__half2float(__ushort_as_half(__ldg(A.silu_tab + h))), b);
+        return;
+    }
+    const int r2 = 2 * u;
+    if (A.epi == FL_EPI_QKV) {
+        if (seg < 2) {
+            const int ip = (r2 % A.head_dim) >> 1;
+            const float2 cs = __ldg((const float2 *)A.rope_cs + (size_t)n_past * (A.head_dim >> 1) + ip);
+            const float y0 = __fmaf_rn(a, cs.x, -__fmul_rn(b, cs.y));
+            const float y1 = __fmaf_rn(a, cs.y, __fmul_rn(b, cs.x));
+            float *o = (seg == 0) ? (A.seg_dst[0] + r2) : (A.kcache + (size_t)n_past * A.n_embd + r2);
+            *(float2 *)o = make_float2(y0, y1);
+        } else {
+            A.vcache[(size_t)r2 * A.n_ctx + n_past] = a;
+            A.vcache[(size_t)(r2 + 1) * A.n_ctx + n_past] = b;
+        }
+        return;
+    }
+    float *dst = A.seg_dst[seg] + r2;
+    if (A.epi == FL_EPI_RESADD) {
+        const float2 r = __ldcg((const float2 *)(A.res + r2));
+        a = __fadd_rn(a, r.x);
+        b = __fadd_rn(b, r.y);
+    }
+    *(float2 *)dst = make_float2(a, b);
+}
+
 // ---- main loop of a matvec phase for one consumer warp ------------------------------------------------
 template <int TYPE, int NFULL>
-__device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const fd_slice &sl, int T0, const fl_block_q8_0 *ysm,
+__device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, const fl_block_q8_0 *ysm,
                                            float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane) {
     constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
     const fl_mv_args &A = ph.a;
-    const int S = prm.S, R = ph.R, kparts = ph.kparts, G = ph.G;
+    const int S = prm.S, kparts = ph.kparts, G = ph.G;
     const int tg = warp / TK_WPG, wl = warp % TK_WPG;
     const int p = wl % kparts, g = wl / kparts;
     const int b0 = p * ph.P;
     const int b1 = min(ph.nb, b0 + ph.P);
+    const uint32_t row_bytes = ph.row_bytes;
+    const bool swiglu = ph.swiglu != 0;
 
     fd_yprep yp[FD_NBL];
     bool valid[FD_NBL];
@@ -193,65 +341,51 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
             for (int q = 0; q < 4; q++) { yp[j].ye[q] = 0; yp[j].yo[q] = 0; }
         }
     }
-    const bool pair = (A.epi == FL_EPI_QKV);
-    const bool staged = (kparts > 1) || pair;
-    const int target = pair ? 2 * kparts : kparts;
-    const int n_past = pair ? *A.n_past : 0;
+    const int n_past = (A.epi == FL_EPI_QKV) ? *A.n_past : 0;
     const int ntiles = sl.ntiles;
     int t = ((tg - (T0 & 3)) + 4) & 3;                 // first tile of this phase owned by the warp's tile group
     int T = T0 + t;
-    int s = T % S;
-    uint32_t par = (uint32_t)(T / S) & 1u;
+    const uint32_t rounds = tk_div((uint32_t)T, prm.s_magic, prm.s_shift);
+    int s = T - (int)rounds * S;
+    uint32_t par = rounds & 1u;
     for (; t < ntiles; t += TK_TG) {
-        int seg, row0, rows;
-        fd_tile_of(sl, R, t, seg, row0, rows);
+        int seg, unit0, nunits;
+        tk_tile_of(sl, G, t, seg, unit0, nunits);
         fl_mbar_wait(bar0 + 8u * s, par);
-        const uint8_t *tile = stage0 + (size_t)s * prm.slot_bytes;
-        float *dseg = A.seg_dst[seg];
-        for (int rr = g; rr < rows; rr += G) {
-            const uint8_t *wrow = tile + (size_t)rr * ph.row_bytes + (size_t)(b0 + lane) * BB;
-            float acc = 0.0f, accm = 0.0f;
+        if (g < nunits) {
+            const uint8_t *tile = stage0 + (size_t)s * prm.slot_bytes;
+            // default: pair rows are adjacent; swiglu: [nunits rows of w1][nunits rows of w3]
+            const uint8_t *rowA = tile + (size_t)(swiglu ? g : 2 * g) * row_bytes + (size_t)(b0 + lane) * BB;
+            const uint8_t *rowB = rowA + (size_t)(swiglu ? nunits : 1) * row_bytes;
+            float accA = 0.0f, accmA = 0.0f, accB = 0.0f, accmB = 0.0f;
 #pragma unroll
             for (int j = 0; j < FD_NBL; j++) {
-                if (j < NFULL) fd_block<TYPE>(wrow + (size_t)(32 * j) * BB, yp[j], acc, accm);
-                else if (valid[j]) fd_block<TYPE>(wrow + (size_t)(32 * j) * BB, yp[j], acc, accm);
+                if (j < NFULL || valid[j]) {
+                    fd_block<TYPE>(rowA + (size_t)(32 * j) * BB, yp[j], accA, accmA);
+                    fd_block<TYPE>(rowB + (size_t)(32 * j) * BB, yp[j], accB, accmB);
+                }
             }
-            float tot = fl_warp_sum(acc);
-            if (TYPE == FL_TYPE_Q4_1) tot = __fadd_rn(tot, fl_warp_sum(accm));
+            float totA = fl_warp_sum(accA), totB = fl_warp_sum(accB);
+            if (TYPE == FL_TYPE_Q4_1) {
+                totA = __fadd_rn(totA, fl_warp_sum(accmA));
+                totB = __fadd_rn(totB, fl_warp_sum(accmB));
+            }
             if (lane == 0) {
-                const int row = row0 + rr;
-                if (!staged) {
-                    dseg[row] = (A.epi == FL_EPI_RESADD) ? __fadd_rn(tot, __ldcg(A.res + row)) : tot;
+                const int u = unit0 + g;
+                if (kparts == 1) {
+                    tk_epilogue(ph, seg, u, totA, totB, n_past);
                 } else {
-                    volatile float *rb = rowbuf + (size_t)s * TK_RMAX * 4;
-                    rb[rr * kparts + p] = tot;
+                    volatile float *rb = rowbuf + ((size_t)s * TK_GMAX + g) * 8;      // [2 rows][kparts <= 4]
+                    rb[p] = totA;
+                    rb[4 + p] = totB;
                     __threadfence_block();
-                    const int gid = pair ? (rr >> 1) : rr;
-                    const int old = atomicAdd(&cnt[s * TK_RMAX + gid], 1);
-                    if (old == target - 1) {
-                        cnt[s * TK_RMAX + gid] = 0;
+                    const int old = atomicAdd(&cnt[s * TK_GMAX + g], 1);
+                    if (old == kparts - 1) {                                            // last arriver combines, parts in index order
+                        cnt[s * TK_GMAX + g] = 0;
                         __threadfence_block();
-                        if (pair) {
-                            const int ra = gid << 1;
-                            float x0 = rb[ra * kparts], x1 = rb[(ra + 1) * kparts];
-                            for (int q = 1; q < kparts; q++) { x0 = __fadd_rn(x0, rb[ra * kparts + q]); x1 = __fadd_rn(x1, rb[(ra + 1) * kparts + q]); }
-                            const int r2 = row0 + ra;
-                            if (seg < 2) {
-                                const int ip = (r2 % A.head_dim) >> 1;
-                                const float2 cs = ((const float2 *)A.rope_cs)[(size_t)n_past * (A.head_dim >> 1) + ip];
-                                const float y0 = __fmaf_rn(x0, cs.x, -__fmul_rn(x1, cs.y));
-                                const float y1 = __fmaf_rn(x0, cs.y, __fmul_rn(x1, cs.x));
-                                float *o = (seg == 0) ? (dseg + r2) : (A.kcache + (size_t)n_past * A.n_embd + r2);
-                                o[0] = y0; o[1] = y1;
-                            } else {
-                                A.vcache[(size_t)r2 * A.n_ctx + n_past] = x0;
-                                A.vcache[(size_t)(r2 + 1) * A.n_ctx + n_past] = x1;
-                            }
-                        } else {
-                            float tsum = rb[rr * kparts];
-                            for (int q = 1; q < kparts; q++) tsum = __fadd_rn(tsum, rb[rr * kparts + q]);
-                            dseg[row] = (A.epi == FL_EPI_RESADD) ? __fadd_rn(tsum, __ldcg(A.res + row)) : tsum;
-                        }
+                        float x0 = rb[0], x1 = rb[4];
+                        for (int q = 1; q < kparts; q++) { x0 = __fadd_rn(x0, rb[q]); x1 = __fadd_rn(x1, rb[4 + q]); }
+                        tk_epilogue(ph, seg, u, x0, x1, n_past);
                     }
                 }
             }
@@ -264,20 +398,32 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
 }
 
 // ---- attention phase: one head, all consumer threads of the CTA ------------------------------------
-__device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params &prm, float *sc, double *red, int head, int warp, int lane, int tid) {
+__device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params &prm, float *sc, double *red, int head, int part_id, int warp, int lane, int tid) {
     float *redf = (float *)(red + 20);                // [16] floats; red[0..16] are the double partials
-    float *part = sc + ph.n_ctx;                      // [TK_NT]
+    float *part = sc + ph.n_ctx;                      // [FD_PV_SUBS][dims of this CTA]
     const int hd = ph.head_dim;
     const int n_pos = *ph.a.n_past + 1;
     const float *q = ph.q + (size_t)head * hd;
+    const float *kbase = ph.kcache + (size_t)head * hd;
     for (int j0 = warp * 4; j0 < n_pos; j0 += TK_CW * 4) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int e = lane; e < hd; e += 32) {
-            const float qe = __ldcg(q + e);
+        if (hd == 128) {                              // all loads of the 4 positions in flight at once
+            float qe[4], kv[4][4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int j = min(j0 + u, n_pos - 1);
-                acc[u] = __fmaf_rn(__ldcg(ph.kcache + (size_t)j * ph.k_row_stride + (size_t)head * hd + e), qe, acc[u]);
+            for (int c = 0; c < 4; c++) {
+                qe[c] = __ldcg(q + lane + 32 * c);
+#pragma unroll
+                for (int u = 0; u < 4; u++) kv[u][c] = __ldcg(kbase + (size_t)min(j0 + u, n_pos - 1) * ph.k_row_stride + lane + 32 * c);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int u = 0; u < 4; u++) acc[u] = __fmaf_rn(kv[u][c], qe[c], acc[u]);
+        } else {
+            for (int e = lane; e < hd; e += 32) {
+                const float qe = __ldcg(q + e);
+#pragma unroll
+                for (int u = 0; u < 4; u++) acc[u] = __fmaf_rn(__ldcg(kbase + (size_t)min(j0 + u, n_pos - 1) * ph.k_row_stride + e), qe, acc[u]);
             }
         }
 #pragma unroll
@@ -307,37 +453,39 @@ __device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params
     double tot = 0.0;
     for (int w = 0; w < TK_CW; w++) tot += red[w];
     const float inv = (float)(1.0 / tot);
-    tk_bar_consumers(12);
+    // each thread normalises exactly the entries it wrote above, so no barrier is needed in between
     for (int j = tid; j < n_pos; j += TK_NT) sc[j] = __fmul_rn(sc[j], inv);
     tk_bar_consumers(12);
-    const int npt = 256 / hd;                           // same split of the positions as k_attn_decode (256 threads): same summation order
-    if (npt >= 1 && tid < npt * hd) {
-        const int d = tid % hd, sub = tid / hd;
-        const float *v = ph.vcache + ((size_t)head * hd + d) * ph.n_ctx;
-        const int n4 = n_pos >> 2;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int i = sub; i < n4; i += npt) {
-            const float4 vv = __ldcg((const float4 *)(v + 4 * i));
-            a0 = __fmaf_rn(vv.x, sc[4 * i + 0], a0);
-            a1 = __fmaf_rn(vv.y, sc[4 * i + 1], a1);
-            a2 = __fmaf_rn(vv.z, sc[4 * i + 2], a2);
-            a3 = __fmaf_rn(vv.w, sc[4 * i + 3], a3);
-        }
-        float acc = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
-        if (sub == 0)
-            for (int j = 4 * n4; j < n_pos; j++) acc = __fmaf_rn(__ldcg(v + j), sc[j], acc);
-        part[tid] = acc;
+    // P*V in the canonical order of fd_pv_partials; this CTA owns dpc = head_dim / head_split output dimensions
+    const int dpc = hd / ph.head_split;
+    const int tpd = TK_NT / dpc;                        // threads per dimension (<= FD_PV_SUBS)
+    const int ns = FD_PV_SUBS / tpd;
+    {
+        const int dl = tid % dpc, sub0 = (tid / dpc) * ns;
+        const int d = part_id * dpc + dl;
+        fd_pv_store_partials<4>(ph.vcache + ((size_t)head * hd + d) * ph.n_ctx, sc, n_pos, sub0, ns, part, dpc, dl);
     }
     tk_bar_consumers(12);
-    if (tid < hd) {
-        float acc = part[tid];
-        for (int u = 1; u < npt; u++) acc = __fadd_rn(acc, part[tid + u * hd]);
-        ph.out[(size_t)head * hd + tid] = acc;
+    if (tid < dpc) ph.out[(size_t)head * hd + part_id * dpc + tid] = fd_pv_combine(part, dpc, tid);
+}
+// pull the cached positions of this head towards L2 while the grid is still finishing the previous phase
+__device__ __forceinline__ void tk_attention_prefetch(const tk_phase &ph, int head, int part_id, int tid) {
+    const int hd = ph.head_dim, n_past = *ph.a.n_past;
+    const int kl = (hd * 4 + 127) / 128;                                  // 128-byte lines per cached K row of the head
+    for (int i = tid; i < n_past * kl; i += TK_NT) {
+        const float *p = ph.kcache + (size_t)(i / kl) * ph.k_row_stride + (size_t)head * hd + (i % kl) * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+    const int dpc = hd / ph.head_split;
+    const int vl = (n_past * 4 + 127) / 128;
+    for (int i = tid; i < dpc * vl; i += TK_NT) {
+        const float *p = ph.vcache + ((size_t)head * hd + part_id * dpc + i / vl) * ph.n_ctx + (i % vl) * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
 }
 
 template <int TYPE>
-__device__ __forceinline__ void tk_consume_dispatch(const tk_phase &ph, const tk_params &prm, const fd_slice &sl, int T0, const fl_block_q8_0 *ysm,
+__device__ __forceinline__ void tk_consume_dispatch(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, const fl_block_q8_0 *ysm,
                                                     float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane) {
     switch (ph.nfull) {
         case 4: tk_consume<TYPE, 4>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane); break;
@@ -352,10 +500,14 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
     uint64_t *bars = (uint64_t *)smem;
     fl_block_q8_0 *ysm = (fl_block_q8_0 *)(smem + prm.off_y);
     double *red = (double *)(smem + prm.off_red);            // 32 doubles
-    float *rowbuf = (float *)(smem + prm.off_rowbuf);        // [S][TK_RMAX][4]
-    int *cnt = (int *)(smem + prm.off_cnt);                  // [S][TK_RMAX]
-    float *sc = (float *)(smem + prm.off_sc);                // attention: [n_ctx] + [TK_NT]
+    float *rowbuf = (float *)(smem + prm.off_rowbuf);        // [S][TK_GMAX][2][4]
+    int *cnt = (int *)(smem + prm.off_cnt);                  // [S][TK_GMAX]
+    float *sc = (float *)(smem + prm.off_sc);                // attention: [n_ctx] + [256]
     uint8_t *stage0 = smem + prm.off_stage0;
+    // Phase descriptors are read from shared memory: every gpu-scope acquire invalidates L1, so reading them from
+    // global would put a chain of L2 round trips right behind each grid barrier.  Descriptor pi+1 is copied in
+    // by warp 15 while phase pi runs and becomes visible through the next barrier's bar.sync.
+    __shared__ __align__(16) tk_phase phs[2];
     const int S = prm.S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = fl_smem_u32(bars);
@@ -376,17 +528,34 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
             int s = 0;
             uint32_t par = 1;
             for (int pi = 0; pi < prm.n_phases; pi++) {
-                const tk_phase &ph = prm.phases[pi];
-                if (ph.kind != TK_PH_MATVEC) continue;
-                const fd_slice sl = fd_make_slice(ph.a, ph.mtot, ph.R);
+                // The descriptor lives in global memory and L1 is invalidated by every grid barrier of the consumers, so
+                // everything the tile loop needs is pulled into registers once per phase (one L2 round trip, hidden
+                // because the producer runs ahead).
+                const tk_phase *gp = prm.phases + pi;
+                if (__ldg(&gp->kind) != TK_PH_MATVEC) continue;
+                const int G = __ldg(&gp->G), lgG = __ldg(&gp->lgG), swiglu = __ldg(&gp->swiglu);
+                const int m0 = __ldg(&gp->units[0]), m1 = __ldg(&gp->units[1]), m2 = __ldg(&gp->units[2]);
+                const uint32_t row_bytes = __ldg(&gp->row_bytes);
+                const uint8_t *w0 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[0]);
+                const uint8_t *w1 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[1]);
+                const uint8_t *w2 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[2]);
+                const tk_slice sl = tk_make_slice_u(m0, m1, m2, lgG, prm.grid_magic, prm.grid_shift);
                 for (int t = 0; t < sl.ntiles; t++) {
-                    int seg, row0, rows;
-                    fd_tile_of(sl, ph.R, t, seg, row0, rows);
+                    int seg, unit0, nunits;
+                    tk_tile_of(sl, G, t, seg, unit0, nunits);
                     fl_mbar_wait(bar0 + 8u * (S + s), par);
-                    const uint32_t bytes = (uint32_t)rows * ph.row_bytes;
-                    const uint8_t *src = (const uint8_t *)ph.a.seg_w[seg] + (size_t)row0 * ph.row_bytes;
-                    fl_mbar_expect_tx(bar0 + 8u * s, bytes);
-                    fl_bulk_g2s_hint(fl_smem_u32(stage0 + (size_t)s * prm.slot_bytes), src, bytes, bar0 + 8u * s, pol);
+                    const uint32_t dst = fl_smem_u32(stage0 + (size_t)s * prm.slot_bytes);
+                    if (swiglu) {
+                        const uint32_t half = (uint32_t)nunits * row_bytes;
+                        fl_mbar_expect_tx(bar0 + 8u * s, 2 * half);
+                        fl_bulk_g2s_hint(dst, w0 + (size_t)unit0 * row_bytes, half, bar0 + 8u * s, pol);
+                        fl_bulk_g2s_hint(dst + half, w1 + (size_t)unit0 * row_bytes, half, bar0 + 8u * s, pol);
+                    } else {
+                        const uint32_t bytes = 2u * (uint32_t)nunits * row_bytes;
+                        const uint8_t *w = seg == 0 ? w0 : seg == 1 ? w1 : w2;
+                        fl_mbar_expect_tx(bar0 + 8u * s, bytes);
+                        fl_bulk_g2s_hint(dst, w + (size_t)(2 * unit0) * row_bytes, bytes, bar0 + 8u * s, pol);
+                    }
                     if (++s == S) { s = 0; par ^= 1u; }
                 }
             }
@@ -396,27 +565,44 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
 
     // ------------------------------ consumers ------------------------------
     const int tid = threadIdx.x;
-    for (int i = tid; i < S * TK_RMAX; i += TK_NT) cnt[i] = 0;
+    for (int i = tid; i < S * TK_GMAX; i += TK_NT) cnt[i] = 0;
+    static_assert(sizeof(tk_phase) % 4 == 0 && sizeof(tk_phase) / 4 <= TK_NT, "descriptor copy is one word per thread");
+    if (warp == TK_CW - 1)
+        for (int i = lane; i < (int)(sizeof(tk_phase) / 4); i += 32) ((uint32_t *)&phs[0])[i] = ((const uint32_t *)&prm.phases[0])[i];
+    tk_bar_consumers(15);
     asm volatile("bar.sync 14, %0;" ::"r"(TK_NT + 32) : "memory");     // mbarriers initialised
     int T0 = 0;
     unsigned epoch = 0;
     for (int pi = 0; pi < prm.n_phases; pi++) {
-        const tk_phase &ph = prm.phases[pi];
+        const tk_phase &ph = phs[pi & 1];
         unsigned long long *pr = (prm.prof && tid == 0) ? prm.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 4 : nullptr;
         if (pr) pr[0] = tk_now();
+        // attention: CTA b works on head b / head_split, output dimensions part b % head_split
+        const bool attn_here = ph.kind == TK_PH_ATTN && (int)blockIdx.x < ph.n_head * ph.head_split;
+        const int a_head = attn_here ? (int)blockIdx.x / ph.head_split : 0, a_part = attn_here ? (int)blockIdx.x % ph.head_split : 0;
+        if (attn_here) tk_attention_prefetch(ph, a_head, a_part, tid);
         if (pi > 0) {
             epoch++;
             tk_grid_sync(prm.grid_bar, epoch * gridDim.x);               // results of phase pi-1 are visible everywhere
         }
         if (pr) pr[1] = tk_now();
+        // Descriptor pi+1: the load is issued now, the store into phs[(pi+1)&1] (which nobody reads any more: everybody is
+        // past the barrier) happens after this phase's prologue, so its L2 latency hides behind the prologue's own loads.
+        uint32_t next_word = 0;
+        const bool copies = tid < (int)(sizeof(tk_phase) / 4) && pi + 1 < prm.n_phases;
+        if (copies) next_word = __ldcg((const uint32_t *)&prm.phases[pi + 1] + tid);
         if (ph.kind == TK_PH_ATTN) {
-            if ((int)blockIdx.x < ph.n_head) tk_attention(ph, prm, sc, red, blockIdx.x, warp, lane, tid);
+            if (attn_here) tk_attention(ph, prm, sc, red, a_head, a_part, warp, lane, tid);
+            if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
             if (pr) pr[2] = pr[3] = tk_now();
             continue;
         }
-        tk_prologue(ph.a, ph.nb * 32, ysm, red, warp, lane, tid);
+        const int K = ph.nb * 32;
+        if (ph.a.pro == FL_PRO_SILUMUL || (ph.a.pro == FL_PRO_RMSNORM && (K >> 2) > TK_PRO_G * TK_NT)) tk_prologue_general(ph.a, K, ysm, red, warp, lane, tid);
+        else tk_prologue_fast(ph.a, K, ysm, red, warp, lane, tid);
+        if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
         if (pr) pr[2] = tk_now();
-        const fd_slice sl = fd_make_slice(ph.a, ph.mtot, ph.R);
+        const tk_slice sl = tk_make_slice_u(ph.units[0], ph.units[1], ph.units[2], ph.lgG, prm.grid_magic, prm.grid_shift);
         if (ph.a.type == FL_TYPE_Q4_0) tk_consume_dispatch<FL_TYPE_Q4_0>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane);
         else                           tk_consume_dispatch<FL_TYPE_Q4_1>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane);
         T0 += sl.ntiles;
@@ -436,6 +622,14 @@ struct fl_token_plan_impl {
     int n_kernels = 0;
 };
 
+// n / d for n < 2^31 as umulhi(n, magic) >> shift: with 2^k < d < 2^(k+1), magic = ceil(2^(32+k) / d) < 2^32
+static void tk_magic(uint32_t d, uint32_t &magic, uint32_t &shift) {
+    uint32_t k = 0;
+    while ((2u << k) <= d) k++;                 // k = floor(log2 d)
+    shift = k;
+    magic = ((d & (d - 1)) == 0) ? 0u : (uint32_t)((((uint64_t)1 << (32 + k)) + d - 1) / d);
+}
+
 static int tk_geometry(tk_phase &ph, size_t &tile_bytes) {
     const fl_mv_args &a = ph.a;
     const int bb = fl_block_bytes(a.type);
@@ -451,24 +645,30 @@ static int tk_geometry(tk_phase &ph, size_t &tile_bytes) {
     int nfull = std::min(P, last) / 32;
     if (nfull > FD_NBL) nfull = FD_NBL;
     if (nfull == 1) nfull = 0;
-    int G = TK_WPG / kparts;
-    int R = std::max(2, G);                       // even tiles keep rope pairs together
-    if (R > TK_RMAX) R = TK_RMAX;
-    int mtot = 0;
-    for (int i = 0; i < a.nseg; i++) {
-        FL_REQUIRE(a.seg_rows[i] > 0 && a.seg_rows[i] % 2 == 0 && ((uintptr_t)a.seg_w[i] & 15) == 0, "token kernel: bad segment %d", i);
-        mtot += a.seg_rows[i];
+    const int G = TK_WPG / kparts;
+    ph.units[0] = ph.units[1] = ph.units[2] = 0;
+    if (ph.swiglu) {
+        ph.units[0] = a.seg_rows[0];
+    } else {
+        for (int i = 0; i < a.nseg; i++) {
+            FL_REQUIRE(a.seg_rows[i] > 0 && a.seg_rows[i] % 2 == 0, "token kernel: segment %d has an odd row count", i);
+            ph.units[i] = a.seg_rows[i] / 2;
+        }
     }
+    for (int i = 0; i < a.nseg; i++) {
+        FL_REQUIRE(((uintptr_t)a.seg_w[i] & 15) == 0, "token kernel: segment %d is not 16-byte aligned", i);
+        FL_REQUIRE(a.epi == FL_EPI_QKV || ph.swiglu || ((uintptr_t)a.seg_dst[i] & 7) == 0, "token kernel: output %d is not 8-byte aligned", i);
+    }
+    FL_REQUIRE(a.epi != FL_EPI_RESADD || ((uintptr_t)a.res & 7) == 0, "token kernel: residual is not 8-byte aligned");
+    FL_REQUIRE((long)ph.units[0] + ph.units[1] + ph.units[2] < (1 << 23), "token kernel: too many rows");
     ph.kind = TK_PH_MATVEC;
-    ph.nb = nb; ph.kparts = kparts; ph.G = G; ph.R = R; ph.P = P; ph.nfull = nfull; ph.mtot = mtot; ph.row_bytes = (uint32_t)row_bytes;
-    tile_bytes = (size_t)R * row_bytes;
+    ph.nb = nb; ph.kparts = kparts; ph.G = G; ph.lgG = (G == 4) ? 2 : (G == 2) ? 1 : 0; ph.P = P; ph.nfull = nfull; ph.row_bytes = (uint32_t)row_bytes;
+    tile_bytes = (size_t)2 * G * row_bytes;
     return 0;
 }
 
 int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_t *silu_tab, const uint16_t *exp_tab, const void *rope_cs, void **out) {
     std::vector<tk_phase> phases((size_t)n_steps);
-    size_t max_tile = 0, max_y = 0;
-    int max_ctx = 0;
     for (int i = 0; i < n_steps; i++) {
         tk_phase &ph = phases[i];
         memset(&ph, 0, sizeof(ph));
@@ -478,12 +678,43 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
             ph.k_row_stride = steps[i].k_row_stride; ph.n_head = steps[i].n_head; ph.head_dim = steps[i].head_dim; ph.n_ctx = steps[i].n_ctx;
             ph.scale = steps[i].scale;
             ph.a.n_past = steps[i].n_past;
-            FL_REQUIRE(ph.n_ctx % 4 == 0 && ph.head_dim <= 256 && 256 % ph.head_dim == 0 && ph.n_head <= 148, "token kernel: unsupported attention shape");
-            max_ctx = std::max(max_ctx, ph.n_ctx);
         } else {
+            ph.kind = TK_PH_MATVEC;
             ph.a = steps[i].mv;
             ph.a.silu_tab = silu_tab;
             ph.a.rope_cs = rope_cs;
+        }
+    }
+    // w1|w3 followed by a silu(.)*(.) prologue over exactly their outputs: fuse the activation into the first phase
+    for (int i = 0; i + 1 < n_steps; i++) {
+        tk_phase &p0 = phases[i], &p1 = phases[i + 1];
+        if (p0.kind != TK_PH_MATVEC || p1.kind != TK_PH_MATVEC) continue;
+        const fl_mv_args &a = p0.a;
+        if (a.nseg == 2 && a.epi == FL_EPI_STORE && a.seg_rows[0] == a.seg_rows[1] && p1.a.pro == FL_PRO_SILUMUL && p1.a.x == a.seg_dst[0] &&
+            p1.a.b == a.seg_dst[1] && p1.a.K == a.seg_rows[0] && p1.a.xadd == nullptr) {
+            p0.swiglu = 1;
+            p1.a.pro = FL_PRO_PLAIN;            // reads silu(w1 x) * (w3 x) from seg_dst[0]
+            p1.a.b = nullptr;
+        }
+    }
+    size_t max_tile = 0, max_y = 0;
+    int max_ctx = 0;
+    int sm_count = 0;
+    {
+        int dev0 = 0;
+        FL_CUDA_OK(cudaGetDevice(&dev0));
+        FL_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev0));
+    }
+    for (int i = 0; i < n_steps; i++) {
+        tk_phase &ph = phases[i];
+        if (ph.kind == TK_PH_ATTN) {
+            FL_REQUIRE(ph.n_ctx % 4 == 0 && ph.head_dim >= 32 && ph.head_dim <= 256 && (ph.head_dim & (ph.head_dim - 1)) == 0 && ph.n_head <= sm_count,
+                       "token kernel: unsupported attention shape");
+            ph.head_split = 1;
+            for (int c = 4; c > 1; c /= 2)
+                if (c * ph.n_head <= sm_count && ph.head_dim / c >= 32) { ph.head_split = c; break; }
+            max_ctx = std::max(max_ctx, ph.n_ctx);
+        } else {
             size_t tb = 0;
             if (tk_geometry(ph, tb)) return -1;
             max_tile = std::max(max_tile, tb);
@@ -504,13 +735,15 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
         p.off_y = ((size_t)(2 * S) * 8 + 127) & ~(size_t)127;
         p.off_red = (p.off_y + max_y + 127) & ~(size_t)127;
         p.off_rowbuf = (p.off_red + 32 * sizeof(double) + 127) & ~(size_t)127;
-        p.off_cnt = (p.off_rowbuf + (size_t)S * TK_RMAX * 4 * sizeof(float) + 127) & ~(size_t)127;
-        p.off_sc = (p.off_cnt + (size_t)S * TK_RMAX * sizeof(int) + 127) & ~(size_t)127;
-        off = (p.off_sc + ((size_t)max_ctx + TK_NT) * sizeof(float) + 127) & ~(size_t)127;
+        p.off_cnt = (p.off_rowbuf + (size_t)S * TK_GMAX * 8 * sizeof(float) + 127) & ~(size_t)127;
+        p.off_sc = (p.off_cnt + (size_t)S * TK_GMAX * sizeof(int) + 127) & ~(size_t)127;
+        off = (p.off_sc + ((size_t)max_ctx + FD_PV_SUBS * 256) * sizeof(float) + 127) & ~(size_t)127;
         if (off + (size_t)S * slot <= (size_t)optin - 1024) break;
     }
     p.off_stage0 = (uint32_t)off;
     p.S = S;
+    tk_magic((uint32_t)sm, p.grid_magic, p.grid_shift);
+    tk_magic((uint32_t)S, p.s_magic, p.s_shift);
     p.slot_bytes = (uint32_t)slot;
     p.n_phases = n_steps;
     p.exp_tab = exp_tab;
