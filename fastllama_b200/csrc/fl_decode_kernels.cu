@@ -116,14 +116,18 @@ __global__ void __launch_bounds__(FD_MAX_THREADS, 1) k_mv_fused(const fd_params 
         float scale = 1.0f;
         if (A.pro == FL_PRO_RMSNORM) {
             double acc = 0.0;
-#pragma unroll 4
-            for (int i = tid; i < nvec; i += NT) {
-                float4 v = __ldcg(x4 + i);
-                if (xa4) { const float4 w = __ldcg(xa4 + i); v.x = __fadd_rn(v.x, w.x); v.y = __fadd_rn(v.y, w.y); v.z = __fadd_rn(v.z, w.z); v.w = __fadd_rn(v.w, w.w); }
-                acc += (double)__fmul_rn(v.x, v.x);
-                acc += (double)__fmul_rn(v.y, v.y);
-                acc += (double)__fmul_rn(v.z, v.z);
-                acc += (double)__fmul_rn(v.w, v.w);
+            // thread t adds the values of the 8-element units t, t + NT, ... in order (the token kernel's order)
+            for (int u = tid; u < (nvec >> 1); u += NT) {
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const int i = 2 * u + k;
+                    float4 v = __ldcg(x4 + i);
+                    if (xa4) { const float4 w = __ldcg(xa4 + i); v.x = __fadd_rn(v.x, w.x); v.y = __fadd_rn(v.y, w.y); v.z = __fadd_rn(v.z, w.z); v.w = __fadd_rn(v.w, w.w); }
+                    acc += (double)__fmul_rn(v.x, v.x);
+                    acc += (double)__fmul_rn(v.y, v.y);
+                    acc += (double)__fmul_rn(v.z, v.z);
+                    acc += (double)__fmul_rn(v.w, v.w);
+                }
             }
             acc = fl_warp_sum_d(acc);
             if (lane == 0) red[warp] = acc;

@@ -34,7 +34,6 @@
 #define TK_WPG 4                 // warps per tile group = kparts * G
 #define TK_GMAX 4                // units (row pairs) per tile at most
 #define TK_THREADS (TK_NT + 32)
-#define TK_PRO_G 4               // float4 groups a thread keeps in registers in the single-pass prologues
 
 enum { TK_PH_MATVEC = 0, TK_PH_ATTN = 1 };
 
@@ -116,169 +115,187 @@ __device__ __forceinline__ void tk_tile_of(const tk_slice &sl, int G, int t, int
     nunits = min(G, n - j * G);
 }
 
-// ---- prologues: q8_0 activations of the phase into shared memory (same arithmetic as k_mv_fused) ----
-// One float4 group -> quantised quarter of a block; 8 consecutive lanes hold one 32-element block.
-__device__ __forceinline__ void tk_quant_group(float v[4], int i, int nvec, fl_block_q8_0 *ysm) {
-    float amax = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+// ---- prologue: the phase's activations, q8_0-quantised and prepared for the block dot, into shared memory ----
+// Same arithmetic as quantize_row_q8_0 + fd_prep_y (so the same bits as k_mv_fused), different work split: one
+// thread quantises one HALF block (16 consecutive values, two lanes per block), which needs one shuffle per
+// reduction and two divisions per block pair instead of per float4 group -- 2.5x fewer issue slots than the
+// float4-group scheme, and this code runs redundantly in every CTA behind every grid barrier.
+// A prepared block is 48 bytes: ye[4] | yo[4] | d, s, c, pad (three conflict-free LDS.128 per lane in the consumers).
+struct __align__(16) tk_yblock {
+    uint32_t ye[4], yo[4];       // even / odd elements of each 8-element group, as in fd_yprep
+    float d, s;
+    int c, pad;                  // c = -8 * sum(q) (the q4_0 offset); q4_1 consumers ignore it
+};
+
+// A thread quantises E consecutive values (E = 8: four lanes per block, E = 16: two lanes per block).
+template <int E>
+__device__ __forceinline__ void tk_load_vals(const float4 *p4, int u, float v[E], bool cg) {
+#pragma unroll
+    for (int k = 0; k < E / 4; k++) {
+        const float4 t = cg ? __ldcg(p4 + (E / 4) * u + k) : __ldg(p4 + (E / 4) * u + k);
+        v[4 * k + 0] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+    }
+}
+template <int E>
+__device__ __forceinline__ void tk_zero_vals(float v[E]) {
+#pragma unroll
+    for (int k = 0; k < E; k++) v[k] = 0.f;
+}
+// x (+ xadd) of unit u
+template <int E>
+__device__ __forceinline__ void tk_load_x(const fl_mv_args &A, int u, float v[E]) {
+    tk_load_vals<E>((const float4 *)A.x, u, v, true);
+    if (A.xadd) {
+        float w[E];
+        tk_load_vals<E>((const float4 *)A.xadd, u, w, true);
+#pragma unroll
+        for (int k = 0; k < E; k++) v[k] = __fadd_rn(v[k], w[k]);
+    }
+}
+template <int E>
+__device__ __forceinline__ void tk_store_vals(float *dst, int u, const float v[E]) {
+#pragma unroll
+    for (int k = 0; k < E / 4; k++) ((float4 *)dst)[(E / 4) * u + k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+// v: the E final values of unit u (all lanes of the warp call this; `valid` lanes store)
+template <int E>
+__device__ __forceinline__ void tk_quant(const float v[E], int u, bool valid, tk_yblock *ysm) {
+    float m0 = 0.f, m1 = 0.f;                        // two chains: max is order-independent
+#pragma unroll
+    for (int k = 0; k < E; k += 2) { m0 = fmaxf(m0, fabsf(v[k])); m1 = fmaxf(m1, fabsf(v[k + 1])); }
+    float amax = fmaxf(m0, m1);
     amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+    if (E == 8) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
     const float d = __fdiv_rn(amax, 127.f);
     const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
-    int q[4], sum = 0;
+    int q[E], s0 = 0, s1 = 0;
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        q[c] = max(-128, min(127, __float2int_rn(__fmul_rn(v[c], id))));
-        sum += q[c];
+    for (int k = 0; k < E; k += 2) {
+        q[k] = max(-128, min(127, __float2int_rn(__fmul_rn(v[k], id))));
+        q[k + 1] = max(-128, min(127, __float2int_rn(__fmul_rn(v[k + 1], id))));
+        s0 += q[k]; s1 += q[k + 1];
     }
+    int sum = s0 + s1;
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-    if (i < nvec) {
-        fl_block_q8_0 *yb = ysm + (i >> 3);
-        const uint32_t packed = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[1] & 0xFF) << 8) | ((uint32_t)(q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
-        ((uint32_t *)yb->qs)[i & 7] = packed;
-        if ((i & 7) == 0) {
-            yb->d = d;
-            yb->s = __fmul_rn(d, (float)sum);
+    if (E == 8) sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (valid) {
+        constexpr int NW = E / 8;                    // 8-element groups of the block this thread owns
+        constexpr int UPB = 32 / E;                  // units per block
+        tk_yblock *yb = ysm + u / UPB;
+        const int part = u % UPB;
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+            const uint32_t ye = (uint32_t)(q[8 * j + 0] & 0xFF) | ((uint32_t)(q[8 * j + 2] & 0xFF) << 8) | ((uint32_t)(q[8 * j + 4] & 0xFF) << 16) | ((uint32_t)(q[8 * j + 6] & 0xFF) << 24);
+            const uint32_t yo = (uint32_t)(q[8 * j + 1] & 0xFF) | ((uint32_t)(q[8 * j + 3] & 0xFF) << 8) | ((uint32_t)(q[8 * j + 5] & 0xFF) << 16) | ((uint32_t)(q[8 * j + 7] & 0xFF) << 24);
+            yb->ye[NW * part + j] = ye;
+            yb->yo[NW * part + j] = yo;
         }
+        if (part == 0) *(uint4 *)&yb->d = make_uint4(__float_as_uint(d), __float_as_uint(__fmul_rn(d, (float)sum)), (uint32_t)(-8 * sum), 0u);
     }
 }
-__device__ __forceinline__ float4 tk_load_x(const float4 *x4, const float4 *xa4, int idx) {
-    float4 v = __ldcg(x4 + idx);
-    if (xa4) { const float4 w = __ldcg(xa4 + idx); v.x = __fadd_rn(v.x, w.x); v.y = __fadd_rn(v.y, w.y); v.z = __fadd_rn(v.z, w.z); v.w = __fadd_rn(v.w, w.w); }
-    return v;
+// plain / silu*mul prologue body for one unit size
+template <int E>
+__device__ __forceinline__ void tk_prologue_nonorm(const fl_mv_args &A, int K, tk_yblock *ysm, int warp, int tid) {
+    const int nu = K / E;
+    for (int u0 = 0; u0 < nu; u0 += TK_NT) {
+        if (u0 + warp * 32 >= nu) break;                 // warp-uniform
+        const int u = u0 + tid;
+        const bool valid = u < nu;
+        float v[E];
+        if (valid) tk_load_x<E>(A, u, v); else tk_zero_vals<E>(v);
+        if (A.sum_out && blockIdx.x == 0 && valid) tk_store_vals<E>(A.sum_out, u, v);
+        if (A.pro == FL_PRO_SILUMUL) {
+            float bm[E];
+            if (valid) tk_load_vals<E>((const float4 *)A.b, u, bm, true); else tk_zero_vals<E>(bm);
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                const uint16_t hh = __half_as_ushort(__float2half_rn(v[k]));
+                v[k] = __fmul_rn(__half2float(__ushort_as_half(__ldg(A.silu_tab + hh))), bm[k]);
+            }
+        }
+        tk_quant<E>(v, u, valid, ysm);
+    }
 }
 
-// Single pass: all of a thread's loads are issued before anything is consumed (one L2 round trip), the
-// rms_norm reduction runs on the registers, and the values are quantised from the registers.
-// Requires nvec <= TK_PRO_G * TK_NT for PRO_RMSNORM (K <= 8192); PRO_PLAIN loops over chunks.
-__device__ __forceinline__ void tk_prologue_fast(const fl_mv_args &A, int K, fl_block_q8_0 *ysm, double *red, int warp, int lane, int tid) {
-    const int nvec = K >> 2;
-    const float4 *x4 = (const float4 *)A.x;
-    const float4 *xa4 = (const float4 *)A.xadd;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (A.pro == FL_PRO_RMSNORM) {
-        const float4 *g4 = (const float4 *)A.gamma;
-        float4 xr[TK_PRO_G], gr[TK_PRO_G];
+// rms_norm * gamma prologue.  RES > 0: the thread's RES 8-element units stay in registers between the sum of squares
+// and the quantisation (K <= 8 * RES * TK_NT); RES == 0: two passes over L2.
+// Sum of squares: thread t adds the values of units t, t + NT, ... in order (k_mv_fused uses the same order).
+template <int RES>
+__device__ __forceinline__ void tk_prologue_norm(const fl_mv_args &A, int K, tk_yblock *ysm, double *red, int warp, int lane, int tid) {
+    constexpr int E = 8, NR = RES > 0 ? RES : 1;
+    const int nu = K >> 3;
+    float v[NR][E], gm[NR][E];
+    double acc = 0.0;
+    if (RES > 0) {
 #pragma unroll
-        for (int g = 0; g < TK_PRO_G; g++) {
-            const int i = tid + g * TK_NT;
-            xr[g] = (i < nvec) ? tk_load_x(x4, xa4, i) : zero4;
-            gr[g] = (i < nvec) ? __ldg(g4 + i) : zero4;
+        for (int r = 0; r < NR; r++) {
+            const int u = tid + r * TK_NT;
+            if (u < nu) { tk_load_x<E>(A, u, v[r]); tk_load_vals<E>((const float4 *)A.gamma, u, gm[r], false); }
+            else { tk_zero_vals<E>(v[r]); tk_zero_vals<E>(gm[r]); }
         }
-        double acc = 0.0;
 #pragma unroll
-        for (int g = 0; g < TK_PRO_G; g++) {
-            acc += (double)__fmul_rn(xr[g].x, xr[g].x);
-            acc += (double)__fmul_rn(xr[g].y, xr[g].y);
-            acc += (double)__fmul_rn(xr[g].z, xr[g].z);
-            acc += (double)__fmul_rn(xr[g].w, xr[g].w);
-        }
-        acc = fl_warp_sum_d(acc);
-        if (lane == 0) red[warp] = acc;
-        tk_bar_consumers(15);
-        if (warp == 0) {                                             // the double division is ~100 instructions: one warp, not sixteen
-            double t = 0.0;
+        for (int r = 0; r < NR; r++)
 #pragma unroll
-            for (int w = 0; w < TK_CW; w++) t += red[w];
-            const float mean = (float)(t / (double)K);
-            if (lane == 0) ((float *)(red + 16))[0] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, 1e-6f)));
-        }
-        tk_bar_consumers(15);
-        const float scale = ((float *)(red + 16))[0];
+            for (int k = 0; k < E; k++) acc += (double)__fmul_rn(v[r][k], v[r][k]);
+    } else {
+        for (int u = tid; u < nu; u += TK_NT) {
+            tk_load_x<E>(A, u, v[0]);
 #pragma unroll
-        for (int g = 0; g < TK_PRO_G; g++) {
-            const int i = tid + g * TK_NT;
-            if (g * TK_NT < nvec) {                                  // warp-uniform
-                float v[4] = {xr[g].x, xr[g].y, xr[g].z, xr[g].w};
-                const float o[4] = {gr[g].x, gr[g].y, gr[g].z, gr[g].w};
-                if (A.sum_out && blockIdx.x == 0 && i < nvec) ((float4 *)A.sum_out)[i] = xr[g];
-#pragma unroll
-                for (int c = 0; c < 4; c++) v[c] = __fmul_rn(o[c], __fmul_rn(v[c], scale));
-                if (A.normed_out && blockIdx.x == 0 && i < nvec) ((float4 *)A.normed_out)[i] = make_float4(v[0], v[1], v[2], v[3]);
-                tk_quant_group(v, i, nvec, ysm);
-            }
-        }
-    } else {   // FL_PRO_PLAIN
-        for (int base = 0; base < nvec; base += TK_PRO_G * TK_NT) {
-            float4 xr[TK_PRO_G];
-#pragma unroll
-            for (int g = 0; g < TK_PRO_G; g++) {
-                const int i = base + tid + g * TK_NT;
-                xr[g] = (i < nvec) ? tk_load_x(x4, xa4, i) : zero4;
-            }
-#pragma unroll
-            for (int g = 0; g < TK_PRO_G; g++) {
-                const int i = base + tid + g * TK_NT;
-                if (base + g * TK_NT < nvec) {
-                    float v[4] = {xr[g].x, xr[g].y, xr[g].z, xr[g].w};
-                    if (A.sum_out && blockIdx.x == 0 && i < nvec) ((float4 *)A.sum_out)[i] = xr[g];
-                    tk_quant_group(v, i, nvec, ysm);
-                }
-            }
+            for (int k = 0; k < E; k++) acc += (double)__fmul_rn(v[0][k], v[0][k]);
         }
     }
+    acc = fl_warp_sum_d(acc);
+    if (lane == 0) red[warp] = acc;
     tk_bar_consumers(15);
-}
-
-// General path (any K, PRO_SILUMUL): two passes with software-pipelined loads, as in k_mv_fused.
-__device__ __noinline__ void tk_prologue_general(const fl_mv_args &A, int K, fl_block_q8_0 *ysm, double *red, int warp, int lane, int tid) {
-    const int nvec = K >> 2;
-    const float4 *x4 = (const float4 *)A.x;
-    const float4 *xa4 = (const float4 *)A.xadd;
-    float scale = 1.0f;
-    if (A.pro == FL_PRO_RMSNORM) {
-        double acc = 0.0;
-#pragma unroll 4
-        for (int i = tid; i < nvec; i += TK_NT) {
-            const float4 v = tk_load_x(x4, xa4, i);
-            acc += (double)__fmul_rn(v.x, v.x);
-            acc += (double)__fmul_rn(v.y, v.y);
-            acc += (double)__fmul_rn(v.z, v.z);
-            acc += (double)__fmul_rn(v.w, v.w);
-        }
-        acc = fl_warp_sum_d(acc);
-        if (lane == 0) red[warp] = acc;
-        tk_bar_consumers(15);
+    if (warp == 0) {                                         // the double division is ~100 instructions: one warp, not sixteen
         double t = 0.0;
+#pragma unroll
         for (int w = 0; w < TK_CW; w++) t += red[w];
         const float mean = (float)(t / (double)K);
-        scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, 1e-6f)));
-    }
-    const float4 *g4 = (const float4 *)A.gamma, *b4 = (const float4 *)A.b;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    int i = tid;
-    float4 xv = (i < nvec) ? tk_load_x(x4, xa4, i) : zero4;
-    float4 ov = zero4;
-    if (A.pro == FL_PRO_RMSNORM) ov = (i < nvec) ? __ldg(g4 + i) : zero4;
-    else if (A.pro == FL_PRO_SILUMUL) ov = (i < nvec) ? __ldcg(b4 + i) : zero4;
-    for (int base = warp * 32; base < nvec; base += TK_NT) {
-        const int inext = i + TK_NT;
-        float4 xn = zero4, on = zero4;
-        if (base + TK_NT < nvec) {
-            xn = (inext < nvec) ? tk_load_x(x4, xa4, inext) : zero4;
-            if (A.pro == FL_PRO_RMSNORM) on = (inext < nvec) ? __ldg(g4 + inext) : zero4;
-            else if (A.pro == FL_PRO_SILUMUL) on = (inext < nvec) ? __ldcg(b4 + inext) : zero4;
-        }
-        float v[4] = {xv.x, xv.y, xv.z, xv.w};
-        const float o[4] = {ov.x, ov.y, ov.z, ov.w};
-        if (A.sum_out && blockIdx.x == 0 && i < nvec) ((float4 *)A.sum_out)[i] = xv;
-        if (A.pro == FL_PRO_RMSNORM) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) v[c] = __fmul_rn(o[c], __fmul_rn(v[c], scale));
-            if (A.normed_out && blockIdx.x == 0 && i < nvec) ((float4 *)A.normed_out)[i] = make_float4(v[0], v[1], v[2], v[3]);
-        } else if (A.pro == FL_PRO_SILUMUL) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const uint16_t h = __half_as_ushort(__float2half_rn(v[c]));
-                v[c] = __fmul_rn(__half2float(__ushort_as_half(__ldg(A.silu_tab + h))), o[c]);
-            }
-        }
-        tk_quant_group(v, i, nvec, ysm);
-        xv = xn; ov = on; i = inext;
+        if (lane == 0) ((float *)(red + 16))[0] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, 1e-6f)));
     }
     tk_bar_consumers(15);
+    const float scale = ((float *)(red + 16))[0];
+    if (RES > 0) {
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            if (r * TK_NT + warp * 32 < nu) {                // warp-uniform
+                const int u = tid + r * TK_NT;
+                const bool valid = u < nu;
+                if (A.sum_out && blockIdx.x == 0 && valid) tk_store_vals<E>(A.sum_out, u, v[r]);
+#pragma unroll
+                for (int k = 0; k < E; k++) v[r][k] = __fmul_rn(gm[r][k], __fmul_rn(v[r][k], scale));
+                if (A.normed_out && blockIdx.x == 0 && valid) tk_store_vals<E>(A.normed_out, u, v[r]);
+                tk_quant<E>(v[r], u, valid, ysm);
+            }
+        }
+    } else {
+        for (int u0 = 0; u0 < nu; u0 += TK_NT) {
+            if (u0 + warp * 32 >= nu) break;
+            const int u = u0 + tid;
+            const bool valid = u < nu;
+            if (valid) { tk_load_x<E>(A, u, v[0]); tk_load_vals<E>((const float4 *)A.gamma, u, gm[0], false); }
+            else { tk_zero_vals<E>(v[0]); tk_zero_vals<E>(gm[0]); }
+            if (A.sum_out && blockIdx.x == 0 && valid) tk_store_vals<E>(A.sum_out, u, v[0]);
+#pragma unroll
+            for (int k = 0; k < E; k++) v[0][k] = __fmul_rn(gm[0][k], __fmul_rn(v[0][k], scale));
+            if (A.normed_out && blockIdx.x == 0 && valid) tk_store_vals<E>(A.normed_out, u, v[0]);
+            tk_quant<E>(v[0], u, valid, ysm);
+        }
+    }
+}
+
+__device__ __forceinline__ void tk_prologue(const fl_mv_args &A, int K, tk_yblock *ysm, double *red, int warp, int lane, int tid) {
+    const int nu8 = K >> 3;
+    if (A.pro == FL_PRO_RMSNORM) {
+        if (nu8 <= TK_NT) tk_prologue_norm<1>(A, K, ysm, red, warp, lane, tid);
+        else if (nu8 <= 2 * TK_NT) tk_prologue_norm<2>(A, K, ysm, red, warp, lane, tid);
+        else tk_prologue_norm<0>(A, K, ysm, red, warp, lane, tid);
+    } else if (nu8 <= TK_NT) {
+        tk_prologue_nonorm<8>(A, K, ysm, warp, tid);          // short vectors: latency matters, spread over all threads
+    } else {
+        tk_prologue_nonorm<16>(A, K, ysm, warp, tid);         // long vectors: issue slots matter
+    }
 }
 
 // ---- epilogue of one unit (lane 0 of the warp that holds the complete sums a, b) --------------------
@@ -315,7 +332,7 @@ __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, 
 
 // ---- main loop of a matvec phase for one consumer warp ------------------------------------------------
 template <int TYPE, int NFULL>
-__device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, const fl_block_q8_0 *ysm,
+__device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, const tk_yblock *ysm,
                                            float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane) {
     constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
     const fl_mv_args &A = ph.a;
@@ -334,7 +351,11 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
         const int ib = b0 + lane + 32 * j;
         valid[j] = (j < NFULL) || ib < b1;
         if (valid[j]) {
-            fd_prep_y<TYPE>(ysm + ib, yp[j]);
+            const uint4 e = *(const uint4 *)ysm[ib].ye, o = *(const uint4 *)ysm[ib].yo, m = *(const uint4 *)&ysm[ib].d;
+            yp[j].ye[0] = e.x; yp[j].ye[1] = e.y; yp[j].ye[2] = e.z; yp[j].ye[3] = e.w;
+            yp[j].yo[0] = o.x; yp[j].yo[1] = o.y; yp[j].yo[2] = o.z; yp[j].yo[3] = o.w;
+            yp[j].d = __uint_as_float(m.x); yp[j].s = __uint_as_float(m.y);
+            yp[j].c = (TYPE == FL_TYPE_Q4_0) ? (int)m.z : 0;
         } else {
             yp[j].d = 0.f; yp[j].s = 0.f; yp[j].c = 0;
 #pragma unroll
@@ -405,31 +426,41 @@ __device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params
     const int n_pos = *ph.a.n_past + 1;
     const float *q = ph.q + (size_t)head * hd;
     const float *kbase = ph.kcache + (size_t)head * hd;
-    for (int j0 = warp * 4; j0 < n_pos; j0 += TK_CW * 4) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        if (hd == 128) {                              // all loads of the 4 positions in flight at once
-            float qe[4], kv[4][4];
+    if (hd == 128) {                                  // 8 positions per warp pass, all 36 loads of a lane in flight at once
+        float qe[4];
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                qe[c] = __ldcg(q + lane + 32 * c);
+        for (int c = 0; c < 4; c++) qe[c] = __ldcg(q + lane + 32 * c);
+        for (int j0 = warp * 8; j0 < n_pos; j0 += TK_CW * 8) {
+            float kv[8][4], acc[8];
 #pragma unroll
-                for (int u = 0; u < 4; u++) kv[u][c] = __ldcg(kbase + (size_t)min(j0 + u, n_pos - 1) * ph.k_row_stride + lane + 32 * c);
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) kv[u][c] = __ldcg(kbase + (size_t)min(j0 + u, n_pos - 1) * ph.k_row_stride + lane + 32 * c);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                acc[u] = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[u] = __fmaf_rn(kv[u][c], qe[c], acc[u]);
             }
 #pragma unroll
-            for (int c = 0; c < 4; c++)
-#pragma unroll
-                for (int u = 0; u < 4; u++) acc[u] = __fmaf_rn(kv[u][c], qe[c], acc[u]);
-        } else {
+            for (int u = 0; u < 8; u++) {
+                const float a = fl_warp_sum(acc[u]);
+                if (lane == 0 && j0 + u < n_pos) sc[j0 + u] = __fmul_rn(a, ph.scale);
+            }
+        }
+    } else {
+        for (int j0 = warp * 4; j0 < n_pos; j0 += TK_CW * 4) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
             for (int e = lane; e < hd; e += 32) {
                 const float qe = __ldcg(q + e);
 #pragma unroll
                 for (int u = 0; u < 4; u++) acc[u] = __fmaf_rn(__ldcg(kbase + (size_t)min(j0 + u, n_pos - 1) * ph.k_row_stride + e), qe, acc[u]);
             }
-        }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const float a = fl_warp_sum(acc[u]);
-            if (lane == 0 && j0 + u < n_pos) sc[j0 + u] = __fmul_rn(a, ph.scale);
+            for (int u = 0; u < 4; u++) {
+                const float a = fl_warp_sum(acc[u]);
+                if (lane == 0 && j0 + u < n_pos) sc[j0 + u] = __fmul_rn(a, ph.scale);
+            }
         }
     }
     tk_bar_consumers(12);
@@ -485,7 +516,7 @@ __device__ __forceinline__ void tk_attention_prefetch(const tk_phase &ph, int he
 }
 
 template <int TYPE>
-__device__ __forceinline__ void tk_consume_dispatch(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, const fl_block_q8_0 *ysm,
+__device__ __forceinline__ void tk_consume_dispatch(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, const tk_yblock *ysm,
                                                     float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane) {
     switch (ph.nfull) {
         case 4: tk_consume<TYPE, 4>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane); break;
@@ -498,7 +529,7 @@ __device__ __forceinline__ void tk_consume_dispatch(const tk_phase &ph, const tk
 __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = (uint64_t *)smem;
-    fl_block_q8_0 *ysm = (fl_block_q8_0 *)(smem + prm.off_y);
+    tk_yblock *ysm = (tk_yblock *)(smem + prm.off_y);
     double *red = (double *)(smem + prm.off_red);            // 32 doubles
     float *rowbuf = (float *)(smem + prm.off_rowbuf);        // [S][TK_GMAX][2][4]
     int *cnt = (int *)(smem + prm.off_cnt);                  // [S][TK_GMAX]
@@ -508,6 +539,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
     // global would put a chain of L2 round trips right behind each grid barrier.  Descriptor pi+1 is copied in
     // by warp 15 while phase pi runs and becomes visible through the next barrier's bar.sync.
     __shared__ __align__(16) tk_phase phs[2];
+    __shared__ tk_slice sl_sh;                                // this CTA's slice of the current phase (computed once, read by all)
     const int S = prm.S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = fl_smem_u32(bars);
@@ -598,11 +630,12 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
             continue;
         }
         const int K = ph.nb * 32;
-        if (ph.a.pro == FL_PRO_SILUMUL || (ph.a.pro == FL_PRO_RMSNORM && (K >> 2) > TK_PRO_G * TK_NT)) tk_prologue_general(ph.a, K, ysm, red, warp, lane, tid);
-        else tk_prologue_fast(ph.a, K, ysm, red, warp, lane, tid);
+        if (tid == TK_NT - 1) sl_sh = tk_make_slice_u(ph.units[0], ph.units[1], ph.units[2], ph.lgG, prm.grid_magic, prm.grid_shift);
+        tk_prologue(ph.a, K, ysm, red, warp, lane, tid);
         if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
+        tk_bar_consumers(15);                                    // activations, slice and next descriptor are in shared memory
         if (pr) pr[2] = tk_now();
-        const tk_slice sl = tk_make_slice_u(ph.units[0], ph.units[1], ph.units[2], ph.lgG, prm.grid_magic, prm.grid_shift);
+        const tk_slice &sl = sl_sh;
         if (ph.a.type == FL_TYPE_Q4_0) tk_consume_dispatch<FL_TYPE_Q4_0>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane);
         else                           tk_consume_dispatch<FL_TYPE_Q4_1>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane);
         T0 += sl.ntiles;
@@ -718,7 +751,7 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
             size_t tb = 0;
             if (tk_geometry(ph, tb)) return -1;
             max_tile = std::max(max_tile, tb);
-            max_y = std::max(max_y, (size_t)ph.nb * 40);
+            max_y = std::max(max_y, (size_t)ph.nb * sizeof(tk_yblock));
         }
     }
     int dev = 0, sm = 0, optin = 0;
