@@ -108,6 +108,10 @@ __device__ __forceinline__ void fl_bulk_g2s_hint(uint32_t dst_smem, const void *
         "l"(src), "r"(bytes), "r"(bar), "l"(policy)
         : "memory");
 }
+// ask L2 to fetch [src, src + bytes) (16-byte granular); no completion signal, no shared memory involved
+__device__ __forceinline__ void fl_bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint64_t fl_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));

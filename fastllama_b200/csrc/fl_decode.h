@@ -14,3 +14,6 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
 int flk_token_plan_launch(cudaStream_t st, void *plan);
 int flk_token_plan_destroy(void *plan);
 int flk_token_plan_profile(void *plan, unsigned long long *out, size_t max_words, int *n_ctas);
+int flk_token_plan_error(void *plan);
+// fl_runtime.cu: the peer-mapped buffers of fl_comm_shared_alloc (nullptr when there are none)
+const void *const *fl_shared_peers(int *rank, int *world);

@@ -321,6 +321,7 @@ extern "C" int fl_dev_rope_table(int n_dims, int n_pos) {
 extern "C" int fl_dev_mv_fused(const fl_mv_args *args) {
     FL_NEED_INIT();
     fl_mv_args a = *args;
+    FL_REQUIRE(a.n_xpeer == 0 && a.n_dst_peer == 0, "fl_dev_mv_fused: peer inputs / outputs exist only inside the token kernel");
     a.silu_tab = g.tab_silu;
     if (a.epi == FL_EPI_QKV) {
         FL_REQUIRE(g.rope_cs && g.rope_dims == a.head_dim && g.rope_pos >= a.n_ctx,
@@ -351,6 +352,10 @@ extern "C" int fl_token_plan_profile(void *plan, unsigned long long *out, size_t
     FL_NEED_INIT();
     FL_CUDA_OK(cudaStreamSynchronize(g.stream));
     return flk_token_plan_profile(plan, out, max_words, n_ctas);
+}
+extern "C" int fl_token_plan_error(void *plan) {
+    FL_NEED_INIT();
+    return flk_token_plan_error(plan);
 }
 extern "C" int fl_token_plan_destroy(void *plan) {
     FL_NEED_INIT();
@@ -446,6 +451,75 @@ extern "C" int fl_comm_allgather_f32(const float *send, float *recv, size_t n_pe
     }
     FL_NCCL_OK(g_nccl.AllGather(send, recv, n_per_rank, /*ncclFloat32*/ 7, g_nccl.comm, g.stream));
     fl_count_launch();
+    return 0;
+}
+
+// ---- peer-mapped scratch (CUDA IPC over the NCCL communicator) for collectives fused into the token kernel ----
+struct fl_shared_comm {
+    void *peers[8] = {nullptr};
+    size_t bytes = 0;
+    bool ready = false;
+};
+static fl_shared_comm g_shared;
+const void *const *fl_shared_peers(int *rank, int *world) {          // used by fl_token_kernel.cu
+    *rank = g_nccl.rank;
+    *world = g_nccl.world;
+    return g_shared.ready ? (const void *const *)g_shared.peers : nullptr;
+}
+extern "C" int fl_comm_shared_alloc(size_t bytes, void **peers_out) {
+    FL_NEED_INIT();
+    const int world = g_nccl.world, rank = g_nccl.rank;
+    FL_REQUIRE(world > 1 && world <= 8 && g_nccl.comm, "fl_comm_shared_alloc: needs an initialised communicator of 2..8 ranks");
+    FL_REQUIRE(bytes >= 4096, "fl_comm_shared_alloc: the first 4096 bytes are reserved for barrier flags");
+    if (g_shared.ready) {
+        FL_REQUIRE(bytes <= g_shared.bytes, "fl_comm_shared_alloc: already allocated with %zu bytes", g_shared.bytes);
+        for (int r = 0; r < world; r++) peers_out[r] = g_shared.peers[r];
+        return 0;
+    }
+    void *local = nullptr;
+    FL_CUDA_OK(cudaMalloc(&local, bytes));
+    FL_CUDA_OK(cudaMemset(local, 0, bytes));
+    cudaIpcMemHandle_t mine;
+    FL_CUDA_OK(cudaIpcGetMemHandle(&mine, local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    char *d_all = nullptr;
+    FL_CUDA_OK(cudaMalloc((void **)&d_all, 64 * (size_t)(world + 1)));
+    FL_CUDA_OK(cudaMemcpyAsync(d_all + 64 * (size_t)world, &mine, 64, cudaMemcpyHostToDevice, g.stream));
+    FL_NCCL_OK(g_nccl.AllGather(d_all + 64 * (size_t)world, d_all, 16, /*ncclFloat32*/ 7, g_nccl.comm, g.stream));
+    cudaIpcMemHandle_t all[8];
+    FL_CUDA_OK(cudaMemcpyAsync(all, d_all, 64 * (size_t)world, cudaMemcpyDeviceToHost, g.stream));
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    cudaFree(d_all);
+    int ok = 1;
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { g_shared.peers[r] = local; continue; }
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            fl_set_error("fl_comm_shared_alloc: cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            ok = 0;
+            break;
+        }
+        g_shared.peers[r] = p;
+    }
+    // every rank must agree, or some would wait inside the kernel for peers that took the NCCL path
+    float *d_ok = nullptr;
+    FL_CUDA_OK(cudaMalloc((void **)&d_ok, sizeof(float)));
+    const float okf = ok ? 0.f : 1.f;
+    FL_CUDA_OK(cudaMemcpyAsync(d_ok, &okf, sizeof(float), cudaMemcpyHostToDevice, g.stream));
+    FL_NCCL_OK(g_nccl.AllReduce(d_ok, d_ok, 1, /*ncclFloat32*/ 7, /*ncclSum*/ 0, g_nccl.comm, g.stream));
+    float bad = 0.f;
+    FL_CUDA_OK(cudaMemcpyAsync(&bad, d_ok, sizeof(float), cudaMemcpyDeviceToHost, g.stream));
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    cudaFree(d_ok);
+    if (bad != 0.f) {
+        if (ok) fl_set_error("fl_comm_shared_alloc: a peer could not map the shared buffers");
+        return -1;
+    }
+    g_shared.bytes = bytes;
+    g_shared.ready = true;
+    for (int r = 0; r < world; r++) peers_out[r] = g_shared.peers[r];
     return 0;
 }
 

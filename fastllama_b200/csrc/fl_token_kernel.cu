@@ -55,12 +55,17 @@ struct tk_phase {
 struct tk_params {
     const tk_phase *phases;
     int n_phases;
-    unsigned *grid_bar;
+    unsigned *grid_bar;              // [0] arrival counter (zeroed per launch), [32] error flag
+    unsigned *xflags_local;          // tensor parallel: flags[q * 32] is written by rank q (through its peer mapping of this buffer)
+    unsigned *xflags_peer[8];        // rank p's flag array as mapped here
+    int rank, world;
+    int xrelease_sys;                // FASTLLAMA_B200_TP_RELEASE_SYS: every CTA releases at sys scope (measured 644 vs 697 tok/s at TP2)
     const uint16_t *exp_tab;
     unsigned long long *prof;      // optional: [n_phases][gridDim.x][4] globaltimer stamps of thread 0
     int S;
     uint32_t grid_magic, grid_shift, s_magic, s_shift;  // n / d == umulhi(n, magic) >> shift (magic 0: d is a power of two, n >> shift); exact for n < 2^31
     uint32_t slot_bytes;
+    int l2_prefetch;
     uint32_t off_y, off_red, off_rowbuf, off_cnt, off_sc, off_stage0;
 };
 
@@ -71,17 +76,52 @@ __device__ __forceinline__ unsigned long long tk_now() {
 }
 __device__ __forceinline__ void tk_bar_consumers(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(TK_NT) : "memory"); }
 
-// Grid barrier: CTA barrier, then one thread publishes the CTA's writes with a gpu-scope release increment
-// and spins on an acquire load; the second CTA barrier hands the acquired view to the other threads, which
-// read shared activations with ld.global.cg only.
-__device__ __forceinline__ void tk_grid_sync(unsigned *bar, unsigned target) {
+// Every spin in this kernel is bounded: after 2 s (a peer GPU that never launched, a bug) the waiter raises the error flag
+// and everybody falls through; the host reports it (fl_token_plan_error) instead of the GPU hanging.
+__device__ __forceinline__ void tk_wait_ge(const unsigned *p, unsigned target, bool sys, unsigned *err, unsigned who) {
+    unsigned long long t0 = 0;
+    for (unsigned n = 1;; n++) {
+        unsigned v;
+        if (sys) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");     // caller fences after the wait
+        else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        if ((int)(v - target) >= 0) return;
+        if ((n & 1023u) == 0) {
+            if (*(volatile unsigned *)err) return;
+            const unsigned long long t = tk_now();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) {
+                if (atomicExch(err, 1u) == 0u) { err[1] = who; err[2] = target; err[3] = v; err[4] = blockIdx.x; }   // first failure, for the host's message
+                return;
+            }
+        }
+    }
+}
+// Grid barrier: CTA barrier, then one thread publishes the CTA's writes with a gpu-scope release increment and spins on
+// an acquire load; the second CTA barrier hands the acquired view to the other threads, which read shared activations
+// with ld.global.cg only.  xe != 0 extends it across the tensor-parallel GPUs: once the local grid has arrived, CTA 0
+// raises this rank's flag in every peer's memory (sys-scope release over NVLink) and every CTA waits for all peers' flags.
+__device__ __forceinline__ void tk_grid_sync(const tk_params &prm, unsigned target, unsigned xe) {
     tk_bar_consumers(13);
     if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-        unsigned v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-        } while (v < target);
+        unsigned *err = prm.grid_bar + 32;
+        // The phase that just ended may have stored to peer memory.  A gpu-scope release per CTA is enough: CTA 0 acquires all of
+        // them and then fences at sys scope before raising the flag, and causality order composes across the two scopes.
+        if (xe && prm.xrelease_sys) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prm.grid_bar) : "memory");
+        else asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(prm.grid_bar) : "memory");
+        tk_wait_ge(prm.grid_bar, target, false, err, 0x100u);
+        if (xe) {
+            if (blockIdx.x == 0) {
+                asm volatile("fence.acq_rel.sys;" ::: "memory");
+                for (int p = 0; p < prm.world; p++)
+                    if (p != prm.rank) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(prm.xflags_peer[p] + 32 * prm.rank), "r"(xe) : "memory");
+            }
+            for (int q = 0; q < prm.world; q++)
+                if (q != prm.rank) {
+                    tk_wait_ge(prm.xflags_local + 32 * q, xe, true, err, 0x200u + (unsigned)q);
+                    unsigned v;                                   // the acquire that orders the data reads behind the flag
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(prm.xflags_local + 32 * q) : "memory");
+                }
+        }
     }
     tk_bar_consumers(13);
 }
@@ -141,10 +181,16 @@ __device__ __forceinline__ void tk_zero_vals(float v[E]) {
 #pragma unroll
     for (int k = 0; k < E; k++) v[k] = 0.f;
 }
-// x (+ xadd) of unit u
+// x (+ the other ranks' partial sums, in rank order: slots of the local peer-written buffer) (+ xadd) of unit u
 template <int E>
 __device__ __forceinline__ void tk_load_x(const fl_mv_args &A, int u, float v[E]) {
     tk_load_vals<E>((const float4 *)A.x, u, v, true);
+    for (int r = 0; r < A.n_xpeer; r++) {
+        float w[E];
+        tk_load_vals<E>((const float4 *)A.xpeer[r], u, w, true);
+#pragma unroll
+        for (int k = 0; k < E; k++) v[k] = __fadd_rn(v[k], w[k]);
+    }
     if (A.xadd) {
         float w[E];
         tk_load_vals<E>((const float4 *)A.xadd, u, w, true);
@@ -328,6 +374,7 @@ __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, 
         b = __fadd_rn(b, r.y);
     }
     *(float2 *)dst = make_float2(a, b);
+    for (int r = 0; r < A.n_dst_peer; r++) *(float2 *)(A.dst_peer[r] + r2) = make_float2(a, b);     // posted stores over NVLink
 }
 
 // ---- main loop of a matvec phase for one consumer warp ------------------------------------------------
@@ -572,6 +619,22 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
                 const uint8_t *w1 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[1]);
                 const uint8_t *w2 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[2]);
                 const tk_slice sl = tk_make_slice_u(m0, m1, m2, lgG, prm.grid_magic, prm.grid_shift);
+                // Optional: ask L2 for this CTA's whole share of the phase now (the producer gets here while the consumers are
+                // still about a ring's worth of tiles inside the previous phase).
+                if (prm.l2_prefetch) {
+                    for (int t = 0; t < sl.ntiles; t++) {
+                        int seg, unit0, nunits;
+                        tk_tile_of(sl, G, t, seg, unit0, nunits);
+                        if (swiglu) {
+                            const uint32_t half = (uint32_t)nunits * row_bytes;
+                            fl_bulk_prefetch_l2(w0 + (size_t)unit0 * row_bytes, half);
+                            fl_bulk_prefetch_l2(w1 + (size_t)unit0 * row_bytes, half);
+                        } else {
+                            const uint8_t *w = seg == 0 ? w0 : seg == 1 ? w1 : w2;
+                            fl_bulk_prefetch_l2(w + (size_t)(2 * unit0) * row_bytes, 2u * (uint32_t)nunits * row_bytes);
+                        }
+                    }
+                }
                 for (int t = 0; t < sl.ntiles; t++) {
                     int seg, unit0, nunits;
                     tk_tile_of(sl, G, t, seg, unit0, nunits);
@@ -605,6 +668,10 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
     asm volatile("bar.sync 14, %0;" ::"r"(TK_NT + 32) : "memory");     // mbarriers initialised
     int T0 = 0;
     unsigned epoch = 0;
+    // cross-GPU epochs continue across launches AND plans: the running count lives next to the flags (word 8 * 32 of the
+    // rank's own shared buffer), so flags left behind by earlier launches can never satisfy a later wait
+    unsigned xepoch = 0;
+    if (prm.world > 1 && tid == 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(xepoch) : "l"(prm.xflags_local + 8 * 32) : "memory");
     for (int pi = 0; pi < prm.n_phases; pi++) {
         const tk_phase &ph = phs[pi & 1];
         unsigned long long *pr = (prm.prof && tid == 0) ? prm.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 4 : nullptr;
@@ -615,7 +682,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         if (attn_here) tk_attention_prefetch(ph, a_head, a_part, tid);
         if (pi > 0) {
             epoch++;
-            tk_grid_sync(prm.grid_bar, epoch * gridDim.x);               // results of phase pi-1 are visible everywhere
+            const bool xgpu = ph.kind == TK_PH_MATVEC && ph.a.n_xpeer > 0;   // this phase reads the other GPUs' partial results
+            if (xgpu) xepoch++;
+            tk_grid_sync(prm, epoch * gridDim.x, xgpu ? xepoch : 0u);   // results of phase pi-1 are visible everywhere
         }
         if (pr) pr[1] = tk_now();
         // Descriptor pi+1: the load is issued now, the store into phs[(pi+1)&1] (which nobody reads any more: everybody is
@@ -626,6 +695,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         if (ph.kind == TK_PH_ATTN) {
             if (attn_here) tk_attention(ph, prm, sc, red, a_head, a_part, warp, lane, tid);
             if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
+            tk_bar_consumers(15);                                // the next iteration reads the new descriptor before its grid barrier
             if (pr) pr[2] = pr[3] = tk_now();
             continue;
         }
@@ -641,6 +711,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         T0 += sl.ntiles;
         if (pr) pr[3] = tk_now();
     }
+    if (prm.world > 1 && blockIdx.x == 0 && tid == 0) prm.xflags_local[8 * 32] = xepoch;     // next launch continues from here
 }
 
 // =================================================================================================
@@ -779,6 +850,9 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     tk_magic((uint32_t)S, p.s_magic, p.s_shift);
     p.slot_bytes = (uint32_t)slot;
     p.n_phases = n_steps;
+    // measured on B200 (round 1): prefetching a whole phase competes with the demand loads of the phase still running
+    // (7B decode 49.6 vs 45.8 us per layer), so it is opt-in
+    p.l2_prefetch = getenv("FASTLLAMA_B200_L2_PREFETCH") ? 1 : 0;
     p.exp_tab = exp_tab;
     pl->smem = off + (size_t)S * slot;
     FL_CUDA_OK(cudaMalloc((void **)&pl->d_phases, sizeof(tk_phase) * (size_t)n_steps));
@@ -786,6 +860,24 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     FL_CUDA_OK(cudaMalloc((void **)&pl->d_bar, 256));
     p.phases = pl->d_phases;
     p.grid_bar = pl->d_bar;
+    FL_CUDA_OK(cudaMemset(pl->d_bar, 0, 256));
+    p.rank = 0; p.world = 1; p.xflags_local = nullptr;
+    p.xrelease_sys = getenv("FASTLLAMA_B200_TP_RELEASE_SYS") ? 1 : 0;
+    for (int r = 0; r < 8; r++) p.xflags_peer[r] = nullptr;
+    bool uses_peers = false;
+    for (int i = 0; i < n_steps; i++) uses_peers = uses_peers || (phases[i].kind == TK_PH_MATVEC && phases[i].a.n_xpeer > 0);
+    if (uses_peers) {
+        int rank = 0, world = 1;
+        const void *const *peers = fl_shared_peers(&rank, &world);
+        if (!peers) { delete pl; fl_set_error("token kernel: steps read peer buffers but fl_comm_shared_alloc was never called"); return -1; }
+        p.rank = rank; p.world = world;
+        p.xflags_local = (unsigned *)peers[rank];
+        for (int r = 0; r < world; r++) p.xflags_peer[r] = (unsigned *)peers[r];
+        for (int i = 0; i < n_steps; i++)
+            if (phases[i].kind == TK_PH_MATVEC && phases[i].a.n_xpeer > 0 && phases[i].a.n_xpeer != world - 1) {
+                delete pl; fl_set_error("token kernel: a step lists %d peers in a communicator of %d", phases[i].a.n_xpeer, world); return -1;
+            }
+    }
     p.prof = nullptr;
     if (getenv("FASTLLAMA_B200_TOKEN_PROF")) {
         FL_CUDA_OK(cudaMalloc((void **)&pl->d_prof, sizeof(unsigned long long) * 4 * (size_t)n_steps * sm));
@@ -822,6 +914,16 @@ int flk_token_plan_profile(void *plan, unsigned long long *out, size_t max_words
     FL_CUDA_OK(cudaMemcpy(out, pl->d_prof, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     *n_ctas = pl->n_kernels;
     return 0;
+}
+
+int flk_token_plan_error(void *plan) {
+    fl_token_plan_impl *pl = (fl_token_plan_impl *)plan;
+    unsigned e[5] = {0, 0, 0, 0, 0};
+    if (pl && pl->d_bar && cudaMemcpy(e, pl->d_bar + 32, sizeof(e), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    if (e[0])
+        fl_set_error("token kernel barrier timeout: %s (code 0x%x), waited for %u, last saw %u, CTA %u, rank %d of %d", (e[1] & 0x200u) ? "peer flag" : "local grid counter",
+                     e[1], e[2], e[3], e[4], pl->prm.rank, pl->prm.world);
+    return (int)e[0];
 }
 
 int flk_token_plan_destroy(void *plan) {

@@ -586,6 +586,7 @@ bool g_verbose = false;
 
 struct Stats { uint64_t n_evals = 0; double last_us = 0, total_us = 0; uint64_t graph_replays = 0; } g_stats;
 bool g_profile = false;
+int g_decode_mode = 0;          // see ggml_b200_decode_mode()
 std::vector<ggml_b200_kernel_stat> g_kstats;
 void *g_pev0 = nullptr, *g_pev1 = nullptr;
 
@@ -709,6 +710,9 @@ extern "C" void ggml_b200_release_all(void) {
     }
     g_last_mirror = -1;
 }
+// how the last single-token eval ran: 0 = node-by-node executor, 1 = fused plan with one kernel per matrix group,
+// 2 = fused plan as one persistent kernel per token (fl_token_kernel.cu)
+extern "C" int ggml_b200_decode_mode(void) { return g_decode_mode; }
 extern "C" void ggml_b200_set_profile(int on) {
     ensure_backend();
     if (!g_pev0) { g_pev0 = fl_event_create(); g_pev1 = fl_event_create(); }
@@ -918,6 +922,10 @@ struct DecodeWs {
     float *xa = nullptr, *xb = nullptr, *q = nullptr, *att = nullptr, *ff = nullptr, *m1 = nullptr, *m3 = nullptr, *emb = nullptr, *logits = nullptr;
     float *part1 = nullptr, *part2 = nullptr, *logits_local = nullptr;
     int32_t *d_tok = nullptr;
+    // tensor parallelism: part1/part2 live in the peer-mapped buffer of fl_comm_shared_alloc when it is available, so the
+    // token kernel can sum the ranks' partial results itself (peers[r] = rank r's buffer as mapped on this rank)
+    void *peers[8] = {nullptr};
+    bool peer_mapped = false;
 };
 struct DecodeState {
     DecodePlan plan;            // the plan the captured graph was built from
@@ -969,6 +977,20 @@ void ensure_ws(DecodeWs &w, int n_embd, int n_ff, int n_vocab) {
     w.m1 = w.part2 + n_embd; w.m3 = w.m1 + n_ff; w.logits = w.m3 + n_ff; w.logits_local = w.logits + n_vocab;
     w.d_tok = (int32_t *)(w.logits_local + n_vocab);
     w.n_embd = n_embd; w.n_ff = n_ff; w.n_vocab = n_vocab;
+    w.peer_mapped = false;
+    if (fl_comm_world() > 1 && getenv("FASTLLAMA_B200_NO_PEER") == nullptr) {
+        // collective: every rank gets here on its first decode step
+        // layout of every rank's buffer: 4096 bytes of flags, then part1[world][n_embd], part2[world][n_embd]: slot r is
+        // written by rank r (into its own buffer and, over NVLink, into everybody else's)
+        const int world = fl_comm_world(), rank = fl_comm_rank();
+        if (fl_comm_shared_alloc(4096 + (size_t)2 * world * n_embd * sizeof(float), w.peers) == 0) {
+            w.part1 = (float *)((char *)w.peers[rank] + 4096) + (size_t)rank * n_embd;
+            w.part2 = w.part1 + (size_t)world * n_embd;
+            w.peer_mapped = true;
+        } else if (g_verbose) {
+            fprintf(stderr, "[ggml_b200] no peer-mapped buffers (%s): tensor-parallel decode keeps the NCCL path\n", fl_last_error());
+        }
+    }
 }
 
 // K-split shards of wo / w2 (tensor parallelism): blocks [blk0, blk0 + nblk) of every row, packed once
@@ -1200,9 +1222,32 @@ void issue_decode(const DecodePlan &P, const int *d_npast) {
 
 // The same steps as issue_decode, handed to the persistent token kernel (one cooperative launch per token;
 // fl_token_kernel.cu).  Returns nullptr when the shapes are outside what that kernel handles.
-void *make_token_plan(const DecodePlan &P, const int *d_npast) {
+void *make_token_plan(const DecodePlan &P, const DecodeWs &W, const int *d_npast) {
     std::vector<fl_token_step> steps;
-    auto mv = [&](const fl_mv_args &a) { fl_token_step s; memset(&s, 0, sizeof(s)); s.kind = 0; s.mv = a; steps.push_back(s); };
+    // tensor parallel: a K-split step also pushes its partial sums into the other ranks' buffers, and a step that used
+    // to read the all-reduced vector reads the ranks' slots of the LOCAL buffer instead, in rank order
+    const int rank = fl_comm_rank();
+    auto slot0 = [&](const float *mine) { return (const char *)mine - (size_t)rank * W.n_embd * sizeof(float); };   // slot of rank 0 in my buffer
+    auto mv = [&](const fl_mv_args &a0) {
+        fl_token_step s;
+        memset(&s, 0, sizeof(s));
+        s.kind = 0;
+        s.mv = a0;
+        if (P.world > 1 && (a0.x == W.part1 || a0.x == W.part2)) {
+            const char *base = slot0(a0.x);
+            s.mv.x = (const float *)base;
+            for (int r = 1; r < P.world; r++) s.mv.xpeer[r - 1] = (const float *)(base + (size_t)r * W.n_embd * sizeof(float));
+            s.mv.n_xpeer = P.world - 1;
+        }
+        if (P.world > 1 && a0.nseg == 1 && (a0.seg_dst[0] == W.part1 || a0.seg_dst[0] == W.part2)) {
+            const size_t off = (const char *)a0.seg_dst[0] - (const char *)W.peers[rank];
+            int n = 0;
+            for (int r = 0; r < P.world; r++)
+                if (r != rank) s.mv.dst_peer[n++] = (float *)((char *)W.peers[r] + off);
+            s.mv.n_dst_peer = n;
+        }
+        steps.push_back(s);
+    };
     const int hd = P.n_embd / P.n_head;
     for (const LayerPlan &Lc : P.layers) {
         fl_mv_args qkv = Lc.qkv;
@@ -1228,6 +1273,7 @@ void *make_token_plan(const DecodePlan &P, const int *d_npast) {
 void issue_decode_token_kernel(const DecodePlan &P, void *token_plan) {
     FLC(fl_dev_dequantize_rows(P.emb_type, P.emb_w, P.emb_stride, P.emb_K, P.emb_ids, 1, P.emb_dst, (size_t)P.emb_K));
     FLC(fl_token_plan_launch(token_plan));
+    if (P.world > 1) FLC(fl_comm_allgather_f32(P.logits_local, P.logits_all, (size_t)P.vocab_local));
 }
 
 // returns true when the graph was executed through the fused plan
@@ -1257,12 +1303,13 @@ bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, 
         FLC(fl_event_record(ev0));
         issue_decode(P, D.d_npast);
         FLC(fl_event_record(ev1));
+        g_decode_mode = 1;
         return true;
     }
     if (!D.graph || !same_plan(P, D.plan)) {
         if (D.graph) { FLC(fl_sync()); FLC(fl_graph_destroy(D.graph)); D.graph = nullptr; }
         if (D.token_plan) { FLC(fl_token_plan_destroy(D.token_plan)); D.token_plan = nullptr; }
-        if (D.use_token_kernel && P.world == 1) D.token_plan = make_token_plan(P, D.d_npast);
+        if (D.use_token_kernel && (P.world == 1 || D.ws.peer_mapped)) D.token_plan = make_token_plan(P, D.ws, D.d_npast);
         // one eager pass first: sets kernel attributes, and gives this token's result
         FLC(fl_event_record(ev0));
         if (D.token_plan) issue_decode_token_kernel(P, D.token_plan); else issue_decode(P, D.d_npast);
@@ -1271,6 +1318,7 @@ bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, 
         if (D.token_plan) issue_decode_token_kernel(P, D.token_plan); else issue_decode(P, D.d_npast);
         FLC(fl_graph_end_capture(&D.graph));
         D.plan = P;
+        g_decode_mode = D.token_plan ? 2 : 1;
         if (g_verbose) fprintf(stderr, "[ggml_b200] decode plan captured: %d layers, n_embd %d, n_ctx %d, %s\n", P.n_layer, P.n_embd, P.n_ctx,
                                D.token_plan ? "persistent token kernel" : "one kernel per matrix group");
         return true;       // the eager pass already produced this token (capture does not execute)
@@ -1278,6 +1326,7 @@ bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, 
     FLC(fl_event_record(ev0));
     FLC(fl_graph_launch(D.graph));
     FLC(fl_event_record(ev1));
+    g_decode_mode = D.token_plan ? 2 : 1;
     g_stats.graph_replays++;
     return true;
 }
@@ -1301,6 +1350,8 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
         FLC(fl_d2h(dout.logits_host, g_dec.ws.logits, dout.logits_bytes));
         FLC(fl_d2h(dout.emb_host, g_dec.ws.emb, dout.emb_bytes));
         FLC(fl_sync());
+        if (g_dec.token_plan && fl_token_plan_error(g_dec.token_plan))
+            B200_FAIL("%s", fl_last_error());
     } else {
         // Leafs.  Weights / KV cache live in persistent arenas (uploaded once by dev_ptr).  Constants the
         // host wrote into the compute arena while building the graph are uploaded per graph, but only

@@ -43,7 +43,7 @@ class FlMvArgs(C.Structure):          # struct fl_mv_args, include/fl_cuda.h
                 ("normed_out", C.c_void_p), ("xadd", C.c_void_p), ("sum_out", C.c_void_p), ("row_stride_bytes", C.c_size_t),
                 ("silu_tab", C.c_void_p), ("epi", C.c_int), ("res", C.c_void_p), ("n_past", C.c_void_p),
                 ("n_ctx", C.c_int), ("n_embd", C.c_int), ("head_dim", C.c_int), ("rope_cs", C.c_void_p), ("kcache", C.c_void_p),
-                ("vcache", C.c_void_p)]
+                ("vcache", C.c_void_p), ("xpeer", C.c_void_p * 7), ("n_xpeer", C.c_int), ("dst_peer", C.c_void_p * 7), ("n_dst_peer", C.c_int)]
 
 
 class FlTokenStep(C.Structure):       # struct fl_token_step, include/fl_cuda.h
@@ -97,6 +97,8 @@ SIGNATURES = {
     "fl_token_plan_create": (C.c_int, [C.POINTER(FlTokenStep), C.c_int, C.POINTER(C.c_void_p)]),
     "fl_token_plan_launch": (C.c_int, [C.c_void_p]),
     "fl_token_plan_destroy": (C.c_int, [C.c_void_p]),
+    "fl_token_plan_error": (C.c_int, [C.c_void_p]),
+    "fl_comm_shared_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "fl_token_plan_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "fl_dev_attn_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "fl_comm_unique_id": (C.c_int, [C.c_void_p]),

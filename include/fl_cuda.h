@@ -157,6 +157,15 @@ typedef struct fl_mv_args {
     int n_ctx, n_embd, head_dim;
     const void *rope_cs;         /* filled in by the library (cos/sin table) */
     float *kcache, *vcache;      /* this layer's K [pos][n_embd] and V [n_embd][n_ctx] cache */
+    /* Tensor parallelism inside the token kernel (fl_token_plan_*, never fl_dev_mv_fused).  Buffers come from
+     * fl_comm_shared_alloc.  A K-split step (wo, w2) PUSHES its partial result: besides seg_dst[0] it stores every
+     * value to dst_peer[0..n_dst_peer) -- the same slot of every other rank's buffer, over NVLink.  The step that
+     * consumes the all-reduced vector reads x + xpeer[0] + ... + xpeer[n_xpeer-1] (+ xadd): the ranks' slots IN RANK
+     * ORDER, all in local memory by then; it is preceded by a cross-GPU barrier. */
+    const float *xpeer[7];
+    int n_xpeer;
+    float *dst_peer[7];
+    int n_dst_peer;
 } fl_mv_args;
 int fl_dev_mv_fused_supported(int type, int K, int mtot);
 int fl_dev_mv_fused(const fl_mv_args *args);
@@ -182,6 +191,8 @@ typedef struct fl_token_step {
 int fl_token_plan_create(const fl_token_step *steps, int n_steps, void **plan_out);
 int fl_token_plan_launch(void *plan);
 int fl_token_plan_destroy(void *plan);
+/* nonzero after a launch whose in-kernel barriers timed out (a peer never arrived); the results are then invalid */
+int fl_token_plan_error(void *plan);
 /* tooling: with FASTLLAMA_B200_TOKEN_PROF set at create time, the last launch's per-step, per-CTA timestamps
  * [n_steps][n_ctas][4] in ns: step entered, grid barrier passed, activations quantised, tiles consumed */
 int fl_token_plan_profile(void *plan, unsigned long long *out, size_t max_words, int *n_ctas);
@@ -195,6 +206,12 @@ int fl_comm_rank(void);
 int fl_comm_world(void);
 int fl_comm_allreduce_f32(float *buf_dev, size_t n);                                   /* in place, sum */
 int fl_comm_allgather_f32(const float *send_dev, float *recv_dev, size_t n_per_rank);
+/* Peer-visible scratch for collectives fused into the token kernel: every rank allocates `bytes` (zeroed) of device
+ * memory, the CUDA IPC handles travel through the NCCL communicator, and each rank maps the others' buffers over
+ * NVLink.  peers_out[r] = pointer, valid on THIS rank, to rank r's buffer (r = own rank: the local allocation).
+ * The first 4096 bytes are reserved for the cross-GPU barrier flags.  Collective call; returns nonzero when peer
+ * mapping is unavailable (the caller then keeps the NCCL path). */
+int fl_comm_shared_alloc(size_t bytes, void **peers_out);
 /* copy blocks [blk0, blk0 + nblk) of every row of a quantised matrix into a packed matrix whose row
  * stride is dst_row_stride bytes (the K-split shard of wo / w2) */
 int fl_dev_pack_cols(int type, const void *W, size_t w_row_stride_bytes, int M, int blk0, int nblk, void *dst, size_t dst_row_stride);

@@ -209,6 +209,9 @@ void ggml_b200_get_stats(struct ggml_b200_stats *out);
 struct ggml_b200_kernel_stat { int type, M, K, N; uint64_t launches; double total_ms; double algo_bytes_per_launch; };
 void ggml_b200_set_profile(int on);
 int ggml_b200_get_kernel_stats(struct ggml_b200_kernel_stat *out, int max_entries);
+/* how the last single-token eval ran: 0 = node-by-node executor, 1 = fused plan, one kernel per matrix group,
+ * 2 = fused plan as one persistent kernel per token (fl_token_kernel.cu) */
+int ggml_b200_decode_mode(void);
 
 #ifdef __cplusplus
 }

@@ -323,6 +323,8 @@ int fl_token_plan_create(const fl_token_step *steps, int n, void **out) {
 }
 int fl_token_plan_launch(void *plan) { mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_PLAN; o.plan = plan; if (g_capture) record(&o); else run_op(&o); return 0; }
 int fl_token_plan_profile(void *plan, unsigned long long *out, size_t n, int *c) { (void)plan; (void)out; (void)n; *c = 0; return -1; }
+int fl_token_plan_error(void *plan) { (void)plan; return 0; }
+int fl_comm_shared_alloc(size_t bytes, void **peers) { (void)bytes; (void)peers; return -1; }   /* no peer memory between CPU processes */
 int fl_token_plan_destroy(void *plan) { mock_graph *pg = plan; if (pg) { free(pg->ops); free(pg); } return 0; }
 int fl_graph_begin_capture(void) { g_capture = calloc(1, sizeof(mock_graph)); return 0; }
 int fl_graph_end_capture(void **out) { *out = g_capture; g_capture = NULL; return 0; }
