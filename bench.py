@@ -12,9 +12,10 @@ written once to $FASTLLAMA_BENCH_DIR or /tmp).  Keys of the JSON line:
   e2e        tokens/s through the reference-facing API -- fastllama_b200.Model.generate() on the drop-in
              pyfastllama.so (the reference's unchanged bridge): wall clock around the call, which per step
              copies the token id host->device and the logits (+ embeddings row) device->host
-  roofline   dominant kernel (the decode matvec): algorithmic bytes per launch / mean launch duration,
-             both summed over every quantised mul_mat launch of extra instrumented decode steps (CUDA events
-             on the launching stream around each launch), against MEASURED_PEAKS.json's hbm_gbs
+  roofline   dominant kernel = k_decode_token, the persistent kernel that runs the whole decode step (one launch per
+             token, reads every quantised weight once): algorithmic bytes per launch (4 129 423 360) / mean launch duration
+             (CUDA events on the launching stream around the graph launch), against MEASURED_PEAKS.json's hbm_gbs;
+             per_matrix_kernels = per-shape timings of the one-kernel-per-matrix-group path from extra instrumented steps
   cpu_baseline  the reference itself (oracle/_ref/pyfastllama_ref.so) on the host cores, bounded sample
 """
 from __future__ import annotations
@@ -314,8 +315,12 @@ def main():
         "scaling": "strong" if (world > 1 and tp) else "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"LLaMA-{args.size} {args.wtype} greedy decode, n_batch=1, n_ctx=512, synthetic random weights N(0,0.02^2) seed 0",
-                   "parallelism": "1 GPU" if world == 1 else (f"tp{world}: wq/wk/wv/w1/w3/output row-split, wo/w2 K-split, 2 NCCL all-reduces of n_embd fp32 per layer + 1 logits all-gather, in the CUDA graph"
-                                                               if tp else f"{world} independent replicas"),
+                   "parallelism": "1 GPU" if world == 1 else (
+                       (f"tp{world}: wq/wk/wv/w1/w3/output row-split, wo/w2 K-split; the 2 reductions per layer are fused into the persistent token kernel "
+                        "(partial sums pushed into peer-mapped buffers over NVLink, cross-GPU flag barrier), 1 NCCL all-gather of the logits, all in the CUDA graph"
+                        if decode_mode == 2 else
+                        f"tp{world}: wq/wk/wv/w1/w3/output row-split, wo/w2 K-split, 2 NCCL all-reduces of n_embd fp32 per layer + 1 logits all-gather, in the CUDA graph")
+                       if tp else f"{world} independent replicas"),
                    "l2": "inputs (4.13 GB of weights per token) are 33x larger than L2; no flush needed",
                    "algorithmic_bytes_per_token": algo, "device": props["name"]},
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 32000 * 4 + 4096 * 4,
