@@ -309,6 +309,14 @@ def main():
         achieved = tot_bytes / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
         roof_kernel = "k_mv_fused (all quantised decode matvecs of the token step, one launch per matrix group)"
         us_per_launch = 1e3 * tot_ms / launches_timed if launches_timed else None
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, like `achieved`)
+    traffic = None
+    if decode_mode == 2 and args.size == "7B" and args.wtype == "q4_0" and world == 1:
+        try:
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_token_kernel.json")))
+            traffic = int(cap["dram_bytes_read"]) + int(cap["dram_bytes_write"])
+        except Exception:
+            traffic = None
     line = {
         "metric": "tokens/sec LLaMA-7B q4_0 decode (n_batch=1, greedy)", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": n_tok,
         "warmup": args.warmup, "ms_per_step": 1000.0 * device_s / n_tok if n_tok else None, "higher_is_better": True,
@@ -326,7 +334,7 @@ def main():
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 32000 * 4 + 4096 * 4,
                 "api": "fastllama_b200.Model.generate -> pyfastllama.so (reference bridge, unchanged) -> libggml_b200 -> libfl_cuda"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      "kernel": roof_kernel, "peak_source": peak_src, "launches_timed": launches_timed, "us_per_launch": us_per_launch,
                      "algorithmic_bytes_per_launch": algo if decode_mode == 2 else None,
                      "per_matrix_kernels": per_shape, "whole_token_gbs": (algo * value / 1e9) if algo else None},
