@@ -33,7 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PROMPT = "The quick brown fox jumps over the lazy dog."
-ALGO_BYTES_PER_TOKEN = {"7B": 4129423360, "13B": None, "65B": None}
+# weights-only bytes of the 7*n_layer+1 quantised matmuls
+ALGO_BYTES_PER_TOKEN = {("7B", "q4_0"): 4129423360, ("7B", "q4_1"): 4955308032, ("13B", "q4_1"): 9638707200, ("65B", "q4_0"): 40638873600}
 
 
 def log(*a):
@@ -290,7 +291,7 @@ def main():
     decode_k = [k for k in ks[:nk] if k.N == 1]
     per_shape = [{"type": "q4_0" if k.type == 2 else "q4_1", "M": k.M, "K": k.K, "launches": int(k.launches), "us_per_launch": 1e3 * k.total_ms / k.launches,
                   "gbs": (k.algo_bytes_per_launch / (k.total_ms / k.launches * 1e-3) / 1e9) if k.total_ms > 0 else None} for k in decode_k if k.launches]
-    algo = ALGO_BYTES_PER_TOKEN.get(args.size)
+    algo = ALGO_BYTES_PER_TOKEN.get((args.size, args.wtype))
     value = total_tokens / device_s if device_s > 0 else 0.0
     e2e = total_tokens / wall if wall > 0 else 0.0
     if decode_mode == 2 and algo and n_tok:
@@ -318,7 +319,7 @@ def main():
         except Exception:
             traffic = None
     line = {
-        "metric": "tokens/sec LLaMA-7B q4_0 decode (n_batch=1, greedy)", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": n_tok,
+        "metric": f"tokens/sec LLaMA-{args.size} {args.wtype} decode (n_batch=1, greedy)", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": n_tok,
         "warmup": args.warmup, "ms_per_step": 1000.0 * device_s / n_tok if n_tok else None, "higher_is_better": True,
         "scaling": "strong" if (world > 1 and tp) else "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -329,7 +330,7 @@ def main():
                         if decode_mode == 2 else
                         f"tp{world}: wq/wk/wv/w1/w3/output row-split, wo/w2 K-split, 2 NCCL all-reduces of n_embd fp32 per layer + 1 logits all-gather, in the CUDA graph")
                        if tp else f"{world} independent replicas"),
-                   "l2": "inputs (4.13 GB of weights per token) are 33x larger than L2; no flush needed",
+                   "l2": f"inputs ({(algo or 0) / 1e9:.2f} GB of weights per token) are {(algo or 0) / 126e6:.0f}x larger than L2; no flush needed",
                    "algorithmic_bytes_per_token": algo, "device": props["name"]},
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 32000 * 4 + 4096 * 4,
                 "api": "fastllama_b200.Model.generate -> pyfastllama.so (reference bridge, unchanged) -> libggml_b200 -> libfl_cuda"},

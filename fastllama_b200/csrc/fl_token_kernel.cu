@@ -622,7 +622,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
                 // Optional: ask L2 for this CTA's whole share of the phase now (the producer gets here while the consumers are
                 // still about a ring's worth of tiles inside the previous phase).
                 if (prm.l2_prefetch) {
-                    for (int t = 0; t < sl.ntiles; t++) {
+                    // l2_prefetch = how many tiles beyond the ring to request (the ring itself covers the first S)
+                    for (int t = S; t < min(sl.ntiles, S + prm.l2_prefetch); t++) {
                         int seg, unit0, nunits;
                         tk_tile_of(sl, G, t, seg, unit0, nunits);
                         if (swiglu) {
@@ -852,7 +853,7 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     p.n_phases = n_steps;
     // measured on B200 (round 1): prefetching a whole phase competes with the demand loads of the phase still running
     // (7B decode 49.6 vs 45.8 us per layer), so it is opt-in
-    p.l2_prefetch = getenv("FASTLLAMA_B200_L2_PREFETCH") ? 1 : 0;
+    p.l2_prefetch = getenv("FASTLLAMA_B200_L2_PREFETCH") ? atoi(getenv("FASTLLAMA_B200_L2_PREFETCH")) : 0;
     p.exp_tab = exp_tab;
     pl->smem = off + (size_t)S * slot;
     FL_CUDA_OK(cudaMalloc((void **)&pl->d_phases, sizeof(tk_phase) * (size_t)n_steps));
