@@ -112,7 +112,13 @@ int ggml_cpu_has_blas(void) { return 0; }
 int ggml_cpu_has_cublas(void) { return 0; }
 
 int64_t ggml_nelements(const struct ggml_tensor *t) { return t->ne[0] * t->ne[1] * t->ne[2] * t->ne[3]; }
-size_t ggml_nbytes(const struct ggml_tensor *t) { return (size_t)(ggml_nelements(t) * (int64_t)k_tsize[t->type]) / k_blck[t->type]; }
+static inline size_t nbytes_of(const struct ggml_tensor *t) { return (size_t)(ggml_nelements(t) * (int64_t)k_tsize[t->type]) / k_blck[t->type]; }
+static void host_access_hook(const struct ggml_tensor *t);
+// Exported ggml_nbytes doubles as the host-access hook of device-written arenas: see host_access_hook below.
+size_t ggml_nbytes(const struct ggml_tensor *t) {
+    host_access_hook(t);
+    return nbytes_of(t);
+}
 int ggml_blck_size(enum ggml_type type) { return k_blck[type]; }
 size_t ggml_type_size(enum ggml_type type) { return k_tsize[type]; }
 float ggml_type_sizef(enum ggml_type type) { return (float)k_tsize[type] / k_blck[type]; }
@@ -288,7 +294,7 @@ struct ggml_tensor *ggml_view_tensor(struct ggml_context *ctx, const struct ggml
     return t;
 }
 struct ggml_tensor *ggml_set_zero(struct ggml_tensor *t) {
-    memset(t->data, 0, ggml_nbytes(t));
+    memset(t->data, 0, nbytes_of(t));
     return t;
 }
 struct ggml_tensor *ggml_set_i32(struct ggml_tensor *t, int32_t value) {
@@ -579,6 +585,7 @@ struct Mirror {
                              // not a ggml arena (mmap'ed weights), uploaded once; MK_SCRATCH: a
                              // ggml_set_scratch buffer (activations only, never uploaded)
     bool alive;
+    bool device_dirty = false;   // a graph wrote into this persistent arena on the device (KV cache) since the last host sync
 };
 std::vector<Mirror> g_mirrors;
 int g_last_mirror = -1;
@@ -587,6 +594,7 @@ bool g_verbose = false;
 struct Stats { uint64_t n_evals = 0; double last_us = 0, total_us = 0; uint64_t graph_replays = 0; } g_stats;
 bool g_profile = false;
 int g_decode_mode = 0;          // see ggml_b200_decode_mode()
+bool g_tp_kv_sharded = false;   // tensor-parallel decode steps have written only this rank's heads into the KV cache
 std::vector<ggml_b200_kernel_stat> g_kstats;
 void *g_pev0 = nullptr, *g_pev1 = nullptr;
 
@@ -684,6 +692,37 @@ static char *dev_ptr(const void *host, size_t nbytes, const ggml_context *comput
     return m.dev + off;
 }
 
+// a device op is about to write `host`'s mirror: remember it if the arena is persistent (the KV cache)
+static void mark_device_write(const void *host, const ggml_context *compute_ctx) {
+    const int i = find_mirror(host);
+    if (i < 0) return;
+    Mirror &m = g_mirrors[i];
+    if (m.kind == MK_ARENA && !(compute_ctx && m.host == compute_ctx->mem_buffer)) m.device_dirty = true;
+}
+// The reference reads and overwrites kv_self.{k,v}->data on the host in KVCacheBuffer::save_state / load_state
+// (reference lib/llama.cpp:57-78) with no ggml call in between -- except ggml_nbytes(k), evaluated as an argument right
+// before each access.  So the exported ggml_nbytes is the hook that keeps the unchanged bridge correct: when it is called
+// on a tensor of a persistent arena the device has written, the arena is copied back to the host (save_state then sees
+// current data) and marked for re-upload before the next graph (load_state's data then reaches the device).  It never
+// fires during eval: Model::eval does not call ggml_nbytes on KV tensors, and the flag is clear outside device writes.
+static void host_access_hook(const struct ggml_tensor *t) {
+    static const bool off = getenv("FASTLLAMA_B200_NO_HOST_HOOK") != nullptr;      // debugging aid: show what breaks without it
+    if (off || !t || !t->data || g_mirrors.empty()) return;
+    const int i = find_mirror(t->data);
+    if (i < 0) return;
+    Mirror &m = g_mirrors[i];
+    if (!m.device_dirty || !m.dev) return;
+    if (fl_comm_world() > 1 && g_tp_kv_sharded)
+        B200_FAIL("host access to the KV cache after tensor-parallel decode steps: each rank holds only its heads (not supported yet)");
+    const size_t n = std::min(m.uploaded, std::min(m.size, m.alloc_end));
+    if (g_verbose) fprintf(stderr, "[ggml_b200] host access to device-written arena %p: syncing %zu MiB back, re-upload before the next graph\n", (const void *)m.host, n >> 20);
+    FLC(fl_sync());
+    if (n) FLC(fl_d2h((void *)m.host, m.dev, n));
+    FLC(fl_sync());
+    m.device_dirty = false;
+    m.uploaded = 0;              // the host may now change the data (load_state): everything is uploaded again on next use
+}
+
 extern "C" void ggml_b200_invalidate(const void *ptr, size_t size) {
     const int i = find_mirror(ptr);
     if (i < 0 || !g_mirrors[i].dev) return;
@@ -745,7 +784,7 @@ Exec g_exec;
 
 fl_view view_of(const ggml_tensor *t, const ggml_context *cctx) {
     fl_view v;
-    v.data = dev_ptr(t->data, ggml_nbytes(t), cctx);
+    v.data = dev_ptr(t->data, nbytes_of(t), cctx);
     for (int i = 0; i < 4; i++) { v.ne[i] = t->ne[i]; v.nb[i] = (int64_t)t->nb[i]; }
     return v;
 }
@@ -776,9 +815,9 @@ void exec_mul_mat(const ggml_tensor *node, const ggml_context *cctx) {
         g_exec.q8_work = fl_dev_malloc(g_exec.q8_cap);
         if (!g_exec.q8_work) B200_FAIL("q8_0 work buffer: %s", fl_last_error());
     }
-    const char *W = dev_ptr(a->data, ggml_nbytes(a), cctx);
-    const float *X = (const float *)dev_ptr(b->data, ggml_nbytes(b), cctx);
-    float *D = (float *)dev_ptr(node->data, ggml_nbytes(node), cctx);
+    const char *W = dev_ptr(a->data, nbytes_of(a), cctx);
+    const float *X = (const float *)dev_ptr(b->data, nbytes_of(b), cctx);
+    float *D = (float *)dev_ptr(node->data, nbytes_of(node), cctx);
     // INIT phase: src1 rows -> q8_0 (reference lib/ggml.c:8105-8119)
     FLC(fl_dev_quantize_q8_0(X, b->nb[1], g_exec.q8_work, K, N));
     // COMPUTE phase (reference lib/ggml.c:8125-8163)
@@ -805,13 +844,17 @@ void exec_node(ggml_tensor *node, const ggml_context *cctx) {
     switch (node->op) {
         case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE:
             return;                                   // pure address arithmetic, already in node->data / nb
+        default: break;
+    }
+    mark_device_write(node->data, cctx);              // a cpy into a KV-cache view lands in a persistent arena
+    switch (node->op) {
         case GGML_OP_GET_ROWS: {
             const ggml_tensor *a = node->src0, *ids = node->src1;
             if (a->type != GGML_TYPE_Q4_0 && a->type != GGML_TYPE_Q4_1)
                 B200_FAIL("get_rows: table type %s is not supported by the B200 backend (q4_0, q4_1)", k_tname[a->type]);
-            FLC(fl_dev_dequantize_rows((int)a->type, dev_ptr(a->data, ggml_nbytes(a), cctx), a->nb[1], (int)a->ne[0],
-                                       (const int32_t *)dev_ptr(ids->data, ggml_nbytes(ids), cctx), (int)ggml_nelements(ids),
-                                       (float *)dev_ptr(node->data, ggml_nbytes(node), cctx), node->nb[1] / sizeof(float)));
+            FLC(fl_dev_dequantize_rows((int)a->type, dev_ptr(a->data, nbytes_of(a), cctx), a->nb[1], (int)a->ne[0],
+                                       (const int32_t *)dev_ptr(ids->data, nbytes_of(ids), cctx), (int)ggml_nelements(ids),
+                                       (float *)dev_ptr(node->data, nbytes_of(node), cctx), node->nb[1] / sizeof(float)));
             return;
         }
         case GGML_OP_RMS_NORM: {
@@ -937,7 +980,7 @@ struct DecodeState {
     bool enabled = true, use_graph = true, use_token_kernel = true, inited = false;
     bool tp_kv_sharded = false;   // tensor-parallel decode steps have written only this rank's heads into the KV cache
 };
-struct DecodeOutputs { void *logits_host = nullptr; size_t logits_bytes = 0; void *emb_host = nullptr; size_t emb_bytes = 0; int32_t token = 0; };
+struct DecodeOutputs { const void *kv_host = nullptr; void *logits_host = nullptr; size_t logits_bytes = 0; void *emb_host = nullptr; size_t emb_bytes = 0; int32_t token = 0; };
 DecodeState g_dec;
 
 struct Cur {
@@ -958,7 +1001,7 @@ inline bool is_qw(const ggml_tensor *w) {
 inline bool is_vec(const ggml_tensor *t, int64_t n) {
     return t && t->type == GGML_TYPE_F32 && t->ne[0] == n && t->ne[1] == 1 && t->ne[2] == 1 && t->ne[3] == 1 && t->nb[0] == 4;
 }
-template <typename T> inline T *dp(const ggml_tensor *t, const ggml_context *c) { return (T *)dev_ptr(t->data, ggml_nbytes(t), c); }
+template <typename T> inline T *dp(const ggml_tensor *t, const ggml_context *c) { return (T *)dev_ptr(t->data, nbytes_of(t), c); }
 
 void mv_base(fl_mv_args &a, int type, int K) {
     memset(&a, 0, sizeof(a));
@@ -1094,6 +1137,7 @@ bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, Decode
         PM(W.n_ff == n_ff);
         L.q = W.q;
         L.kcache = dp<const float>(Kv, ctx);
+        O.kv_host = Kv->data;
         L.vcache = dp<const float>(Vv, ctx);
         L.att = W.att;
         // wq|wk|wv: rms_norm prologue, rope + cache-store epilogue
@@ -1344,7 +1388,8 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
 
     DecodeOutputs dout;
     if (run_decode_plan(ctx, g, dout, ev0, ev1)) {
-        if (fl_comm_world() > 1) g_dec.tp_kv_sharded = true;
+        mark_device_write(dout.kv_host, ctx);          // the step appended one position to the KV cache on the device
+        if (fl_comm_world() > 1) { g_dec.tp_kv_sharded = true; g_tp_kv_sharded = true; }
         // fused decode step: the two results the caller reads (reference lib/llama.cpp:476-489) come
         // straight from the private workspace
         FLC(fl_d2h(dout.logits_host, g_dec.ws.logits, dout.logits_bytes));
@@ -1363,7 +1408,7 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
             auto upload_leaf = [&](const ggml_tensor *t) {
                 if (!t || t->op != GGML_OP_NONE || !t->data || !in_ctx(ctx, t->data)) return;
                 for (int i = 0; i < n_done; i++) if (done[i] == t) return;
-                const size_t nb = ggml_nbytes(t);
+                const size_t nb = nbytes_of(t);
                 FLC(fl_h2d(dev_ptr(t->data, nb, ctx), t->data, nb));
                 if (n_done < 16) done[n_done++] = t;
             };
@@ -1415,7 +1460,7 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
             ggml_tensor *t = g->nodes[i];
             const bool want = sync_all || !consumed[i] || (last_mm && t == last_mm->src1);
             if (!want || !in_ctx(ctx, t->data) || !is_contiguous(t)) continue;
-            const size_t nb = ggml_nbytes(t);
+            const size_t nb = nbytes_of(t);
             FLC(fl_d2h(t->data, dev_ptr(t->data, nb, ctx), nb));
         }
         FLC(fl_sync());
