@@ -132,11 +132,14 @@ def test_get_rows_and_quantised_mul_mat(libs, t):
 
 
 @pytest.mark.parametrize("t", [G.Q4_0, G.Q4_1])
-def test_llama_eval_prompt_then_decode(libs, t):
+@pytest.mark.parametrize("dims", ["generic", "fused"])
+def test_llama_eval_prompt_then_decode(libs, t, dims):
     """Model::eval semantics: a 5-token prompt (N = 5), then three decode steps (N = 1) that read the
-    KV cache written by the earlier graphs."""
+    KV cache written by the earlier graphs.  "generic": n_ff = 352 rows are not 16-byte multiples, so the decode steps
+    run node by node; "fused": shapes the decode plan accepts, so they run as the persistent token kernel."""
     orc = Oracle()
-    hp = HParams(n_vocab=96, n_embd=128, n_head=4, n_layer=3, n_mult=32, n_ctx=32)
+    hp = HParams(n_vocab=96, n_embd=128, n_head=4, n_layer=3, n_mult=32, n_ctx=32) if dims == "generic" else \
+        HParams(n_vocab=96, n_embd=256, n_head=4, n_layer=3, n_mult=256, n_ctx=32)
     w = make_weights(hp, t, lambda x, tt: orc.quantize_q4(x, tt), seed=3)
     models = [MiniLlama(g, hp, w, compute_mb=32) for g in libs]
     steps = [([5, 17, 3, 80, 41], 0), ([7], 5), ([60], 6), ([2], 7)]
@@ -151,6 +154,8 @@ def test_llama_eval_prompt_then_decode(libs, t):
         assert np.abs(rl - ol).max() <= 2e-2 * np.abs(rl).max(), (n_past, np.abs(rl - ol).max(), np.abs(rl).max())
         assert np.abs(re - oe).max() <= 2e-2 * np.abs(re).max()
         assert np.array_equal(rl.argmax(-1), ol.argmax(-1))
+    import ctypes as C
+    assert C.CDLL(OURS).ggml_b200_decode_mode() == (2 if dims == "fused" else 0)
 
 
 def test_unsupported_op_aborts_loudly():

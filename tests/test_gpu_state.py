@@ -20,7 +20,7 @@ def test_state_round_trip_and_interop_with_reference_on_gpu(tmp_path):
         pytest.skip("oracle/_ref not built")
     orc = Oracle()
     model = str(tmp_path / "toy.bin")
-    write_synthetic_numpy(model, Q4_0, n_vocab=512, n_embd=256, n_mult=64, n_head=4, n_layer=3, seed=7, std=0.01, quantize=lambda w, t: orc.quantize_q4(w, t))
+    write_synthetic_numpy(model, Q4_0, n_vocab=512, n_embd=256, n_mult=256, n_head=4, n_layer=3, seed=7, std=0.01, quantize=lambda w, t: orc.quantize_q4(w, t))
     ours_lib = os.path.join(LIB_DIR, "pyfastllama.so")
 
     ours = _run(tmp_path, "save", ours_lib, model, str(tmp_path / "ours.state"), "ours")
