@@ -1398,6 +1398,7 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
         if (g_dec.token_plan && fl_token_plan_error(g_dec.token_plan))
             B200_FAIL("%s", fl_last_error());
     } else {
+        g_decode_mode = 0;
         // Leafs.  Weights / KV cache live in persistent arenas (uploaded once by dev_ptr).  Constants the
         // host wrote into the compute arena while building the graph are uploaded per graph, but only
         // those a device op reads as DATA (token ids); rope / mask / scale parameters are read on the
