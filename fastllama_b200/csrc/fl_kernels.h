@@ -21,6 +21,10 @@ int flk_dequantize_rows(cudaStream_t st, int type, const void *W, size_t w_row_s
 int flk_mul_mat_q(cudaStream_t st, int type, const void *W, size_t w_row_stride, int M, int K, const void *Yq8, int N,
                   float *dst, size_t dst_row_stride, int impl);
 
+// fl_mma_kernel.cu: N > 1, integer block sums on the tensor cores (mma.sync m16n8k32 u8 x s8), scales in fp32
+int flk_mul_mat_q_mma(cudaStream_t st, int type, const void *W, size_t w_row_stride, int M, int K, const void *Yq8, int N, float *dst,
+                      size_t dst_row_stride);
+
 // ---- fl_ops_kernels.cu: the non-matmul ops Model::eval emits (reference lib/llama.cpp:301-465) ----
 // A strided 4-D view of device memory: ne = element counts, nb = byte strides (ggml conventions,
 // reference include/ggml.h:279-309).

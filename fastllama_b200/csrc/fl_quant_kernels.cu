@@ -577,5 +577,7 @@ int flk_mul_mat_q(cudaStream_t st, int type, const void *W, size_t wrs, int M, i
         p.dst = dst;
         return launch_ring(st, type, nfull, p, threads, smem);
     }
+    // N > 1 (prompt ingest): the block dots go to the tensor cores (fl_mma_kernel.cu); tiny N stays on the plain kernel
+    if (impl == 3 || (impl == 0 && N >= 4)) return flk_mul_mat_q_mma(st, type, W, wrs, M, K, Yq8, N, dst, drs);
     return launch_plain(st, type, W, wrs, M, K, Yq8, N, dst, drs);
 }

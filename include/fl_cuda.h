@@ -85,8 +85,9 @@ int fl_host_free_pinned(void *p);
 /* activations -> q8_0 rows.  x row r starts at x + r*x_row_stride_bytes; y rows are packed. */
 int fl_dev_quantize_q8_0(const float *x, size_t x_row_stride_bytes, void *y, int k, int nrows);
 
-/* dst[n*dst_row_stride + m] = vec_dot(W row m, Yq8 row n).  impl: 0 = auto, 1 = plain
- * warp-per-row LDG kernel, 2 = TMA-bulk-staged persistent matvec (N = 1 only). */
+/* dst[n*dst_row_stride + m] = vec_dot(W row m, Yq8 row n).  impl: 0 = auto (N = 1: ring, N >= 4: tensor cores, else plain),
+ * 1 = plain warp-per-row LDG kernel, 2 = TMA-bulk-staged persistent matvec (N = 1 only), 3 = tensor-core kernel
+ * (mma.sync m16n8k32 u8 x s8 block sums, fp32 scales; any N). */
 int fl_dev_mul_mat_q(int type, const void *W, size_t w_row_stride_bytes, int M, int K, const void *Yq8, int N,
                      float *dst, size_t dst_row_stride_elems, int impl);
 

@@ -147,3 +147,31 @@ def test_live_reference_q8_and_dots(fl, ref, oracle):
         got = fl.mul_mat_q(w, x, t)
         assert _dot_ok(got, ex, mag)
         assert np.all(np.abs(got.astype(np.float64) - r) <= 2 * REORDER_BUDGET * mag + 1e-30)
+
+
+@pytest.mark.parametrize("t", [GGML_TYPE_Q4_0, GGML_TYPE_Q4_1])
+@pytest.mark.parametrize("m,k,n", [(33, 64, 9), (300, 256, 5), (1000, 11008, 37), (1024, 4096, 128), (514, 4096, 200), (16, 32, 1)])
+def test_prompt_ingest_tensor_core_kernel(fl, oracle, t, m, k, n):
+    """N > 1 (impl 3): integer block sums on the tensor cores (mma.sync m16n8k32 u8 x s8), scales in fp32 -- same budget
+    as every other dot product against the order-free oracle, ragged M / N tails included; and it must agree with the
+    plain kernel (impl 1) to within twice the budget and be run-to-run deterministic."""
+    rng = np.random.default_rng(m + 3 * k + 7 * n)
+    from oracle.pyoracle import np_quantize_q4_0, np_quantize_q4_1
+
+    w = (rng.standard_normal((m, k)) * 0.03).astype(np.float32)
+    wq = (np_quantize_q4_0 if t == GGML_TYPE_Q4_0 else np_quantize_q4_1)(w)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    ex, mag = oracle.mul_mat_q_exact(wq, x, t)
+    q8 = oracle.quantize_q8_0(x)
+    dW, dY, dD = fl.to_device(wq), fl.to_device(q8), fl.alloc(m * n * 4)
+    outs = {}
+    for impl in (3, 3, 1):
+        fl.check(fl.lib.fl_dev_memset(dD, 0xFF, m * n * 4))
+        fl.check(fl.lib.fl_dev_mul_mat_q(t, dW, wq.shape[1], m, k, dY, n, dD, m, impl))
+        got = fl.to_host(dD, (n, m), np.float32)
+        assert _dot_ok(got, ex, mag), f"impl {impl}"
+        outs.setdefault(impl, []).append(got)
+    assert np.array_equal(outs[3][0].view(np.uint32), outs[3][1].view(np.uint32))
+    assert np.all(np.abs(outs[3][0].astype(np.float64) - outs[1][0]) <= 2 * REORDER_BUDGET * mag + 1e-30)
+    for d in (dW, dY, dD):
+        fl.free(d)
