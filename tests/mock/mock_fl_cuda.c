@@ -234,6 +234,36 @@ typedef struct {
 typedef struct { mock_op *ops; int n, cap; } mock_graph;
 static mock_graph *g_capture = NULL;
 
+/* peer-mapped buffers between the CPU processes of a gloo test: POSIX shared memory, one segment per rank, named by
+ * $FL_MOCK_SESSION (unset: no peer memory, the caller keeps the collective path) */
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+static void mock_barrier(void) { float z = 0.f; if (g_coll && g_world > 1) g_coll(0, &z, &z, 1); }
+int fl_comm_shared_alloc(size_t bytes, void **peers) {
+    const char *sess = getenv("FL_MOCK_SESSION");
+    if (!sess || g_world <= 1 || !g_coll) return -1;
+    char name[128];
+    snprintf(name, sizeof(name), "/flmock_%s_%d", sess, g_rank);
+    int fd = shm_open(name, O_CREAT | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) return -1;
+    peers[g_rank] = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    memset(peers[g_rank], 0, bytes);
+    mock_barrier();                                              /* every segment exists and is zeroed */
+    for (int r = 0; r < g_world; r++) {
+        if (r == g_rank) continue;
+        snprintf(name, sizeof(name), "/flmock_%s_%d", sess, r);
+        fd = shm_open(name, O_RDWR, 0600);
+        if (fd < 0) return -1;
+        peers[r] = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+    }
+    mock_barrier();
+    snprintf(name, sizeof(name), "/flmock_%s_%d", sess, g_rank);
+    shm_unlink(name);                                            /* everybody has it mapped; the name can go */
+    return 0;
+}
 static void record(const mock_op *op) {
     if (g_capture->n == g_capture->cap) { g_capture->cap = g_capture->cap ? 2 * g_capture->cap : 64; g_capture->ops = realloc(g_capture->ops, sizeof(mock_op) * g_capture->cap); }
     g_capture->ops[g_capture->n++] = *op;
@@ -242,7 +272,11 @@ static void run_mv(const fl_mv_args *a) {
     const int K = a->K, nb = K / 32, bb = a->type == 2 ? 20 : 24;
     const size_t rstride = a->row_stride_bytes ? a->row_stride_bytes : (size_t)nb * bb;
     float *v = malloc(sizeof(float) * K), *xin = malloc(sizeof(float) * K);
-    for (int i = 0; i < K; i++) xin[i] = a->xadd ? a->x[i] + a->xadd[i] : a->x[i];
+    for (int i = 0; i < K; i++) {
+        float t = a->x[i];
+        for (int r = 0; r < a->n_xpeer; r++) t += a->xpeer[r][i];          /* the ranks' slots, rank order */
+        xin[i] = a->xadd ? t + a->xadd[i] : t;
+    }
     if (a->sum_out) memcpy(a->sum_out, xin, sizeof(float) * K);
     if (a->pro == FL_PRO_RMSNORM) {
         double sum = 0; for (int i = 0; i < K; i++) sum += (double)(xin[i] * xin[i]);
@@ -272,7 +306,11 @@ static void run_mv(const fl_mv_args *a) {
                     o[0] = y0; o[1] = y1;
                 } else { a->vcache[(size_t)r * a->n_ctx + n_past] = x0; a->vcache[(size_t)(r + 1) * a->n_ctx + n_past] = x1; }
             }
-        } else for (int r = 0; r < a->seg_rows[sg]; r++) a->seg_dst[sg][r] = a->epi == FL_EPI_RESADD ? tmp[r] + a->res[r] : tmp[r];
+        } else for (int r = 0; r < a->seg_rows[sg]; r++) {
+            const float o = a->epi == FL_EPI_RESADD ? tmp[r] + a->res[r] : tmp[r];
+            a->seg_dst[sg][r] = o;
+            for (int pr = 0; pr < a->n_dst_peer; pr++) a->dst_peer[pr][r] = o;             /* push into the peers' buffers */
+        }
         free(tmp);
     }
     free(q8); free(v);
@@ -292,7 +330,15 @@ static void run_attn(const mock_op *o) {
 }
 static void run_op(const mock_op *o) {
     g_launches++;
-    if (o->kind == OP_PLAN) { const mock_graph *pg = o->plan; for (int i = 0; i < pg->n; i++) { run_op(&pg->ops[i]); g_launches--; } return; }
+    if (o->kind == OP_PLAN) {
+        const mock_graph *pg = o->plan;
+        for (int i = 0; i < pg->n; i++) {
+            if (pg->ops[i].kind == OP_MV && pg->ops[i].mv.n_xpeer > 0) mock_barrier();       /* the kernel's cross-GPU barrier */
+            run_op(&pg->ops[i]);
+            g_launches--;
+        }
+        return;
+    }
     if (o->kind == OP_MV) run_mv(&o->mv);
     else if (o->kind == OP_ATTN) run_attn(o);
     else if (o->kind == OP_ALLREDUCE) g_coll(0, o->co.send, o->co.recv, o->co.n);
@@ -324,7 +370,7 @@ int fl_token_plan_create(const fl_token_step *steps, int n, void **out) {
 int fl_token_plan_launch(void *plan) { mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_PLAN; o.plan = plan; if (g_capture) record(&o); else run_op(&o); return 0; }
 int fl_token_plan_profile(void *plan, unsigned long long *out, size_t n, int *c) { (void)plan; (void)out; (void)n; *c = 0; return -1; }
 int fl_token_plan_error(void *plan) { (void)plan; return 0; }
-int fl_comm_shared_alloc(size_t bytes, void **peers) { (void)bytes; (void)peers; return -1; }   /* no peer memory between CPU processes */
+
 int fl_token_plan_destroy(void *plan) { mock_graph *pg = plan; if (pg) { free(pg->ops); free(pg); } return 0; }
 int fl_graph_begin_capture(void) { g_capture = calloc(1, sizeof(mock_graph)); return 0; }
 int fl_graph_end_capture(void **out) { *out = g_capture; g_capture = NULL; return 0; }

@@ -38,14 +38,19 @@ m = Model(path, num_threads=2, n_ctx=64, n_batch=int(sys.argv[5]), logger=QuietL
 m.ingest("Tensor parallel decode over two ranks.")
 toks = []
 m.generate(lambda s: toks.append(s), num_tokens=10, temp=0.0, top_k=1, top_p=1.0, repeat_penalty=1.0)
-np.savez(out + f".rank{rank}.npz", toks=np.array(toks), logits=m.get_logits_array())
+mode = C.CDLL(os.path.join(mock, "libggml_b200.so")).ggml_b200_decode_mode()
+np.savez(out + f".rank{rank}.npz", toks=np.array(toks), logits=m.get_logits_array(), mode=mode)
 m.close()
 '''
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(MOCK, "pyfastllama.so")), reason="tests/mock not built (needs the drop-in library)")
 @pytest.mark.parametrize("n_batch", [1, 8])
-def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch):
+@pytest.mark.parametrize("peer", [False, True])
+def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch, peer):
+    """peer=False: the two reductions per layer are collectives between per-matrix kernels (the NCCL path).
+    peer=True: the mock maps POSIX shared memory between the ranks like fl_comm_shared_alloc maps peer HBM, so the
+    sharded plan runs as the token program with partial sums pushed into the peers' buffers and summed in rank order."""
     from fastllama_b200.ggjt import Q4_0, write_synthetic_numpy
     from oracle.pyoracle import Oracle
 
@@ -60,6 +65,9 @@ def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch):
         procs = []
         for r in range(world):
             env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", OMP_NUM_THREADS="2")
+            env.pop("FL_MOCK_SESSION", None)
+            if peer:
+                env["FL_MOCK_SESSION"] = f"{os.getpid()}_{tag}_{n_batch}"
             procs.append(subprocess.Popen([sys.executable, str(script), ROOT, MOCK, path, str(tmp_path / tag), str(n_batch)], env=env,
                                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE))
         for p in procs:
@@ -69,7 +77,9 @@ def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch):
 
     single = launch(1, "w1")[0]
     tp = launch(2, "w2")
+    assert int(single["mode"]) == 2                                   # one rank: the token program
     for r in tp:
+        assert int(r["mode"]) == (2 if peer else 1)                   # two ranks: token program only with peer-mapped buffers
         assert list(r["toks"]) == list(single["toks"])
         # K-split changes the fp32 summation order across ranks: same tolerance policy as the single-GPU path
         assert np.abs(r["logits"] - single["logits"]).max() <= 2e-2 * np.abs(single["logits"]).max()
