@@ -41,6 +41,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The reference's C++ layers print a banner and progress on the process's stdout (fd 1).  The driver wants exactly one JSON
+# line there, so fd 1 is pointed at stderr for the whole run and the line is written to a private duplicate of the real stdout.
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 class _Stats(C.Structure):
     _fields_ = [("n_evals", C.c_uint64), ("last_eval_device_us", C.c_double), ("total_device_us", C.c_double),
                 ("launches", C.c_uint64), ("graph_replays", C.c_uint64)]
@@ -144,6 +163,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    _claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -176,7 +196,7 @@ def main():
                 "config": {"workload": f"LLaMA-{args.size} {args.wtype} decode n_batch=1 n_ctx=512, reference CPU path", "cpu_threads": cb["cores"]},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "wall_s": time.perf_counter() - t0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ---------------------------------------------------------------- our arm
@@ -343,7 +363,7 @@ def main():
     }
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":
