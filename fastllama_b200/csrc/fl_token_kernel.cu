@@ -433,6 +433,10 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
                     fd_block<TYPE>(rowB + (size_t)(32 * j) * BB, yp[j], accB, accmB);
                 }
             }
+            // the tile has been read (the sums above consumed every shared load of the warp): hand the slot back to the
+            // producer before the reduction and the epilogue, whose latency then overlaps the refill
+            __syncwarp();
+            if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));
             float totA = fl_warp_sum(accA), totB = fl_warp_sum(accB);
             if (TYPE == FL_TYPE_Q4_1) {
                 totA = __fadd_rn(totA, fl_warp_sum(accmA));
@@ -457,9 +461,10 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
                     }
                 }
             }
+        } else {
+            __syncwarp();
+            if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));      // no unit of this tile for the warp
         }
-        __syncwarp();
-        if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));
         s += TK_TG;
         if (s >= S) { s -= S; par ^= 1u; }
     }
