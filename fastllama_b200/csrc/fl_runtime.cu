@@ -224,6 +224,12 @@ extern "C" int fl_d2d(void *dst, const void *src, size_t bytes) {
     FL_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g.stream));
     return 0;
 }
+extern "C" int fl_d2d_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t height) {
+    FL_NEED_INIT();
+    if (width == 0 || height == 0) return 0;
+    FL_CUDA_OK(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, cudaMemcpyDeviceToDevice, g.stream));
+    return 0;
+}
 extern "C" int fl_sync(void) {
     FL_NEED_INIT();
     FL_CUDA_OK(cudaStreamSynchronize(g.stream));

@@ -692,6 +692,7 @@ static char *dev_ptr(const void *host, size_t nbytes, const ggml_context *comput
     return m.dev + off;
 }
 
+static void tp_gather_kv();
 // a device op is about to write `host`'s mirror: remember it if the arena is persistent (the KV cache)
 static void mark_device_write(const void *host, const ggml_context *compute_ctx) {
     const int i = find_mirror(host);
@@ -712,8 +713,7 @@ static void host_access_hook(const struct ggml_tensor *t) {
     if (i < 0) return;
     Mirror &m = g_mirrors[i];
     if (!m.device_dirty || !m.dev) return;
-    if (fl_comm_world() > 1 && g_tp_kv_sharded)
-        B200_FAIL("host access to the KV cache after tensor-parallel decode steps: each rank holds only its heads (not supported yet)");
+    if (fl_comm_world() > 1 && g_tp_kv_sharded) tp_gather_kv();      // collective: every rank saves / loads its state at the same point
     const size_t n = std::min(m.uploaded, std::min(m.size, m.alloc_end));
     if (g_verbose) fprintf(stderr, "[ggml_b200] host access to device-written arena %p: syncing %zu MiB back, re-upload before the next graph\n", (const void *)m.host, n >> 20);
     FLC(fl_sync());
@@ -978,7 +978,8 @@ struct DecodeState {
     int *d_npast = nullptr;
     int *h_scalars = nullptr;   // pinned: [0] n_past, [1] token id
     bool enabled = true, use_graph = true, use_token_kernel = true, inited = false;
-    bool tp_kv_sharded = false;   // tensor-parallel decode steps have written only this rank's heads into the KV cache
+    bool tp_kv_sharded = false;   // tensor-parallel decode steps have written only this rank's heads into the KV cache ...
+    int tp_first_pos = 0, tp_end_pos = 0;   // ... for positions [tp_first_pos, tp_end_pos)
 };
 struct DecodeOutputs { const void *kv_host = nullptr; void *logits_host = nullptr; size_t logits_bytes = 0; void *emb_host = nullptr; size_t emb_bytes = 0; int32_t token = 0; };
 DecodeState g_dec;
@@ -992,7 +993,7 @@ struct Cur {
         return g->nodes[i++];
     }
 };
-#define PM(cond) do { if (!(cond)) return false; } while (0)
+#define PM(cond) do { if (!(cond)) { if (g_verbose) fprintf(stderr, "[ggml_b200] decode plan: no match (line %d): %s\n", __LINE__, #cond); return false; } } while (0)
 
 inline bool is_qw(const ggml_tensor *w) {
     return w && w->op == GGML_OP_NONE && (w->type == GGML_TYPE_Q4_0 || w->type == GGML_TYPE_Q4_1) && w->ne[2] == 1 && w->ne[3] == 1 &&
@@ -1376,6 +1377,44 @@ bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, 
 }
 }  // namespace
 
+// Tensor-parallel decode steps write only this rank's heads of the new positions into the KV cache (K [pos][n_embd]: nl
+// columns per row; V [n_embd][n_ctx]: nl rows).  Before anything reads the cache as a whole -- a replicated multi-token
+// eval, save_state -- the ranks exchange those slices: pack (strided copies) -> one all-gather -> unpack.  Collective.
+static void tp_gather_kv() {
+    DecodeState &D = g_dec;
+    const DecodePlan &P = D.plan;
+    const int world = fl_comm_world(), rank = fl_comm_rank();
+    if (!D.tp_kv_sharded || world <= 1 || P.layers.empty()) { D.tp_kv_sharded = false; g_tp_kv_sharded = false; return; }
+    const int npos = D.tp_end_pos - D.tp_first_pos, first = D.tp_first_pos;
+    const int n_embd = P.n_embd, n_ctx = P.n_ctx, nl = n_embd / world, L = (int)P.layers.size();
+    const size_t per_layer = (size_t)2 * npos * nl, count = per_layer * L;
+    float *send = (float *)fl_dev_malloc(count * sizeof(float) * (size_t)(world + 1));
+    if (!send) B200_FAIL("KV gather: %s", fl_last_error());
+    float *recv = send + count;
+    for (int l = 0; l < L; l++) {
+        const float *kmine = P.layers[l].kcache + (size_t)first * n_embd;                  // already offset to this rank's columns
+        const float *vmine = P.layers[l].vcache + first;                                   // already offset to this rank's rows
+        FLC(fl_d2d_2d(send + l * per_layer, (size_t)nl * 4, kmine, (size_t)n_embd * 4, (size_t)nl * 4, (size_t)npos));
+        FLC(fl_d2d_2d(send + l * per_layer + (size_t)npos * nl, (size_t)npos * 4, vmine, (size_t)n_ctx * 4, (size_t)npos * 4, (size_t)nl));
+    }
+    FLC(fl_comm_allgather_f32(send, recv, count));
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        for (int l = 0; l < L; l++) {
+            float *kbase = (float *)P.layers[l].kcache - (size_t)rank * nl;                // the layer's K [pos][n_embd]
+            float *vbase = (float *)P.layers[l].vcache - (size_t)rank * nl * n_ctx;        // the layer's V [n_embd][n_ctx]
+            const float *src = recv + (size_t)r * count + l * per_layer;
+            FLC(fl_d2d_2d(kbase + (size_t)first * n_embd + (size_t)r * nl, (size_t)n_embd * 4, src, (size_t)nl * 4, (size_t)nl * 4, (size_t)npos));
+            FLC(fl_d2d_2d(vbase + (size_t)r * nl * n_ctx + first, (size_t)n_ctx * 4, src + (size_t)npos * nl, (size_t)npos * 4, (size_t)npos * 4, (size_t)nl));
+        }
+    }
+    FLC(fl_sync());
+    FLC(fl_dev_free(send));
+    if (g_verbose) fprintf(stderr, "[ggml_b200] gathered the KV cache of positions [%d, %d) from %d ranks\n", first, D.tp_end_pos, world);
+    D.tp_kv_sharded = false;
+    g_tp_kv_sharded = false;
+}
+
 extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph *g) {
     ensure_backend();
     static void *ev0 = nullptr, *ev1 = nullptr;
@@ -1389,7 +1428,12 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
     DecodeOutputs dout;
     if (run_decode_plan(ctx, g, dout, ev0, ev1)) {
         mark_device_write(dout.kv_host, ctx);          // the step appended one position to the KV cache on the device
-        if (fl_comm_world() > 1) { g_dec.tp_kv_sharded = true; g_tp_kv_sharded = true; }
+        if (fl_comm_world() > 1) {
+            const int pos = g_dec.h_scalars[0];                   // n_past of this step = the position it wrote
+            if (!g_dec.tp_kv_sharded) { g_dec.tp_first_pos = pos; g_dec.tp_end_pos = pos + 1; }
+            else { g_dec.tp_first_pos = std::min(g_dec.tp_first_pos, pos); g_dec.tp_end_pos = std::max(g_dec.tp_end_pos, pos + 1); }
+            g_dec.tp_kv_sharded = true; g_tp_kv_sharded = true;
+        }
         // fused decode step: the two results the caller reads (reference lib/llama.cpp:476-489) come
         // straight from the private workspace
         FLC(fl_d2h(dout.logits_host, g_dec.ws.logits, dout.logits_bytes));
@@ -1423,9 +1467,7 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
 
         if (g_dec.tp_kv_sharded)
             for (int i = 0; i < g->n_nodes; i++)
-                if (g->nodes[i]->op == GGML_OP_SOFT_MAX)
-                    B200_FAIL("tensor-parallel mode: a replicated (multi-token) attention eval after sharded decode steps would read KV-cache "
-                              "entries of other ranks' heads; the KV all-gather for that case is not implemented");
+                if (g->nodes[i]->op == GGML_OP_SOFT_MAX) { tp_gather_kv(); break; }    // a replicated attention eval needs every head's K/V
         FLC(fl_event_record(ev0));
         for (int i = 0; i < g->n_nodes; i++) exec_node(g->nodes[i], ctx);
         FLC(fl_event_record(ev1));

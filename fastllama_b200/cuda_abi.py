@@ -72,6 +72,7 @@ SIGNATURES = {
     "fl_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fl_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fl_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "fl_d2d_2d": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
     "fl_sync": (C.c_int, []),
     "fl_host_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "fl_host_free_pinned": (C.c_int, [C.c_void_p]),

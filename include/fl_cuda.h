@@ -78,6 +78,8 @@ int fl_dev_memset(void *p, int value, size_t bytes);
 int fl_h2d(void *dst_dev, const void *src_host, size_t bytes);   /* async on the library stream */
 int fl_d2h(void *dst_host, const void *src_dev, size_t bytes);   /* async; call fl_sync before reading */
 int fl_d2d(void *dst_dev, const void *src_dev, size_t bytes);
+/* strided device-to-device copy: `height` rows of `width_bytes`, rows `dpitch` / `spitch` bytes apart (async) */
+int fl_d2d_2d(void *dst_dev, size_t dpitch, const void *src_dev, size_t spitch, size_t width_bytes, size_t height);
 int fl_sync(void);
 void *fl_host_alloc_pinned(size_t bytes);
 int fl_host_free_pinned(void *p);

@@ -70,6 +70,7 @@ int fl_dev_memset(void *p, int v, size_t b) { memset(p, v, b); return 0; }
 int fl_h2d(void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
 int fl_d2h(void *d, const void *s, size_t b) { memcpy(d, s, b); return 0; }
 int fl_d2d(void *d, const void *s, size_t b) { memmove(d, s, b); return 0; }
+int fl_d2d_2d(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h) { for (size_t r = 0; r < h; r++) memmove((char *)d + r * dp, (const char *)s + r * sp, w); return 0; }
 int fl_sync(void) { return 0; }
 void *fl_host_alloc_pinned(size_t b) { return malloc(b ? b : 1); }
 int fl_host_free_pinned(void *p) { free(p); return 0; }

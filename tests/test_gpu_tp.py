@@ -28,10 +28,23 @@ if world > 1:
         idbuf = torch.tensor(list(raw.raw), dtype=torch.uint8, device="cuda")
     dist.broadcast(idbuf, 0)
     fl.check(fl.lib.fl_comm_init(rank, world, idbuf.cpu().numpy().tobytes()))
-m = Model(path, num_threads=2, n_ctx=64, n_batch=8, logger=QuietLogger())
+scenario = sys.argv[4] if len(sys.argv) > 4 else "decode"
+m = Model(path, num_threads=2, n_ctx=64 if scenario == "decode" else 128, n_batch=8, logger=QuietLogger())
 m.ingest("Tensor parallel decode over two ranks.")
 toks = []
-m.generate(lambda s: toks.append(s), num_tokens=16, temp=0.0, top_k=1, top_p=1.0, repeat_penalty=1.0)
+gen = lambda n: m.generate(lambda s: toks.append(s), num_tokens=n, temp=0.0, top_k=1, top_p=1.0, repeat_penalty=1.0)
+if scenario == "reingest":       # sharded decode, then a replicated multi-token eval and a state file: both need the KV gather
+    gen(5)
+    m.ingest(" And a second prompt that attends to all of it.")
+    gen(4)
+    assert m.save_state(out + f".rank{rank}.state")
+    gen(3)
+    first = list(toks[-3:])
+    assert m.load_state(out + f".rank{rank}.state")
+    gen(3)
+    assert list(toks[-3:]) == first, (toks[-3:], first)
+else:
+    gen(16)
 np.savez(out + f".rank{rank}.npz", toks=np.array(toks), logits=m.get_logits_array())
 m.close()
 '''
@@ -46,7 +59,8 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-def test_tp2_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("scenario", ["decode", "reingest"])
+def test_tp2_matches_single_gpu(tmp_path, scenario):
     from fastllama_b200.ggjt import Q4_0, write_synthetic_numpy
     from oracle.pyoracle import Oracle
 
@@ -60,7 +74,7 @@ def test_tp2_matches_single_gpu(tmp_path):
         procs = []
         for r in range(world):
             env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT="29641")
-            procs.append(subprocess.Popen([sys.executable, str(script), ROOT, path, str(tmp_path / tag)], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE))
+            procs.append(subprocess.Popen([sys.executable, str(script), ROOT, path, str(tmp_path / tag), scenario], env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE))
         for p in procs:
             _, err = p.communicate(timeout=300)
             assert p.returncode == 0, err.decode()[-2000:]

@@ -34,10 +34,25 @@ def coll(kind, send, recv, n):
         r[:] = torch.cat(parts).numpy()
 cb = CB(coll)
 lib.fl_mock_set_collective(cb, rank, world)
-m = Model(path, num_threads=2, n_ctx=64, n_batch=int(sys.argv[5]), logger=QuietLogger(), library_path=os.path.join(mock, "pyfastllama.so"))
+scenario = sys.argv[6] if len(sys.argv) > 6 else "decode"
+m = Model(path, num_threads=2, n_ctx=64 if scenario == "decode" else 128, n_batch=int(sys.argv[5]), logger=QuietLogger(), library_path=os.path.join(mock, "pyfastllama.so"))
 m.ingest("Tensor parallel decode over two ranks.")
 toks = []
-m.generate(lambda s: toks.append(s), num_tokens=10, temp=0.0, top_k=1, top_p=1.0, repeat_penalty=1.0)
+gen = lambda n: m.generate(lambda s: toks.append(s), num_tokens=n, temp=0.0, top_k=1, top_p=1.0, repeat_penalty=1.0)
+if scenario == "reingest":
+    # sharded decode steps, then a replicated multi-token eval that reads the whole KV cache (needs the KV gather), then
+    # a state file written from a gathered cache and resumed
+    gen(5)
+    m.ingest(" And a second prompt that attends to all of it.")
+    gen(4)
+    assert m.save_state(out + f".rank{rank}.state")
+    gen(3)
+    first = list(toks[-3:])
+    assert m.load_state(out + f".rank{rank}.state")
+    gen(3)
+    assert list(toks[-3:]) == first, (toks[-3:], first)
+else:
+    gen(10)
 mode = C.CDLL(os.path.join(mock, "libggml_b200.so")).ggml_b200_decode_mode()
 np.savez(out + f".rank{rank}.npz", toks=np.array(toks), logits=m.get_logits_array(), mode=mode)
 m.close()
@@ -47,7 +62,7 @@ m.close()
 @pytest.mark.skipif(not os.path.exists(os.path.join(MOCK, "pyfastllama.so")), reason="tests/mock not built (needs the drop-in library)")
 @pytest.mark.parametrize("n_batch", [1, 8])
 @pytest.mark.parametrize("peer", [False, True])
-def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch, peer):
+def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch, peer, scenario="decode"):
     """peer=False: the two reductions per layer are collectives between per-matrix kernels (the NCCL path).
     peer=True: the mock maps POSIX shared memory between the ranks like fl_comm_shared_alloc maps peer HBM, so the
     sharded plan runs as the token program with partial sums pushed into the peers' buffers and summed in rank order."""
@@ -68,7 +83,7 @@ def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch, peer):
             env.pop("FL_MOCK_SESSION", None)
             if peer:
                 env["FL_MOCK_SESSION"] = f"{os.getpid()}_{tag}_{n_batch}"
-            procs.append(subprocess.Popen([sys.executable, str(script), ROOT, MOCK, path, str(tmp_path / tag), str(n_batch)], env=env,
+            procs.append(subprocess.Popen([sys.executable, str(script), ROOT, MOCK, path, str(tmp_path / tag), str(n_batch), scenario], env=env,
                                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE))
         for p in procs:
             _, err = p.communicate(timeout=240)
@@ -84,3 +99,12 @@ def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch, peer):
         # K-split changes the fp32 summation order across ranks: same tolerance policy as the single-GPU path
         assert np.abs(r["logits"] - single["logits"]).max() <= 2e-2 * np.abs(single["logits"]).max()
     assert np.array_equal(tp[0]["logits"], tp[1]["logits"])          # ranks stay in lockstep bit for bit
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(MOCK, "pyfastllama.so")), reason="tests/mock not built (needs the drop-in library)")
+@pytest.mark.parametrize("peer", [False, True])
+def test_tensor_parallel_kv_gather_before_replicated_eval_and_state(tmp_path, peer):
+    """Decode steps shard the KV cache by head; a later multi-token eval and save_state need all heads: the ranks
+    all-gather the sharded positions first (ggml_b200.cpp tp_gather_kv).  Same tokens as one rank, and each rank's state
+    file resumes identically."""
+    test_tensor_parallel_decode_matches_single_rank(tmp_path, 4, peer, scenario="reingest")
