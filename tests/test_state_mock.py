@@ -11,7 +11,9 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-MOCK = os.path.join(ROOT, "tests", "mock", "build")
+from tests.mockbuild import ensure_mock  # noqa: E402
+
+MOCK = ensure_mock()
 
 WORKER = r'''
 import ctypes as C, os, sys, numpy as np
