@@ -35,6 +35,37 @@ def activation_rows(rng, n, k):
     return x
 
 
+LLAMA_TOY = dict(n_vocab=96, n_embd=256, n_head=4, n_layer=3, n_mult=256, n_ctx=32)
+LLAMA_TOY_STEPS = [([5, 17, 3, 80, 41], 0), ([7], 5), ([60], 6), ([2], 7)]
+LLAMA_TOY_SEED = 3
+
+
+def llama_toy(ref):
+    """Whole-graph fixture: logits and final embeddings of the reference LIBRARY (libggml_ref.so, CPU) for a tiny LLaMA
+    built through the ggml C API exactly like Model::eval builds it (tests/llama_graph.py): a 5-token prompt, then three
+    decode steps that read the KV cache.  Weights come from tests.llama_graph.make_weights (numpy seed + the reference's
+    own file quantiser), so a test on a machine without /root/reference rebuilds the same model bit for bit."""
+    from oracle.pyoracle import REF_GGML_SO, Oracle
+    from tests import ggml_api as G
+    from tests.llama_graph import HParams, MiniLlama, make_weights
+
+    orc = Oracle()
+    g = G.Ggml(REF_GGML_SO)
+    for name, t in (("q4_0", G.Q4_0), ("q4_1", G.Q4_1)):
+        hp = HParams(**LLAMA_TOY)
+        w = make_weights(hp, t, lambda x, tt: orc.quantize_q4(x, tt), seed=LLAMA_TOY_SEED)
+        m = MiniLlama(g, hp, w, compute_mb=32)
+        out = {}
+        for i, (tokens, n_past) in enumerate(LLAMA_TOY_STEPS):
+            c, gf, named = m.eval(tokens, n_past)
+            m.compute(c, gf)
+            out[f"logits{i}"] = c.numpy(named["logits"]).copy()
+            out[f"emb{i}"] = c.numpy(named["embeddings"]).copy()
+        path = os.path.join(OUT, f"llama_toy_{name}.npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     build_oracle()
     ref = RefGgml()
@@ -56,6 +87,7 @@ def main():
         path = os.path.join(OUT, f"rowfns_k{k}.npz")
         np.savez_compressed(path, **out)
         print("wrote", path, os.path.getsize(path), "bytes")
+    llama_toy(ref)
 
 
 if __name__ == "__main__":
