@@ -1,6 +1,6 @@
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from fastllama_b200.build import lib_path
 from fastllama_b200.ggjt import Q4_0, write_synthetic_numpy
 from fastllama_b200.model import Model, QuietLogger, Logger

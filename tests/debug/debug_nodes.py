@@ -6,7 +6,7 @@ import sys
 import numpy as np
 
 os.environ["FASTLLAMA_B200_SYNC_ALL"] = "1"
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from fastllama_b200.build import lib_path  # noqa: E402
 from oracle.pyoracle import REF_GGML_SO, Oracle  # noqa: E402
 from tests import ggml_api as G  # noqa: E402
