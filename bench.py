@@ -190,7 +190,7 @@ def main():
         args.warmup_cpu = min(args.warmup, 3)
         t0 = time.perf_counter()
         cb = run_reference(args, path, steps)
-        line = {"impl": "reference", "metric": "tokens/sec LLaMA-7B q4_0 decode (n_batch=1, greedy)", "value": cb["value"], "unit": "tokens/s",
+        line = {"impl": "reference", "metric": f"tokens/sec LLaMA-{args.size} {args.wtype} decode (n_batch=1, greedy)", "value": cb["value"], "unit": "tokens/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup_cpu, "ms_per_step": 1000.0 / cb["value"] if cb["value"] else None,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": f"LLaMA-{args.size} {args.wtype} decode n_batch=1 n_ctx=512, reference CPU path", "cpu_threads": cb["cores"]},
@@ -338,6 +338,9 @@ def main():
             traffic = int(cap["dram_bytes_read"]) + int(cap["dram_bytes_write"])
         except Exception:
             traffic = None
+    from fastllama_b200.ggjt import LLAMA_SIZES
+
+    n_embd_model = LLAMA_SIZES[args.size][0]
     line = {
         "metric": f"tokens/sec LLaMA-{args.size} {args.wtype} decode (n_batch=1, greedy)", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": n_tok,
         "warmup": args.warmup, "ms_per_step": 1000.0 * device_s / n_tok if n_tok else None, "higher_is_better": True,
@@ -352,7 +355,7 @@ def main():
                        if tp else f"{world} independent replicas"),
                    "l2": f"inputs ({(algo or 0) / 1e9:.2f} GB of weights per token) are {(algo or 0) / 126e6:.0f}x larger than L2; no flush needed",
                    "algorithmic_bytes_per_token": algo, "device": props["name"]},
-        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 32000 * 4 + 4096 * 4,
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 32000 * 4 + n_embd_model * 4,
                 "api": "fastllama_b200.Model.generate -> pyfastllama.so (reference bridge, unchanged) -> libggml_b200 -> libfl_cuda"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
