@@ -6,8 +6,7 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-# FASTLLAMA_B200_LIB_DIR: tests point this at tests/mock/build to dry-run host logic against the CPU mock
-LIB_DIR = os.environ.get("FASTLLAMA_B200_LIB_DIR") or os.path.join(PKG, "lib")
+LIB_DIR = os.path.join(PKG, "lib")       # the only place the package loads native code from (tests pass explicit paths to stand-ins)
 CSRC = os.path.join(PKG, "csrc")
 
 

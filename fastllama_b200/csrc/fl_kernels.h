@@ -43,3 +43,9 @@ int flk_soft_max(cudaStream_t st, const fl_view &t, const uint16_t *exp_table_f1
 int flk_rope(cudaStream_t st, const fl_view &t, int n_past, int n_dims, int mode, const float2 *cs, int n_pos);
 int flk_cpy_f32(cudaStream_t st, const fl_view &src, const fl_view &dst);
 int flk_mul_mat_f32(cudaStream_t st, const fl_view &src0, const fl_view &src1, const fl_view &dst);
+
+// fl_umma_kernel.cu: N > 1 on the Blackwell tensor cores: one tcgen05.mma kind::i8 (M = 128, K = 32) per quant block into TMEM,
+// weights by TMA, exact fp32 block scaling by the epilogue warps.  nt_hint: column-tile width (0 = choose; 32 / 64 / 128)
+int flk_mul_mat_q_umma_supported(int type, const void *W, size_t w_row_stride, int M, int K, int N);
+int flk_mul_mat_q_umma(cudaStream_t st, int type, const void *W, size_t w_row_stride, int M, int K, const void *Yq8, int N, float *dst,
+                       size_t dst_row_stride, int nt_hint);

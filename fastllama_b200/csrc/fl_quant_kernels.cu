@@ -577,7 +577,13 @@ int flk_mul_mat_q(cudaStream_t st, int type, const void *W, size_t wrs, int M, i
         p.dst = dst;
         return launch_ring(st, type, nfull, p, threads, smem);
     }
-    // N > 1 (prompt ingest): the block dots go to the tensor cores (fl_mma_kernel.cu); tiny N stays on the plain kernel
+    // N > 1 (prompt ingest): the block dots go to the tensor cores.  tcgen05 path (fl_umma_kernel.cu): impl 4 (tile width chosen),
+    // 5 / 6 / 7 = column tiles of 32 / 64 / 128; legacy mma.sync path (fl_mma_kernel.cu): impl 3 and small N; tiny N stays on the plain kernel
+    if (impl >= 4 && impl <= 7) return flk_mul_mat_q_umma(st, type, W, wrs, M, K, Yq8, N, dst, drs, impl == 4 ? 0 : 16 << (impl - 4));
+    {
+        static const int umma_auto = getenv("FASTLLAMA_B200_UMMA") ? atoi(getenv("FASTLLAMA_B200_UMMA")) : 0;
+        if (impl == 0 && umma_auto && N >= 16 && flk_mul_mat_q_umma_supported(type, W, wrs, M, K, N)) return flk_mul_mat_q_umma(st, type, W, wrs, M, K, Yq8, N, dst, drs, 0);
+    }
     if (impl == 3 || (impl == 0 && N >= 4)) return flk_mul_mat_q_mma(st, type, W, wrs, M, K, Yq8, N, dst, drs);
     return launch_plain(st, type, W, wrs, M, K, Yq8, N, dst, drs);
 }

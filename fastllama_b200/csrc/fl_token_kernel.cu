@@ -66,6 +66,7 @@ struct tk_params {
     uint32_t grid_magic, grid_shift, s_magic, s_shift;  // n / d == umulhi(n, magic) >> shift (magic 0: d is a power of two, n >> shift); exact for n < 2^31
     uint32_t slot_bytes;
     int l2_prefetch;
+    int diag;                        // FASTLLAMA_B200_TK_DIAG (timing experiments only; results are garbage): 1 = no weight copies, 2 = no dot products, 4 = no grid barriers, 8 = no prologue
     uint32_t off_y, off_red, off_rowbuf, off_cnt, off_sc, off_stage0;
 };
 
@@ -345,7 +346,20 @@ __device__ __forceinline__ void tk_prologue(const fl_mv_args &A, int K, tk_ybloc
 }
 
 // ---- epilogue of one unit (lane 0 of the warp that holds the complete sums a, b) --------------------
-__device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, float a, float b, int n_past) {
+// `pre` is what the epilogue needs from memory -- the residual pair (RESADD) or the rope (cos, sin) pair (QKV, q and k rows) --
+// loaded by tk_epilogue_preload BEFORE the warp's dot products, so its L2 round trip hides behind them.
+__device__ __forceinline__ float2 tk_epilogue_preload(const tk_phase &ph, int seg, int u, int n_past) {
+    const fl_mv_args &A = ph.a;
+    if (ph.swiglu) return make_float2(0.f, 0.f);
+    const int r2 = 2 * u;
+    if (A.epi == FL_EPI_QKV) {
+        if (seg < 2) return __ldg((const float2 *)A.rope_cs + (size_t)n_past * (A.head_dim >> 1) + ((r2 % A.head_dim) >> 1));
+        return make_float2(0.f, 0.f);
+    }
+    if (A.epi == FL_EPI_RESADD) return __ldcg((const float2 *)(A.res + r2));
+    return make_float2(0.f, 0.f);
+}
+__device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, float a, float b, int n_past, float2 pre) {
     const fl_mv_args &A = ph.a;
     if (ph.swiglu) {
         const uint16_t h = __half_as_ushort(__float2half_rn(a));
@@ -355,8 +369,7 @@ __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, 
     const int r2 = 2 * u;
     if (A.epi == FL_EPI_QKV) {
         if (seg < 2) {
-            const int ip = (r2 % A.head_dim) >> 1;
-            const float2 cs = __ldg((const float2 *)A.rope_cs + (size_t)n_past * (A.head_dim >> 1) + ip);
+            const float2 cs = pre;
             const float y0 = __fmaf_rn(a, cs.x, -__fmul_rn(b, cs.y));
             const float y1 = __fmaf_rn(a, cs.y, __fmul_rn(b, cs.x));
             float *o = (seg == 0) ? (A.seg_dst[0] + r2) : (A.kcache + (size_t)n_past * A.n_embd + r2);
@@ -369,9 +382,8 @@ __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, 
     }
     float *dst = A.seg_dst[seg] + r2;
     if (A.epi == FL_EPI_RESADD) {
-        const float2 r = __ldcg((const float2 *)(A.res + r2));
-        a = __fadd_rn(a, r.x);
-        b = __fadd_rn(b, r.y);
+        a = __fadd_rn(a, pre.x);
+        b = __fadd_rn(b, pre.y);
     }
     *(float2 *)dst = make_float2(a, b);
     for (int r = 0; r < A.n_dst_peer; r++) *(float2 *)(A.dst_peer[r] + r2) = make_float2(a, b);     // posted stores over NVLink
@@ -420,12 +432,14 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
         int seg, unit0, nunits;
         tk_tile_of(sl, G, t, seg, unit0, nunits);
         fl_mbar_wait(bar0 + 8u * s, par);
-        if (g < nunits) {
+        if (g < nunits && !(prm.diag & 2)) {
             const uint8_t *tile = stage0 + (size_t)s * prm.slot_bytes;
             // default: pair rows are adjacent; swiglu: [nunits rows of w1][nunits rows of w3]
             const uint8_t *rowA = tile + (size_t)(swiglu ? g : 2 * g) * row_bytes + (size_t)(b0 + lane) * BB;
             const uint8_t *rowB = rowA + (size_t)(swiglu ? nunits : 1) * row_bytes;
             float accA = 0.0f, accmA = 0.0f, accB = 0.0f, accmB = 0.0f;
+            float2 pre = make_float2(0.f, 0.f);
+            if (lane == 0) pre = tk_epilogue_preload(ph, seg, unit0 + g, n_past);
 #pragma unroll
             for (int j = 0; j < FD_NBL; j++) {
                 if (j < NFULL || valid[j]) {
@@ -445,7 +459,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
             if (lane == 0) {
                 const int u = unit0 + g;
                 if (kparts == 1) {
-                    tk_epilogue(ph, seg, u, totA, totB, n_past);
+                    tk_epilogue(ph, seg, u, totA, totB, n_past, pre);
                 } else {
                     volatile float *rb = rowbuf + ((size_t)s * TK_GMAX + g) * 8;      // [2 rows][kparts <= 4]
                     rb[p] = totA;
@@ -457,7 +471,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
                         __threadfence_block();
                         float x0 = rb[0], x1 = rb[4];
                         for (int q = 1; q < kparts; q++) { x0 = __fadd_rn(x0, rb[q]); x1 = __fadd_rn(x1, rb[4 + q]); }
-                        tk_epilogue(ph, seg, u, x0, x1, n_past);
+                        tk_epilogue(ph, seg, u, x0, x1, n_past, pre);
                     }
                 }
             }
@@ -646,7 +660,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
                     tk_tile_of(sl, G, t, seg, unit0, nunits);
                     fl_mbar_wait(bar0 + 8u * (S + s), par);
                     const uint32_t dst = fl_smem_u32(stage0 + (size_t)s * prm.slot_bytes);
-                    if (swiglu) {
+                    if (prm.diag & 1) {
+                        fl_mbar_arrive(bar0 + 8u * s);
+                    } else if (swiglu) {
                         const uint32_t half = (uint32_t)nunits * row_bytes;
                         fl_mbar_expect_tx(bar0 + 8u * s, 2 * half);
                         fl_bulk_g2s_hint(dst, w0 + (size_t)unit0 * row_bytes, half, bar0 + 8u * s, pol);
@@ -690,7 +706,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
             epoch++;
             const bool xgpu = ph.kind == TK_PH_MATVEC && ph.a.n_xpeer > 0;   // this phase reads the other GPUs' partial results
             if (xgpu) xepoch++;
-            tk_grid_sync(prm, epoch * gridDim.x, xgpu ? xepoch : 0u);   // results of phase pi-1 are visible everywhere
+            if (!(prm.diag & 4)) tk_grid_sync(prm, epoch * gridDim.x, xgpu ? xepoch : 0u);   // results of phase pi-1 are visible everywhere
         }
         if (pr) pr[1] = tk_now();
         // Descriptor pi+1: the load is issued now, the store into phs[(pi+1)&1] (which nobody reads any more: everybody is
@@ -699,7 +715,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         const bool copies = tid < (int)(sizeof(tk_phase) / 4) && pi + 1 < prm.n_phases;
         if (copies) next_word = __ldcg((const uint32_t *)&prm.phases[pi + 1] + tid);
         if (ph.kind == TK_PH_ATTN) {
-            if (attn_here) tk_attention(ph, prm, sc, red, a_head, a_part, warp, lane, tid);
+            if (attn_here && !(prm.diag & 16)) tk_attention(ph, prm, sc, red, a_head, a_part, warp, lane, tid);
             if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
             tk_bar_consumers(15);                                // the next iteration reads the new descriptor before its grid barrier
             if (pr) pr[2] = pr[3] = tk_now();
@@ -707,7 +723,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         }
         const int K = ph.nb * 32;
         if (tid == TK_NT - 1) sl_sh = tk_make_slice_u(ph.units[0], ph.units[1], ph.units[2], ph.lgG, prm.grid_magic, prm.grid_shift);
-        tk_prologue(ph.a, K, ysm, red, warp, lane, tid);
+        if (!(prm.diag & 8)) tk_prologue(ph.a, K, ysm, red, warp, lane, tid);
         if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
         tk_bar_consumers(15);                                    // activations, slice and next descriptor are in shared memory
         if (pr) pr[2] = tk_now();
@@ -860,6 +876,7 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     // (7B decode 49.6 vs 45.8 us per layer), so it is opt-in
     p.l2_prefetch = getenv("FASTLLAMA_B200_L2_PREFETCH") ? atoi(getenv("FASTLLAMA_B200_L2_PREFETCH")) : 0;
     p.exp_tab = exp_tab;
+    p.diag = getenv("FASTLLAMA_B200_TK_DIAG") ? atoi(getenv("FASTLLAMA_B200_TK_DIAG")) : 0;
     pl->smem = off + (size_t)S * slot;
     FL_CUDA_OK(cudaMalloc((void **)&pl->d_phases, sizeof(tk_phase) * (size_t)n_steps));
     FL_CUDA_OK(cudaMemcpy(pl->d_phases, phases.data(), sizeof(tk_phase) * (size_t)n_steps, cudaMemcpyHostToDevice));
@@ -895,7 +912,7 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     FL_CUDA_OK(cudaFuncSetAttribute(k_decode_token, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     int per_sm = 0;
     FL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_token, TK_THREADS, pl->smem));
-    if (per_sm < 1) { delete pl; fl_set_error("token kernel: one CTA per SM does not fit (smem %zu)", pl->smem); return -1; }
+    if (per_sm < 1) { const size_t need = pl->smem; delete pl; fl_set_error("token kernel: one CTA per SM does not fit (smem %zu)", need); return -1; }
     pl->n_kernels = sm;
     *out = pl;
     return 0;

@@ -637,6 +637,14 @@ Mirror &mirror_alloc(Mirror &m) {
 }
 }  // namespace
 
+static void packed_shards_clear();
+static void drop_external_mirrors() {
+    bool any = false;
+    for (auto &m : g_mirrors)
+        if (m.alive && m.kind == MK_EXTERNAL) { if (!any && fl_is_initialized()) fl_sync(); any = true; drop_mirror(m); m.alive = false; m.uploaded = 0; }
+    if (any) packed_shards_clear();
+    g_last_mirror = -1;
+}
 static void mirrors_on_ctx_init(ggml_context *ctx) {
     // an arena re-created over the same buffer (Model::eval does this every call) re-uses its mirror
     int found = -1;
@@ -645,7 +653,7 @@ static void mirrors_on_ctx_init(ggml_context *ctx) {
         if (!m.alive) continue;
         const bool same = m.host == ctx->mem_buffer && m.size == ctx->mem_size;
         const bool overlap = m.host < ctx->mem_buffer + ctx->mem_size && ctx->mem_buffer < m.host + m.size;
-        if (same) { found = i; m.alloc_end = 0; m.uploaded = 0; m.kind = MK_ARENA; }
+        if (same) { found = i; if (m.uploaded) packed_shards_clear(); m.alloc_end = 0; m.uploaded = 0; m.kind = MK_ARENA; }
         else if (overlap) { drop_mirror(m); m.alive = false; }      // the buffer was re-allocated
     }
     if (found < 0) {
@@ -654,6 +662,11 @@ static void mirrors_on_ctx_init(ggml_context *ctx) {
     }
     ctx->mirror_id = found;
     g_last_mirror = -1;
+    // A no_alloc context is how the reference loads a model whose tensors point into an mmap'ed file
+    // (include/tensor/mem_context.hpp:12-16, lib/llama.cpp:213-258).  MK_EXTERNAL mirrors are keyed by host address only, and a
+    // new mapping may land on the addresses of an earlier model's: everything registered for earlier mappings is stale now.
+    // (A model that is still alive simply re-registers and re-uploads its tensors on next use.)
+    if (ctx->no_alloc) drop_external_mirrors();
 }
 static void mirrors_on_ctx_free(ggml_context *) {}   // the arena (and its device mirror) outlives the context slot
 static void mirrors_note_alloc(ggml_context *ctx, size_t end) {
@@ -740,13 +753,21 @@ extern "C" void ggml_b200_sync_to_host(const void *ptr, size_t size) {
     FLC(fl_d2h((void *)(m.host + off), m.dev + off, n));
     FLC(fl_sync());
 }
+static void decode_state_release();
+// Frees every device resource of the backend: decode graph / token plan / workspace, tensor-parallel shards, all mirrors.
+// fastllama_b200.Model.close() calls it after llama_free_context; the next model starts from a clean device.
 extern "C" void ggml_b200_release_all(void) {
     if (fl_is_initialized()) fl_sync();
+    decode_state_release();
+    packed_shards_clear();
     for (auto &m : g_mirrors) {
         drop_mirror(m);
         m.uploaded = 0;
+        m.device_dirty = false;
         if (m.kind != MK_ARENA) m.alive = false;
     }
+    // arenas whose host buffer is gone would never be matched again: forget all records (a live arena re-registers at its next ggml_init,
+    // and a context that is still open keeps working because mirror lookups are by address)
     g_last_mirror = -1;
 }
 // how the last single-token eval ran: 0 = node-by-node executor, 1 = fused plan with one kernel per matrix group,
@@ -1027,7 +1048,7 @@ void ensure_ws(DecodeWs &w, int n_embd, int n_ff, int n_vocab) {
         // layout of every rank's buffer: 4096 bytes of flags, then part1[world][n_embd], part2[world][n_embd]: slot r is
         // written by rank r (into its own buffer and, over NVLink, into everybody else's)
         const int world = fl_comm_world(), rank = fl_comm_rank();
-        if (fl_comm_shared_alloc(4096 + (size_t)2 * world * n_embd * sizeof(float), w.peers) == 0) {
+        if (fl_comm_shared_alloc(4096 + (size_t)2 * world * std::max(n_embd, 8192) * sizeof(float), w.peers) == 0) {
             w.part1 = (float *)((char *)w.peers[rank] + 4096) + (size_t)rank * n_embd;
             w.part2 = w.part1 + (size_t)world * n_embd;
             w.peer_mapped = true;
@@ -1040,6 +1061,14 @@ void ensure_ws(DecodeWs &w, int n_embd, int n_ff, int n_vocab) {
 // K-split shards of wo / w2 (tensor parallelism): blocks [blk0, blk0 + nblk) of every row, packed once
 // into a private matrix with a 16-byte-multiple row stride so each tile is still one bulk copy
 std::unordered_map<const void *, void *> g_packed;
+}  // namespace
+static void packed_shards_clear() {
+    if (g_packed.empty()) return;
+    if (fl_is_initialized()) fl_sync();
+    for (auto &kv : g_packed) fl_dev_free(kv.second);
+    g_packed.clear();
+}
+namespace {
 const void *packed_shard(const ggml_tensor *w, const void *w_dev, int blk0, int nblk, size_t &stride_out) {
     const size_t bb = k_tsize[w->type];
     stride_out = ((size_t)nblk * bb + 15) & ~(size_t)15;
@@ -1376,6 +1405,18 @@ bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, 
     return true;
 }
 }  // namespace
+
+static void decode_state_release() {
+    DecodeState &D = g_dec;
+    if (!fl_is_initialized()) return;
+    if (D.graph) { fl_graph_destroy(D.graph); D.graph = nullptr; }
+    if (D.token_plan) { fl_token_plan_destroy(D.token_plan); D.token_plan = nullptr; }
+    if (D.ws.xa) { fl_dev_free(D.ws.xa); D.ws = DecodeWs(); }      // the peer-mapped reduction buffers (tensor parallel) stay: they are per process
+    D.plan = DecodePlan();
+    D.tp_kv_sharded = false;
+    g_tp_kv_sharded = false;
+    if (g_exec.q8_work) { fl_dev_free(g_exec.q8_work); g_exec.q8_work = nullptr; g_exec.q8_cap = 0; }
+}
 
 // Tensor-parallel decode steps write only this rank's heads of the new positions into the KV cache (K [pos][n_embd]: nl
 // columns per row; V [n_embd][n_ctx]: nl rows).  Before anything reads the cache as a whole -- a replicated multi-token
