@@ -15,5 +15,6 @@ int flk_token_plan_launch(cudaStream_t st, void *plan);
 int flk_token_plan_destroy(void *plan);
 int flk_token_plan_profile(void *plan, unsigned long long *out, size_t max_words, int *n_ctas);
 int flk_token_plan_error(void *plan);
+int flk_token_plan_profile2(void *plan, unsigned *out, size_t max_words);
 // fl_runtime.cu: the peer-mapped buffers of fl_comm_shared_alloc (nullptr when there are none)
 const void *const *fl_shared_peers(int *rank, int *world);

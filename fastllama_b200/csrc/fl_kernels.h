@@ -49,3 +49,9 @@ int flk_mul_mat_f32(cudaStream_t st, const fl_view &src0, const fl_view &src1, c
 int flk_mul_mat_q_umma_supported(int type, const void *W, size_t w_row_stride, int M, int K, int N);
 int flk_mul_mat_q_umma(cudaStream_t st, int type, const void *W, size_t w_row_stride, int M, int K, const void *Yq8, int N, float *dst,
                        size_t dst_row_stride, int nt_hint);
+
+// fl_lora_kernels.cu: the SIMD weight quantisers (quantize_fns[].quantize_row_q) and the ops of attach_lora / detach_lora
+int flk_quantize_q4_simd(cudaStream_t st, int type, const float *x, void *y, int k, int nrows);
+int flk_add_q_f32(cudaStream_t st, int type, const void *W, size_t w_row_stride, int M, int K, const float *X, size_t x_row_stride_elems, void *dst,
+                  size_t dst_row_stride);
+int flk_mul_mat_f32_ref(cudaStream_t st, const float *A, size_t lda, int Ma, const float *B, size_t ldb, int Mb, int K, float *out, size_t ldo);

@@ -271,6 +271,20 @@ extern "C" int fl_dev_quantize_q4(int type, const float *x, void *y, int k, int 
     return flk_quantize_q4(g.stream, type, x, y, k, nrows);
 }
 
+extern "C" int fl_dev_quantize_q4_simd(int type, const float *x, void *y, int k, int nrows) {
+    FL_NEED_INIT();
+    return flk_quantize_q4_simd(g.stream, type, x, y, k, nrows);
+}
+extern "C" int fl_dev_add_q_f32(int type, const void *W, size_t w_row_stride_bytes, int M, int K, const float *X, size_t x_row_stride_elems, void *dst,
+                                size_t dst_row_stride_bytes) {
+    FL_NEED_INIT();
+    return flk_add_q_f32(g.stream, type, W, w_row_stride_bytes, M, K, X, x_row_stride_elems, dst, dst_row_stride_bytes);
+}
+extern "C" int fl_dev_mul_mat_f32_ref(const float *A, size_t lda, int Ma, const float *B, size_t ldb, int Mb, int K, float *out, size_t ldo) {
+    FL_NEED_INIT();
+    return flk_mul_mat_f32_ref(g.stream, A, lda, Ma, B, ldb, Mb, K, out, ldo);
+}
+
 extern "C" int fl_dev_rms_norm(const fl_view *src, const fl_view *dst) {
     FL_NEED_INIT();
     return flk_rms_norm(g.stream, *src, *dst, 1e-6f);
@@ -358,6 +372,11 @@ extern "C" int fl_token_plan_profile(void *plan, unsigned long long *out, size_t
     FL_NEED_INIT();
     FL_CUDA_OK(cudaStreamSynchronize(g.stream));
     return flk_token_plan_profile(plan, out, max_words, n_ctas);
+}
+extern "C" int fl_token_plan_profile2(void *plan, unsigned *out, size_t max_words) {
+    FL_NEED_INIT();
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return flk_token_plan_profile2(plan, out, max_words);
 }
 extern "C" int fl_token_plan_error(void *plan) {
     FL_NEED_INIT();
@@ -764,6 +783,21 @@ extern "C" int fl_quantize_rows_q4(int type, const float *x, void *y, int k, int
     if (scratch_get(0, xin, &dx) || scratch_get(1, yout, &dy)) return -1;
     FL_CUDA_OK(cudaMemcpyAsync(dx, x, xin, cudaMemcpyHostToDevice, g.stream));
     if (flk_quantize_q4(g.stream, type, (const float *)dx, dy, k, nrows)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(y, dy, yout, cudaMemcpyDeviceToHost, g.stream));
+    FL_CUDA_OK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+
+extern "C" int fl_quantize_rows_q4_simd(int type, const float *x, void *y, int k, int nrows) {
+    FL_NEED_INIT();
+    FL_REQUIRE(x && y && k > 0 && k % FL_QK == 0 && nrows >= 0, "fl_quantize_rows_q4_simd: bad arguments (k=%d)", k);
+    FL_REQUIRE(type == FL_TYPE_Q4_0 || type == FL_TYPE_Q4_1, "fl_quantize_rows_q4_simd: unsupported type %d", type);
+    if (nrows == 0) return 0;
+    const size_t xin = (size_t)k * nrows * sizeof(float), yout = (size_t)(k / FL_QK) * nrows * fl_block_bytes(type);
+    void *dx, *dy;
+    if (scratch_get(0, xin, &dx) || scratch_get(1, yout, &dy)) return -1;
+    FL_CUDA_OK(cudaMemcpyAsync(dx, x, xin, cudaMemcpyHostToDevice, g.stream));
+    if (flk_quantize_q4_simd(g.stream, type, (const float *)dx, dy, k, nrows)) return -1;
     FL_CUDA_OK(cudaMemcpyAsync(y, dy, yout, cudaMemcpyDeviceToHost, g.stream));
     FL_CUDA_OK(cudaStreamSynchronize(g.stream));
     return 0;

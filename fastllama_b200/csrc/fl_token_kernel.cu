@@ -55,13 +55,15 @@ struct tk_phase {
 struct tk_params {
     const tk_phase *phases;
     int n_phases;
-    unsigned *grid_bar;              // [0] arrival counter (zeroed per launch), [32] error flag
+    unsigned *grid_bar;              // [0] arrival counter (zeroed per launch)
+    unsigned *err;                   // error block in pinned, device-mapped HOST memory: [0] flag, [1..4] details (the host reads it without a copy)
     unsigned *xflags_local;          // tensor parallel: flags[q * 32] is written by rank q (through its peer mapping of this buffer)
     unsigned *xflags_peer[8];        // rank p's flag array as mapped here
     int rank, world;
     int xrelease_sys;                // FASTLLAMA_B200_TP_RELEASE_SYS: every CTA releases at sys scope (measured 644 vs 697 tok/s at TP2)
     const uint16_t *exp_tab;
     unsigned long long *prof;      // optional: [n_phases][gridDim.x][4] globaltimer stamps of thread 0
+    unsigned *prof2;               // optional (PROF kernel only): [n_phases][gridDim.x][TK_CW][8] cycle counts of every consumer warp's tile loop
     int S;
     uint32_t grid_magic, grid_shift, s_magic, s_shift;  // n / d == umulhi(n, magic) >> shift (magic 0: d is a power of two, n >> shift); exact for n < 2^31
     uint32_t slot_bytes;
@@ -104,7 +106,7 @@ __device__ __forceinline__ void tk_wait_ge(const unsigned *p, unsigned target, b
 __device__ __forceinline__ void tk_grid_sync(const tk_params &prm, unsigned target, unsigned xe) {
     tk_bar_consumers(13);
     if (threadIdx.x == 0) {
-        unsigned *err = prm.grid_bar + 32;
+        unsigned *err = prm.err;
         // The phase that just ended may have stored to peer memory.  A gpu-scope release per CTA is enough: CTA 0 acquires all of
         // them and then fences at sys scope before raising the flag, and causality order composes across the two scopes.
         if (xe && prm.xrelease_sys) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prm.grid_bar) : "memory");
@@ -390,9 +392,16 @@ __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, 
 }
 
 // ---- main loop of a matvec phase for one consumer warp ------------------------------------------------
-template <int TYPE, int NFULL>
+__device__ __forceinline__ unsigned tk_clock() {
+    unsigned c;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+    return c;
+}
+template <int TYPE, int NFULL, bool PROF>
 __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, const tk_yblock *ysm,
-                                           float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane) {
+                                           float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw) {
+    unsigned c_begin = 0, c_wait = 0, c_dot = 0, c_tail = 0, c_rounds = 0, c_t = 0, c_yp = 0;
+    if (PROF) c_begin = tk_clock();
     constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
     const fl_mv_args &A = ph.a;
     const int S = prm.S, kparts = ph.kparts, G = ph.G;
@@ -423,6 +432,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
     }
     const int n_past = (A.epi == FL_EPI_QKV) ? *A.n_past : 0;
     const int ntiles = sl.ntiles;
+    if (PROF) { c_t = tk_clock(); c_yp = c_t - c_begin; }
     int t = ((tg - (T0 & 3)) + 4) & 3;                 // first tile of this phase owned by the warp's tile group
     int T = T0 + t;
     const uint32_t rounds = tk_div((uint32_t)T, prm.s_magic, prm.s_shift);
@@ -432,6 +442,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
         int seg, unit0, nunits;
         tk_tile_of(sl, G, t, seg, unit0, nunits);
         fl_mbar_wait(bar0 + 8u * s, par);
+        if (PROF) { const unsigned c = tk_clock(); c_wait += c - c_t; c_t = c; c_rounds++; }
         if (g < nunits && !(prm.diag & 2)) {
             const uint8_t *tile = stage0 + (size_t)s * prm.slot_bytes;
             // default: pair rows are adjacent; swiglu: [nunits rows of w1][nunits rows of w3]
@@ -451,6 +462,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
             // producer before the reduction and the epilogue, whose latency then overlaps the refill
             __syncwarp();
             if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));
+            if (PROF) { const unsigned c = tk_clock(); c_dot += c - c_t; c_t = c; }
             float totA = fl_warp_sum(accA), totB = fl_warp_sum(accB);
             if (TYPE == FL_TYPE_Q4_1) {
                 totA = __fadd_rn(totA, fl_warp_sum(accmA));
@@ -481,6 +493,10 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
         }
         s += TK_TG;
         if (s >= S) { s -= S; par ^= 1u; }
+        if (PROF) { const unsigned c = tk_clock(); c_tail += c - c_t; c_t = c; }
+    }
+    if (PROF && lane == 0 && pw) {
+        pw[0] = c_yp; pw[1] = c_wait; pw[2] = c_dot; pw[3] = c_tail; pw[4] = c_rounds; pw[5] = tk_clock() - c_begin; pw[6] = (unsigned)ntiles; pw[7] = 0;
     }
 }
 
@@ -581,17 +597,18 @@ __device__ __forceinline__ void tk_attention_prefetch(const tk_phase &ph, int he
     }
 }
 
-template <int TYPE>
+template <int TYPE, bool PROF>
 __device__ __forceinline__ void tk_consume_dispatch(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, const tk_yblock *ysm,
-                                                    float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane) {
+                                                    float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw) {
     switch (ph.nfull) {
-        case 4: tk_consume<TYPE, 4>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane); break;
-        case 3: tk_consume<TYPE, 3>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane); break;
-        case 2: tk_consume<TYPE, 2>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane); break;
-        default: tk_consume<TYPE, 0>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane); break;
+        case 4: tk_consume<TYPE, 4, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw); break;
+        case 3: tk_consume<TYPE, 3, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw); break;
+        case 2: tk_consume<TYPE, 2, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw); break;
+        default: tk_consume<TYPE, 0, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw); break;
     }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = (uint64_t *)smem;
@@ -728,8 +745,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         tk_bar_consumers(15);                                    // activations, slice and next descriptor are in shared memory
         if (pr) pr[2] = tk_now();
         const tk_slice &sl = sl_sh;
-        if (ph.a.type == FL_TYPE_Q4_0) tk_consume_dispatch<FL_TYPE_Q4_0>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane);
-        else                           tk_consume_dispatch<FL_TYPE_Q4_1>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane);
+        unsigned *pw = (PROF && prm.prof2) ? prm.prof2 + (((size_t)pi * gridDim.x + blockIdx.x) * TK_CW + warp) * 8 : nullptr;
+        if (ph.a.type == FL_TYPE_Q4_0) tk_consume_dispatch<FL_TYPE_Q4_0, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw);
+        else                           tk_consume_dispatch<FL_TYPE_Q4_1, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw);
         T0 += sl.ntiles;
         if (pr) pr[3] = tk_now();
     }
@@ -742,7 +760,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
 struct fl_token_plan_impl {
     tk_phase *d_phases = nullptr;
     unsigned *d_bar = nullptr;
+    unsigned *h_err = nullptr;
     unsigned long long *d_prof = nullptr;
+    unsigned *d_prof2 = nullptr;
     tk_params prm;
     size_t smem = 0;
     int n_kernels = 0;
@@ -857,7 +877,7 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     int S = 16;
     size_t off = 0;
     for (;; S -= 4) {
-        if (S < 4) { delete pl; fl_set_error("token kernel: tiles of %zu bytes do not fit shared memory", slot); return -1; }
+        if (S < 4) { flk_token_plan_destroy(pl); fl_set_error("token kernel: tiles of %zu bytes do not fit shared memory", slot); return -1; }
         p.off_y = ((size_t)(2 * S) * 8 + 127) & ~(size_t)127;
         p.off_red = (p.off_y + max_y + 127) & ~(size_t)127;
         p.off_rowbuf = (p.off_red + 32 * sizeof(double) + 127) & ~(size_t)127;
@@ -884,6 +904,9 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     p.phases = pl->d_phases;
     p.grid_bar = pl->d_bar;
     FL_CUDA_OK(cudaMemset(pl->d_bar, 0, 256));
+    FL_CUDA_OK(cudaHostAlloc((void **)&pl->h_err, 64, cudaHostAllocMapped));
+    memset(pl->h_err, 0, 64);
+    FL_CUDA_OK(cudaHostGetDevicePointer((void **)&p.err, pl->h_err, 0));
     p.rank = 0; p.world = 1; p.xflags_local = nullptr;
     p.xrelease_sys = getenv("FASTLLAMA_B200_TP_RELEASE_SYS") ? 1 : 0;
     for (int r = 0; r < 8; r++) p.xflags_peer[r] = nullptr;
@@ -892,27 +915,34 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     if (uses_peers) {
         int rank = 0, world = 1;
         const void *const *peers = fl_shared_peers(&rank, &world);
-        if (!peers) { delete pl; fl_set_error("token kernel: steps read peer buffers but fl_comm_shared_alloc was never called"); return -1; }
+        if (!peers) { flk_token_plan_destroy(pl); fl_set_error("token kernel: steps read peer buffers but fl_comm_shared_alloc was never called"); return -1; }
         p.rank = rank; p.world = world;
         p.xflags_local = (unsigned *)peers[rank];
         for (int r = 0; r < world; r++) p.xflags_peer[r] = (unsigned *)peers[r];
         for (int i = 0; i < n_steps; i++)
             if (phases[i].kind == TK_PH_MATVEC && phases[i].a.n_xpeer > 0 && phases[i].a.n_xpeer != world - 1) {
-                delete pl; fl_set_error("token kernel: a step lists %d peers in a communicator of %d", phases[i].a.n_xpeer, world); return -1;
+                flk_token_plan_destroy(pl); fl_set_error("token kernel: a step lists %d peers in a communicator of %d", phases[i].a.n_xpeer, world); return -1;
             }
     }
     p.prof = nullptr;
+    p.prof2 = nullptr;
     if (getenv("FASTLLAMA_B200_TOKEN_PROF")) {
         FL_CUDA_OK(cudaMalloc((void **)&pl->d_prof, sizeof(unsigned long long) * 4 * (size_t)n_steps * sm));
         FL_CUDA_OK(cudaMemset(pl->d_prof, 0, sizeof(unsigned long long) * 4 * (size_t)n_steps * sm));
         p.prof = pl->d_prof;
+        const size_t n2 = (size_t)n_steps * sm * TK_CW * 8;
+        FL_CUDA_OK(cudaMalloc((void **)&pl->d_prof2, n2 * sizeof(unsigned)));
+        FL_CUDA_OK(cudaMemset(pl->d_prof2, 0, n2 * sizeof(unsigned)));
+        p.prof2 = pl->d_prof2;
     }
     cudaFuncAttributes fa;
-    FL_CUDA_OK(cudaFuncGetAttributes(&fa, k_decode_token));
-    FL_CUDA_OK(cudaFuncSetAttribute(k_decode_token, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    FL_CUDA_OK(cudaFuncGetAttributes(&fa, k_decode_token<false>));
+    FL_CUDA_OK(cudaFuncSetAttribute(k_decode_token<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    FL_CUDA_OK(cudaFuncGetAttributes(&fa, k_decode_token<true>));
+    FL_CUDA_OK(cudaFuncSetAttribute(k_decode_token<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     int per_sm = 0;
-    FL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_token, TK_THREADS, pl->smem));
-    if (per_sm < 1) { const size_t need = pl->smem; delete pl; fl_set_error("token kernel: one CTA per SM does not fit (smem %zu)", need); return -1; }
+    FL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_token<false>, TK_THREADS, pl->smem));
+    if (per_sm < 1) { const size_t need = pl->smem; flk_token_plan_destroy(pl); fl_set_error("token kernel: one CTA per SM does not fit (smem %zu)", need); return -1; }
     pl->n_kernels = sm;
     *out = pl;
     return 0;
@@ -923,7 +953,8 @@ int flk_token_plan_launch(cudaStream_t st, void *plan) {
     FL_CUDA_OK(cudaMemsetAsync(pl->d_bar, 0, 4, st));
     void *args[] = {(void *)&pl->prm};
     // cooperative launch: all 148 CTAs are guaranteed co-resident, which the grid barrier needs
-    FL_CUDA_OK(cudaLaunchCooperativeKernel((const void *)k_decode_token, dim3(pl->n_kernels), dim3(TK_THREADS), args, pl->smem, st));
+    const void *fn = pl->prm.prof2 ? (const void *)k_decode_token<true> : (const void *)k_decode_token<false>;
+    FL_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(pl->n_kernels), dim3(TK_THREADS), args, pl->smem, st));
     fl_count_launch();
     return 0;
 }
@@ -939,10 +970,19 @@ int flk_token_plan_profile(void *plan, unsigned long long *out, size_t max_words
     return 0;
 }
 
+int flk_token_plan_profile2(void *plan, unsigned *out, size_t max_words) {
+    fl_token_plan_impl *pl = (fl_token_plan_impl *)plan;
+    FL_REQUIRE(pl && pl->d_prof2, "token plan was created without FASTLLAMA_B200_TOKEN_PROF");
+    const size_t words = (size_t)pl->prm.n_phases * pl->n_kernels * TK_CW * 8;
+    FL_REQUIRE(max_words >= words, "profile buffer too small (%zu words needed)", words);
+    FL_CUDA_OK(cudaMemcpy(out, pl->d_prof2, words * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int flk_token_plan_error(void *plan) {
     fl_token_plan_impl *pl = (fl_token_plan_impl *)plan;
-    unsigned e[5] = {0, 0, 0, 0, 0};
-    if (pl && pl->d_bar && cudaMemcpy(e, pl->d_bar + 32, sizeof(e), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    if (!pl || !pl->h_err) return 0;
+    const volatile unsigned *e = pl->h_err;      // written by the kernel straight into host memory; the caller has synchronised the stream
     if (e[0])
         fl_set_error("token kernel barrier timeout: %s (code 0x%x), waited for %u, last saw %u, CTA %u, rank %d of %d", (e[1] & 0x200u) ? "peer flag" : "local grid counter",
                      e[1], e[2], e[3], e[4], pl->prm.rank, pl->prm.world);
@@ -954,7 +994,9 @@ int flk_token_plan_destroy(void *plan) {
     if (!pl) return 0;
     if (pl->d_phases) cudaFree(pl->d_phases);
     if (pl->d_bar) cudaFree(pl->d_bar);
+    if (pl->h_err) cudaFreeHost(pl->h_err);
     if (pl->d_prof) cudaFree(pl->d_prof);
+    if (pl->d_prof2) cudaFree(pl->d_prof2);
     delete pl;
     return 0;
 }

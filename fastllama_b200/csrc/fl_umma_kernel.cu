@@ -10,7 +10,7 @@
 // columns, so the kernel issues one MMA per k-block into a fresh TMEM accumulator (no accumulation across
 // blocks on the tensor core), and the epilogue warps pull each s32 tile out of TMEM (tcgen05.ld) and do the
 // reference's fp32 step  acc = fma(d_w * d_y, float(isum), acc)  on the CUDA cores while the next MMAs run.
-// Accumulators rotate through 256 TMEM columns.  Result: exactly the arithmetic of every other kernel of this
+// Accumulators rotate through the 512 TMEM columns in two groups of KG k-blocks (one synchronisation round per group).  Result: exactly the arithmetic of every other kernel of this
 // backend (exact block sums, fp32 scales, blocks added sequentially), so the same 2e-6 * sum|d q| budget.
 //
 // Warp roles (448 threads, one CTA per 128-row x NT-column output tile):
@@ -32,8 +32,6 @@
 #define UM_M 128
 #define UM_KC 4               // k-blocks per TMA stage
 #define UM_STAGES 4
-#define UM_ASLOTS 8           // unpacked A tiles in flight
-#define UM_TCOLS 256          // TMEM columns allocated (accumulator ring = UM_TCOLS / NT buffers)
 #define UM_UNPACK_WARPS 4
 #define UM_EPI_WARPS 8
 #define UM_THREADS ((UM_UNPACK_WARPS + UM_EPI_WARPS + 2) * 32)
@@ -86,9 +84,13 @@ struct um_params {
     int ntiles;                 // column tiles
 };
 
+// Synchronisation is per GROUP of KG k-blocks (KG * NT = at most 256 TMEM columns; two groups in flight = all 512 columns):
+// one a_full / acc_full / acc_empty / a_empty round per group instead of per k-block.
 template <int TYPE, int NT>
 struct um_layout {
     static constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
+    static constexpr int KG = (NT == 128) ? 2 : 4;                       // k-blocks per accumulator group
+    static constexpr int GPS = UM_KC / KG;                               // groups per TMA stage
     static constexpr int RAW_A = UM_M * UM_KC * BB;                      // TMA box: 128 rows x KC blocks
     static constexpr int RAW_B = UM_KC * NT * 32;
     static constexpr int RAW_S = UM_KC * NT * 4;
@@ -96,12 +98,13 @@ struct um_layout {
     static constexpr int STAGE = RAW_A + RAW_B + NSC * RAW_S;
     static constexpr int ATILE = UM_M * 32;                              // unpacked operand of one k-block
     static constexpr int ASLOT = ATILE + NSC * UM_M * 4;                 // + d_w [, m_w] per row
+    static constexpr int AGROUP = KG * ASLOT;
     static constexpr int OFF_A = UM_STAGES * STAGE;
-    static constexpr int OFF_BAR = OFF_A + UM_ASLOTS * ASLOT;
-    static constexpr int NBUF = UM_TCOLS / NT;
-    static constexpr int NBAR = 2 * UM_STAGES + 2 * UM_ASLOTS + 2 * NBUF;
+    static constexpr int OFF_BAR = OFF_A + 2 * AGROUP;
+    static constexpr int NBAR = 2 * UM_STAGES + 8;
     static constexpr int SMEM = OFF_BAR + NBAR * 8 + 16;
     static constexpr int CPT = NT / 2;                                   // columns per epilogue thread
+    static constexpr int TCOLS = 512;
 };
 
 // ---- activations: q8_0 rows -> the operand layout of the MMA ------------------------------------------
@@ -141,7 +144,7 @@ __global__ void k_umma_prep(const fl_block_q8_0 *__restrict__ Y, int N, int nb, 
 template <int TYPE, int NT>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_constant__ CUtensorMap tmap_w, const um_params prm) {
     using L = um_layout<TYPE, NT>;
-    constexpr int BB = L::BB;
+    constexpr int BB = L::BB, KG = L::KG, GPS = L::GPS;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_base_sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,31 +154,29 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
 
     const uint32_t sm0 = fl_smem_u32(smem);
     const uint32_t bar0 = sm0 + L::OFF_BAR;
-    // barrier map (8 bytes each)
+    // barrier map (8 bytes each); g = accumulator / operand group slot (0, 1)
     auto raw_full = [&](int s) { return bar0 + 8u * s; };
     auto raw_empty = [&](int s) { return bar0 + 8u * (UM_STAGES + s); };
-    auto a_full = [&](int t) { return bar0 + 8u * (2 * UM_STAGES + t); };
-    auto a_empty = [&](int t) { return bar0 + 8u * (2 * UM_STAGES + UM_ASLOTS + t); };
-    auto acc_full = [&](int b) { return bar0 + 8u * (2 * UM_STAGES + 2 * UM_ASLOTS + b); };
-    auto acc_empty = [&](int b) { return bar0 + 8u * (2 * UM_STAGES + 2 * UM_ASLOTS + L::NBUF + b); };
+    auto a_full = [&](int g) { return bar0 + 8u * (2 * UM_STAGES + g); };
+    auto a_empty = [&](int g) { return bar0 + 8u * (2 * UM_STAGES + 2 + g); };
+    auto acc_full = [&](int g) { return bar0 + 8u * (2 * UM_STAGES + 4 + g); };
+    auto acc_empty = [&](int g) { return bar0 + 8u * (2 * UM_STAGES + 6 + g); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < UM_STAGES; s++) {
             fl_mbar_init(raw_full(s), 1);
-            fl_mbar_init(raw_empty(s), UM_UNPACK_WARPS + 1 + UM_EPI_WARPS);
+            fl_mbar_init(raw_empty(s), UM_UNPACK_WARPS + UM_EPI_WARPS);     // the MMAs that read a stage's B tiles are complete before the epilogue lets go of it
         }
-        for (int t = 0; t < UM_ASLOTS; t++) {
-            fl_mbar_init(a_full(t), UM_UNPACK_WARPS);
-            fl_mbar_init(a_empty(t), 1 + UM_EPI_WARPS);
-        }
-        for (int b = 0; b < L::NBUF; b++) {
-            fl_mbar_init(acc_full(b), 1);
-            fl_mbar_init(acc_empty(b), UM_EPI_WARPS);
+        for (int g = 0; g < 2; g++) {
+            fl_mbar_init(a_full(g), UM_UNPACK_WARPS);
+            fl_mbar_init(a_empty(g), UM_EPI_WARPS);                         // same: the epilogue has waited for the group's MMAs
+            fl_mbar_init(acc_full(g), 1);
+            fl_mbar_init(acc_empty(g), UM_EPI_WARPS);
         }
         fl_mbar_fence_init();
     }
     if (warp == UM_UNPACK_WARPS + UM_EPI_WARPS + 1) {           // the MMA warp owns the TMEM allocation
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fl_smem_u32(&tmem_base_sh)), "r"((uint32_t)UM_TCOLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fl_smem_u32(&tmem_base_sh)), "r"((uint32_t)L::TCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     um_tc_fence_before();
@@ -200,32 +201,36 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
             __syncwarp();
             if (lane == 0) fl_mbar_arrive(raw_empty(s));          // the raw weights of this stage are in registers
 #pragma unroll
-            for (int kbi = 0; kbi < UM_KC; kbi++) {
-                const int kb = st * UM_KC + kbi;
-                const int t = kb % UM_ASLOTS;
-                um_wait(a_empty(t), ((uint32_t)(kb / UM_ASLOTS) & 1u) ^ 1u);
-                uint8_t *slot = smem + L::OFF_A + (size_t)t * L::ASLOT;
-                constexpr int WPB = BB / 4;                        // words per block
-                constexpr int QOFF = WPB - 4;                      // first qs word
-                uint32_t lo[4], hi[4];
+            for (int gs = 0; gs < GPS; gs++) {
+                const int gi = st * GPS + gs;                      // group index; slot gi & 1, use gi >> 1
+                const int g = gi & 1;
+                um_wait(a_empty(g), ((uint32_t)(gi >> 1) & 1u) ^ 1u);
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t q = w[kbi * WPB + QOFF + j];
-                    lo[j] = q & 0x0F0F0F0Fu;
-                    hi[j] = (q >> 4) & 0x0F0F0F0Fu;
-                    if (TYPE == FL_TYPE_Q4_0) {                    // (x - 8) as s8, per byte, no carries: (x + 0x78) ^ 0x80
-                        lo[j] = (lo[j] + 0x78787878u) ^ 0x80808080u;
-                        hi[j] = (hi[j] + 0x78787878u) ^ 0x80808080u;
+                for (int i = 0; i < KG; i++) {
+                    const int kbi = gs * KG + i;
+                    uint8_t *slot = smem + L::OFF_A + (size_t)g * L::AGROUP + (size_t)i * L::ASLOT;
+                    constexpr int WPB = BB / 4;                    // words per block
+                    constexpr int QOFF = WPB - 4;                  // first qs word
+                    uint32_t lo[4], hi[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t q = w[kbi * WPB + QOFF + j];
+                        lo[j] = q & 0x0F0F0F0Fu;
+                        hi[j] = (q >> 4) & 0x0F0F0F0Fu;
+                        if (TYPE == FL_TYPE_Q4_0) {                // (x - 8) as s8, per byte, no carries: (x + 0x78) ^ 0x80
+                            lo[j] = (lo[j] + 0x78787878u) ^ 0x80808080u;
+                            hi[j] = (hi[j] + 0x78787878u) ^ 0x80808080u;
+                        }
                     }
+                    *(uint4 *)(slot + (size_t)r * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);                 // k = 0..15: low nibbles = even elements
+                    *(uint4 *)(slot + (size_t)UM_M * 16 + (size_t)r * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);   // k = 16..31: high nibbles = odd elements
+                    float *dw = (float *)(slot + L::ATILE);
+                    dw[r] = __uint_as_float(w[kbi * WPB]);
+                    if (TYPE == FL_TYPE_Q4_1) dw[UM_M + r] = __uint_as_float(w[kbi * WPB + 1]);
                 }
-                *(uint4 *)(slot + (size_t)r * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);                 // k = 0..15: low nibbles = even elements
-                *(uint4 *)(slot + (size_t)UM_M * 16 + (size_t)r * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);   // k = 16..31: high nibbles = odd elements
-                float *dw = (float *)(slot + L::ATILE);
-                dw[r] = __uint_as_float(w[kbi * WPB]);
-                if (TYPE == FL_TYPE_Q4_1) dw[UM_M + r] = __uint_as_float(w[kbi * WPB + 1]);
                 um_fence_proxy_async();                            // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) fl_mbar_arrive(a_full(t));
+                if (lane == 0) fl_mbar_arrive(a_full(g));
             }
         }
     } else if (warp < UM_UNPACK_WARPS + UM_EPI_WARPS) {
@@ -234,65 +239,71 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
         const int quad = warp & 3;                                 // TMEM lanes 32 * quad .. + 31 are the ones this warp may touch
         const int half = ew >> 2;
         constexpr int CPT = L::CPT;
+        constexpr int CW = CPT < 32 ? CPT : 32;                    // columns per TMEM round trip (keeps v[] at 32 registers)
         const int row = quad * 32 + lane;
         const int c0 = half * CPT;
-        float acc[CPT], accm[(TYPE == FL_TYPE_Q4_1) ? CPT : 1];
+        float2 acc[CPT / 2], accm[(TYPE == FL_TYPE_Q4_1) ? CPT / 2 : 1];
 #pragma unroll
-        for (int j = 0; j < CPT; j++) acc[j] = 0.f;
+        for (int j = 0; j < CPT / 2; j++) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < ((TYPE == FL_TYPE_Q4_1) ? CPT : 1); j++) accm[j] = 0.f;
+        for (int j = 0; j < ((TYPE == FL_TYPE_Q4_1) ? CPT / 2 : 1); j++) accm[j] = make_float2(0.f, 0.f);
         for (int st = 0; st < nstages; st++) {
             const int s = st % UM_STAGES;
             um_wait(raw_full(s), (uint32_t)(st / UM_STAGES) & 1u);          // the stage's d_y / s_y have landed
             const float *dys = (const float *)(smem + (size_t)s * L::STAGE + L::RAW_A + L::RAW_B);
 #pragma unroll 1
-            for (int kbi = 0; kbi < UM_KC; kbi++) {
-                const int kb = st * UM_KC + kbi;
-                const int t = kb % UM_ASLOTS, b = kb % L::NBUF;
-                um_wait(acc_full(b), (uint32_t)(kb / L::NBUF) & 1u);
+            for (int gs = 0; gs < GPS; gs++) {
+                const int gi = st * GPS + gs;
+                const int g = gi & 1;
+                const uint32_t par = (uint32_t)(gi >> 1) & 1u;
+                um_wait(a_full(g), par);                           // acquire the unpack warps' d_w stores
+                um_wait(acc_full(g), par);
                 um_tc_fence_after();
-                // d_w (and the stage's d_y) first: their shared-memory latency overlaps the TMEM loads
-                um_wait(a_full(t), (uint32_t)(kb / UM_ASLOTS) & 1u);        // acquire the unpack warps' d_w stores
-                const float *dwp = (const float *)(smem + L::OFF_A + (size_t)t * L::ASLOT + L::ATILE);
-                const float dwm = dwp[row];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * NT + c0);
-                constexpr int CW = CPT < 32 ? CPT : 32;            // columns per TMEM round trip (keeps v[] at 32 registers)
 #pragma unroll
-                for (int ch = 0; ch < CPT / CW; ch++) {
-                    uint32_t v[CW];
+                for (int i = 0; i < KG; i++) {
+                    const int kbi = gs * KG + i;
+                    const float *dwp = (const float *)(smem + L::OFF_A + (size_t)g * L::AGROUP + (size_t)i * L::ASLOT + L::ATILE);
+                    const float dwm = dwp[row];
+                    const float2 dw2 = make_float2(dwm, dwm);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 256 + i * NT + c0);
 #pragma unroll
-                    for (int c = 0; c < CW / 16; c++) UM_LD16(taddr + (uint32_t)(ch * CW + 16 * c), (&v[16 * c]));
-                    um_wait_ld();
-                    if (ch == CPT / CW - 1) {                      // every column of the buffer is in registers: hand it back
-                        um_tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) fl_mbar_arrive(acc_empty(b));
+                    for (int ch = 0; ch < CPT / CW; ch++) {
+                        uint32_t v[CW];
+#pragma unroll
+                        for (int c = 0; c < CW / 16; c++) UM_LD16(taddr + (uint32_t)(ch * CW + 16 * c), (&v[16 * c]));
+                        um_wait_ld();
+                        if (i == KG - 1 && ch == CPT / CW - 1) {   // every column of the group's accumulators is in registers: hand them back
+                            um_tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) fl_mbar_arrive(acc_empty(g));
+                        }
+                        const float4 *dy4 = (const float4 *)(dys + kbi * NT + c0 + ch * CW);
+#pragma unroll
+                        for (int j = 0; j < CW / 4; j++) {
+                            const float4 d4 = dy4[j];
+                            // packed fp32 (FMUL2 / FFMA2): element-wise IEEE round-to-nearest, the same results as the scalar forms
+                            const float2 s01 = __fmul2_rn(dw2, make_float2(d4.x, d4.y)), s23 = __fmul2_rn(dw2, make_float2(d4.z, d4.w));
+                            const float2 i01 = make_float2(__int2float_rn((int)v[4 * j + 0]), __int2float_rn((int)v[4 * j + 1]));
+                            const float2 i23 = make_float2(__int2float_rn((int)v[4 * j + 2]), __int2float_rn((int)v[4 * j + 3]));
+                            float2 *a = acc + (ch * CW + 4 * j) / 2;
+                            a[0] = __ffma2_rn(s01, i01, a[0]);
+                            a[1] = __ffma2_rn(s23, i23, a[1]);
+                        }
                     }
-                    const float4 *dy4 = (const float4 *)(dys + kbi * NT + c0 + ch * CW);
+                    if (TYPE == FL_TYPE_Q4_1) {
+                        const float mwm = dwp[UM_M + row];
+                        const float2 mw2 = make_float2(mwm, mwm);
+                        const float4 *sy4 = (const float4 *)(dys + UM_KC * NT + kbi * NT + c0);
 #pragma unroll
-                    for (int j = 0; j < CW / 4; j++) {
-                        const float4 d4 = dy4[j];
-                        float *a = acc + ch * CW + 4 * j;
-                        a[0] = __fmaf_rn(__fmul_rn(dwm, d4.x), __int2float_rn((int)v[4 * j + 0]), a[0]);
-                        a[1] = __fmaf_rn(__fmul_rn(dwm, d4.y), __int2float_rn((int)v[4 * j + 1]), a[1]);
-                        a[2] = __fmaf_rn(__fmul_rn(dwm, d4.z), __int2float_rn((int)v[4 * j + 2]), a[2]);
-                        a[3] = __fmaf_rn(__fmul_rn(dwm, d4.w), __int2float_rn((int)v[4 * j + 3]), a[3]);
-                    }
-                }
-                if (TYPE == FL_TYPE_Q4_1) {
-                    const float mwm = dwp[UM_M + row];
-                    const float4 *sy4 = (const float4 *)(dys + UM_KC * NT + kbi * NT + c0);
-#pragma unroll
-                    for (int j = 0; j < CPT / 4; j++) {
-                        const float4 s4 = sy4[j];
-                        accm[4 * j + 0] = __fmaf_rn(mwm, s4.x, accm[4 * j + 0]);
-                        accm[4 * j + 1] = __fmaf_rn(mwm, s4.y, accm[4 * j + 1]);
-                        accm[4 * j + 2] = __fmaf_rn(mwm, s4.z, accm[4 * j + 2]);
-                        accm[4 * j + 3] = __fmaf_rn(mwm, s4.w, accm[4 * j + 3]);
+                        for (int j = 0; j < CPT / 4; j++) {
+                            const float4 s4 = sy4[j];
+                            accm[2 * j] = __ffma2_rn(mw2, make_float2(s4.x, s4.y), accm[2 * j]);
+                            accm[2 * j + 1] = __ffma2_rn(mw2, make_float2(s4.z, s4.w), accm[2 * j + 1]);
+                        }
                     }
                 }
                 __syncwarp();
-                if (lane == 0) fl_mbar_arrive(a_empty(t));         // d_w / m_w of the slot have been read
+                if (lane == 0) fl_mbar_arrive(a_empty(g));         // d_w / m_w of the group have been read (and its MMAs are long complete)
             }
             __syncwarp();
             if (lane == 0) fl_mbar_arrive(raw_empty(s));           // d_y / s_y of the stage have been read
@@ -303,7 +314,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
             for (int j = 0; j < CPT; j++) {
                 const int col = n0 + c0 + j;
                 if (col < prm.N) {
-                    const float o = (TYPE == FL_TYPE_Q4_1) ? __fadd_rn(acc[j], accm[j]) : acc[j];
+                    const float a = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
+                    float o = a;
+                    if (TYPE == FL_TYPE_Q4_1) o = __fadd_rn(a, (j & 1) ? accm[j / 2].y : accm[j / 2].x);
                     prm.dst[(size_t)col * prm.dst_row_stride + (size_t)(m0 + row)] = o;
                 }
             }
@@ -335,18 +348,21 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
                 const int s = st % UM_STAGES;
                 um_wait(raw_full(s), (uint32_t)(st / UM_STAGES) & 1u);
                 const uint32_t bstage = sm0 + (uint32_t)(s * L::STAGE + L::RAW_A);
-                for (int kbi = 0; kbi < UM_KC; kbi++) {
-                    const int kb = st * UM_KC + kbi;
-                    const int t = kb % UM_ASLOTS, b = kb % L::NBUF;
-                    um_wait(a_full(t), (uint32_t)(kb / UM_ASLOTS) & 1u);
-                    um_wait(acc_empty(b), ((uint32_t)(kb / L::NBUF) & 1u) ^ 1u);
+                for (int gs = 0; gs < GPS; gs++) {
+                    const int gi = st * GPS + gs;
+                    const int g = gi & 1;
+                    const uint32_t par = (uint32_t)(gi >> 1) & 1u;
+                    um_wait(a_full(g), par);
+                    um_wait(acc_empty(g), par ^ 1u);
                     um_tc_fence_after();
-                    const uint64_t adesc = um_smem_desc(sm0 + (uint32_t)(L::OFF_A + t * L::ASLOT), UM_M * 16, 128);
-                    const uint64_t bdesc = um_smem_desc(bstage + (uint32_t)(kbi * NT * 32), NT * 16, 128);
-                    um_mma_i8(tmem_base + (uint32_t)(b * NT), adesc, bdesc, idesc);
-                    um_commit(acc_full(b));
-                    um_commit(a_empty(t));
-                    if (kbi == UM_KC - 1) um_commit(raw_empty(s));
+#pragma unroll
+                    for (int i = 0; i < KG; i++) {
+                        const int kbi = gs * KG + i;
+                        const uint64_t adesc = um_smem_desc(sm0 + (uint32_t)(L::OFF_A + g * L::AGROUP + i * L::ASLOT), UM_M * 16, 128);
+                        const uint64_t bdesc = um_smem_desc(bstage + (uint32_t)(kbi * NT * 32), NT * 16, 128);
+                        um_mma_i8(tmem_base + (uint32_t)(g * 256 + i * NT), adesc, bdesc, idesc);
+                    }
+                    um_commit(acc_full(g));                        // arrives when the group's MMAs (and everything before them) are complete
                 }
             }
         }
@@ -355,7 +371,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
     __syncthreads();
     if (warp == UM_UNPACK_WARPS + UM_EPI_WARPS + 1) {
         um_tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)UM_TCOLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L::TCOLS) : "memory");
     }
 }
 

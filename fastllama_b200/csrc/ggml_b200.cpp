@@ -592,6 +592,11 @@ int g_last_mirror = -1;
 bool g_verbose = false;
 
 struct Stats { uint64_t n_evals = 0; double last_us = 0, total_us = 0; uint64_t graph_replays = 0; } g_stats;
+// host-side time of the fused decode path, microseconds summed over decode steps (ggml_b200_get_host_profile):
+// [0] steps, [1] graph match, [2] scalars + launch issue, [3] waiting for the device + result copies, [4] between two graph computes (caller:
+// sampling, graph building, callbacks)
+double g_hostprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int64_t g_last_exit_us = 0;
 bool g_profile = false;
 int g_decode_mode = 0;          // see ggml_b200_decode_mode()
 bool g_tp_kv_sharded = false;   // tensor-parallel decode steps have written only this rank's heads into the KV cache
@@ -773,6 +778,9 @@ extern "C" void ggml_b200_release_all(void) {
 // how the last single-token eval ran: 0 = node-by-node executor, 1 = fused plan with one kernel per matrix group,
 // 2 = fused plan as one persistent kernel per token (fl_token_kernel.cu)
 extern "C" int ggml_b200_decode_mode(void) { return g_decode_mode; }
+extern "C" void ggml_b200_get_host_profile(double out[8], int reset) {
+    for (int i = 0; i < 8; i++) { out[i] = g_hostprof[i]; if (reset) g_hostprof[i] = 0; }
+}
 extern "C" void ggml_b200_set_profile(int on) {
     ensure_backend();
     if (!g_pev0) { g_pev0 = fl_event_create(); g_pev1 = fl_event_create(); }
@@ -817,6 +825,14 @@ void need_f32(const ggml_tensor *t, const char *what) {
 void exec_mul_mat(const ggml_tensor *node, const ggml_context *cctx) {
     const ggml_tensor *a = node->src0, *b = node->src1;
     need_f32(b, "mul_mat src1");
+    if (a->type == GGML_TYPE_F32 && a->ne[2] == 1 && a->ne[3] == 1 && b->ne[2] == 1 && b->ne[3] == 1 && a->ne[0] <= 256 && a->nb[0] == 4 && b->nb[0] == 4 &&
+        node->nb[0] == 4) {
+        // two plain f32 matrices with a short contraction (B*A of a LoRA adapter, reference lib/llama.cpp:867): the reference's exact
+        // summation order, so that the merged weights re-quantise to the reference's bytes
+        FLC(fl_dev_mul_mat_f32_ref((const float *)dev_ptr(a->data, nbytes_of(a), cctx), a->nb[1] / 4, (int)a->ne[1], (const float *)dev_ptr(b->data, nbytes_of(b), cctx),
+                                   b->nb[1] / 4, (int)b->ne[1], (int)a->ne[0], (float *)dev_ptr(node->data, nbytes_of(node), cctx), node->nb[1] / 4));
+        return;
+    }
     if (a->type == GGML_TYPE_F32) {
         fl_view va = view_of(a, cctx), vb = view_of(b, cctx), vd = view_of(node, cctx);
         FLC(fl_dev_mul_mat_f32(&va, &vb, &vd));
@@ -885,6 +901,17 @@ void exec_node(ggml_tensor *node, const ggml_context *cctx) {
             return;
         }
         case GGML_OP_ADD: case GGML_OP_MUL: {
+            if (node->op == GGML_OP_ADD && (node->src0->type == GGML_TYPE_Q4_0 || node->src0->type == GGML_TYPE_Q4_1)) {
+                // W (+)= f32 matrix: the LoRA merge, ggml_compute_forward_add_q_f32 (reference lib/ggml.c:6414-6520)
+                const ggml_tensor *a = node->src0, *b = node->src1;
+                need_f32(b, "add (quantised + f32) src1");
+                B200_ASSERT(node->type == a->type && same_shape(a, b) && same_shape(a, node) && a->ne[2] == 1 && a->ne[3] == 1);
+                B200_ASSERT(a->nb[0] == k_tsize[a->type] && b->nb[0] == sizeof(float) && node->nb[0] == k_tsize[a->type] && a->ne[0] % 32 == 0);
+                FLC(fl_dev_add_q_f32((int)a->type, dev_ptr(a->data, nbytes_of(a), cctx), a->nb[1], (int)a->ne[1], (int)a->ne[0],
+                                     (const float *)dev_ptr(b->data, nbytes_of(b), cctx), b->nb[1] / sizeof(float), dev_ptr(node->data, nbytes_of(node), cctx), node->nb[1]));
+                packed_shards_clear();          // tensor-parallel K-slices packed from the old weights are stale now
+                return;
+            }
             need_f32(node->src0, k_opname[node->op]); need_f32(node->src1, k_opname[node->op]);
             fl_view a = view_of(node->src0, cctx), b = view_of(node->src1, cctx), d = view_of(node, cctx);
             if (node->op == GGML_OP_ADD) FLC(fl_dev_add(&a, &b, &d)); else FLC(fl_dev_mul(&a, &b, &d));
@@ -998,6 +1025,8 @@ struct DecodeState {
     void *token_plan = nullptr;   // the persistent per-token kernel's program (single-GPU decode)
     int *d_npast = nullptr;
     int *h_scalars = nullptr;   // pinned: [0] n_past, [1] token id
+    char *h_out = nullptr;      // pinned staging of the step's results (logits, then the embeddings row): the caller's arena is pageable
+    size_t h_out_cap = 0;
     bool enabled = true, use_graph = true, use_token_kernel = true, inited = false;
     bool tp_kv_sharded = false;   // tensor-parallel decode steps have written only this rank's heads into the KV cache ...
     int tp_first_pos = 0, tp_end_pos = 0;   // ... for positions [tp_first_pos, tp_end_pos)
@@ -1361,7 +1390,9 @@ bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, 
     }
     if (!D.enabled) return false;
     DecodePlan P;
+    const int64_t t_m0 = ggml_time_us();
     if (!match_decode(ctx, g, P, D.ws, O)) return false;
+    g_hostprof[1] += (double)(ggml_time_us() - t_m0);
     if (!D.d_npast) {
         D.d_npast = (int *)fl_dev_malloc(64);
         D.h_scalars = (int *)fl_host_alloc_pinned(64);
@@ -1467,7 +1498,9 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
     g->work_size = 0;
 
     DecodeOutputs dout;
+    const int64_t t_in = ggml_time_us();
     if (run_decode_plan(ctx, g, dout, ev0, ev1)) {
+        const int64_t t_issued = ggml_time_us();
         mark_device_write(dout.kv_host, ctx);          // the step appended one position to the KV cache on the device
         if (fl_comm_world() > 1) {
             const int pos = g_dec.h_scalars[0];                   // n_past of this step = the position it wrote
@@ -1477,12 +1510,28 @@ extern "C" void ggml_graph_compute(struct ggml_context *ctx, struct ggml_cgraph 
         }
         // fused decode step: the two results the caller reads (reference lib/llama.cpp:476-489) come
         // straight from the private workspace
-        FLC(fl_d2h(dout.logits_host, g_dec.ws.logits, dout.logits_bytes));
-        FLC(fl_d2h(dout.emb_host, g_dec.ws.emb, dout.emb_bytes));
+        // through pinned staging: a device-to-host copy into the caller's pageable arena would be staged by the driver, synchronously
+        if (g_dec.h_out_cap < dout.logits_bytes + dout.emb_bytes) {
+            if (g_dec.h_out) FLC(fl_host_free_pinned(g_dec.h_out));
+            g_dec.h_out_cap = dout.logits_bytes + dout.emb_bytes;
+            g_dec.h_out = (char *)fl_host_alloc_pinned(g_dec.h_out_cap);
+            if (!g_dec.h_out) B200_FAIL("decode result staging: %s", fl_last_error());
+        }
+        FLC(fl_d2h(g_dec.h_out, g_dec.ws.logits, dout.logits_bytes));
+        FLC(fl_d2h(g_dec.h_out + dout.logits_bytes, g_dec.ws.emb, dout.emb_bytes));
         FLC(fl_sync());
+        memcpy(dout.logits_host, g_dec.h_out, dout.logits_bytes);
+        memcpy(dout.emb_host, g_dec.h_out + dout.logits_bytes, dout.emb_bytes);
         if (g_dec.token_plan && fl_token_plan_error(g_dec.token_plan))
             B200_FAIL("%s", fl_last_error());
+        const int64_t t_out = ggml_time_us();
+        g_hostprof[0] += 1;
+        g_hostprof[2] += (double)(t_issued - t_in);          // includes [1]
+        g_hostprof[3] += (double)(t_out - t_issued);
+        if (g_last_exit_us) g_hostprof[4] += (double)(t_in - g_last_exit_us);
+        g_last_exit_us = t_out;
     } else {
+        g_last_exit_us = 0;
         g_decode_mode = 0;
         // Leafs.  Weights / KV cache live in persistent arenas (uploaded once by dev_ptr).  Constants the
         // host wrote into the compute arena while building the graph are uploaded per graph, but only
@@ -1595,14 +1644,15 @@ extern "C" size_t ggml_quantize_chunk(enum ggml_type type, const float *src, voi
 namespace {
 template <int T> void hook_dequantize(const void *x, float *y, int k) { ensure_backend(); FLC(fl_dequantize_rows_q4(T, x, y, k, 1)); }
 template <int T> void hook_quantize_ref(const float *x, void *y, int k) { ensure_backend(); FLC(fl_quantize_rows_q4(T, x, y, k, 1)); }
+template <int T> void hook_quantize_simd(const float *x, void *y, int k) { ensure_backend(); FLC(fl_quantize_rows_q4_simd(T, x, y, k, 1)); }
 void hook_quantize_q8(const float *x, void *y, int k) { ensure_backend(); FLC(fl_quantize_row_q8_0(x, y, k)); }
 template <int T> void hook_vec_dot(const int n, float *s, const void *x, const void *y) { ensure_backend(); FLC(fl_vec_dot_q4_q8(T, n, s, x, y)); }
 }  // namespace
 
 extern "C" quantize_fns_t ggml_internal_get_quantize_fn(size_t i) {
     quantize_fns_t f = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (i == GGML_TYPE_Q4_0) f = {hook_dequantize<FL_Q4_0>, hook_quantize_ref<FL_Q4_0>, hook_quantize_ref<FL_Q4_0>, hook_quantize_q8, hook_vec_dot<FL_Q4_0>};
-    if (i == GGML_TYPE_Q4_1) f = {hook_dequantize<FL_Q4_1>, hook_quantize_ref<FL_Q4_1>, hook_quantize_ref<FL_Q4_1>, hook_quantize_q8, hook_vec_dot<FL_Q4_1>};
+    if (i == GGML_TYPE_Q4_0) f = {hook_dequantize<FL_Q4_0>, hook_quantize_simd<FL_Q4_0>, hook_quantize_ref<FL_Q4_0>, hook_quantize_q8, hook_vec_dot<FL_Q4_0>};
+    if (i == GGML_TYPE_Q4_1) f = {hook_dequantize<FL_Q4_1>, hook_quantize_simd<FL_Q4_1>, hook_quantize_ref<FL_Q4_1>, hook_quantize_q8, hook_vec_dot<FL_Q4_1>};
     if (i == GGML_TYPE_Q8_0) f.quantize_row_q = f.quantize_row_q_reference = f.quantize_row_q_dot = hook_quantize_q8;
     return f;
 }

@@ -80,6 +80,10 @@ SIGNATURES = {
     "fl_dev_mul_mat_q": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]),
     "fl_dev_dequantize_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "fl_dev_quantize_q4": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "fl_quantize_rows_q4_simd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "fl_dev_quantize_q4_simd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "fl_dev_add_q_f32": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "fl_dev_mul_mat_f32_ref": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "fl_dev_time_mul_mat_q": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_float)]),
     "fl_dev_time_mul_mat_q_rot": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_float)]),
     "fl_dev_rms_norm": (C.c_int, [_VP, _VP]),
@@ -101,6 +105,7 @@ SIGNATURES = {
     "fl_token_plan_error": (C.c_int, [C.c_void_p]),
     "fl_comm_shared_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "fl_token_plan_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
+    "fl_token_plan_profile2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "fl_dev_attn_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]),
     "fl_comm_unique_id": (C.c_int, [C.c_void_p]),
     "fl_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),

@@ -54,6 +54,11 @@ int fl_quantize_rows_q8_0(const float *x, void *y, int k, int nrows);
  * ggml_quantize_q4_0/_q4_1 :12122-12166).  Bit-exact. */
 int fl_quantize_rows_q4(int type, const float *x, void *y, int k, int nrows);
 
+/* quantize_row_q4_0 / quantize_row_q4_1 == quantize_fns[type].quantize_row_q, the SIMD quantisers (lib/ggml.c:666-915 AVX2 branch
+ * :739-803, :958-1079 AVX2 branch :965-1038): q4_0 uses id = 7/amax and round-half-even, q4_1 round-half-even.  This is what
+ * ggml_compute_forward_add_q_f32 (:6516-6518) re-quantises a LoRA-merged row with.  Bit-exact with the reference's x86 build. */
+int fl_quantize_rows_q4_simd(int type, const float *x, void *y, int k, int nrows);
+
 /* dequantize_row_q4_0 / _q4_1 == quantize_fns[type].dequantize_row_q (lib/ggml.c:1443-1665).
  * Bit-exact (q4_1 uses a fused multiply-add like the reference's GNU-mode x86 build). */
 int fl_dequantize_rows_q4(int type, const void *x, float *y, int k, int nrows);
@@ -96,6 +101,17 @@ int fl_dev_mul_mat_q(int type, const void *W, size_t w_row_stride_bytes, int M, 
 int fl_dev_dequantize_rows(int type, const void *W, size_t w_row_stride_bytes, int K, const int32_t *ids_dev,
                            int n_ids, float *dst, size_t dst_row_stride_elems);
 int fl_dev_quantize_q4(int type, const float *x, void *y, int k, int nrows);
+
+/* ---- attach_lora / detach_lora on the device (reference lib/llama.cpp:697-944) ----
+ * fl_dev_quantize_q4_simd: device-resident fl_quantize_rows_q4_simd.
+ * fl_dev_add_q_f32: ggml_compute_forward_add_q_f32 (lib/ggml.c:6414-6520): row r of dst = quantize_row_q(dequantize_row_q(row r of W) +
+ *   row r of X); dst may be W itself (ggml_add_inplace).  Bit-exact.
+ * fl_dev_mul_mat_f32_ref: ggml_mul_mat of two f32 matrices with ggml_vec_dot_f32's summation order of the AVX2 + FMA build
+ *   (lib/ggml.c:2295-2325): out[j * ldo + i] = dot(A row i, B row j), K elements.  Bit-exact; meant for small K (B*A of a LoRA adapter). */
+int fl_dev_quantize_q4_simd(int type, const float *x, void *y, int k, int nrows);
+int fl_dev_add_q_f32(int type, const void *W, size_t w_row_stride_bytes, int M, int K, const float *X, size_t x_row_stride_elems, void *dst,
+                     size_t dst_row_stride_bytes);
+int fl_dev_mul_mat_f32_ref(const float *A, size_t lda_elems, int Ma, const float *B, size_t ldb_elems, int Mb, int K, float *out, size_t ldo_elems);
 
 /* Timing helpers for bench.py / profiling (CUDA events on the library stream, mean ms per launch
  * over `iters` back-to-back launches).  W may hold n_copies identical copies of the matrix,
@@ -199,6 +215,9 @@ int fl_token_plan_error(void *plan);
 /* tooling: with FASTLLAMA_B200_TOKEN_PROF set at create time, the last launch's per-step, per-CTA timestamps
  * [n_steps][n_ctas][4] in ns: step entered, grid barrier passed, activations quantised, tiles consumed */
 int fl_token_plan_profile(void *plan, unsigned long long *out, size_t max_words, int *n_ctas);
+/* tooling: per step, CTA and consumer warp [n_steps][n_ctas][16][8] SM-clock cycle counts of the last launch's tile loops:
+ * activation fetch, waiting for weight tiles, dot products, reduction + epilogue, rounds, total, tiles of the CTA, 0 */
+int fl_token_plan_profile2(void *plan, unsigned *out, size_t max_words);
 
 /* ---- tensor parallelism: one process per GPU, NCCL (dlopen'ed libnccl.so.2) on the
  * library stream; collectives are captured into the decode CUDA graph.  fl_comm_unique_id is called on

@@ -212,6 +212,9 @@ int ggml_b200_get_kernel_stats(struct ggml_b200_kernel_stat *out, int max_entrie
 /* how the last single-token eval ran: 0 = node-by-node executor, 1 = fused plan, one kernel per matrix group,
  * 2 = fused plan as one persistent kernel per token (fl_token_kernel.cu) */
 int ggml_b200_decode_mode(void);
+/* host-side time of the fused decode path in microseconds, summed over decode steps: [0] steps, [1] graph match, [2] match + scalars +
+ * launch issue, [3] waiting for the device + result copies, [4] time spent in the caller between two decode steps */
+void ggml_b200_get_host_profile(double out[8], int reset);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,69 @@ def llama_toy(ref):
         print("wrote", path, os.path.getsize(path), "bytes")
 
 
+LORA_SHAPE = dict(k=256, m=24, ranks=(8, 16, 40, 64))
+
+
+def lora_inputs(rng, m, k):
+    """Rows for the SIMD re-quantisers and the LoRA merge: random, ties after scaling (amax = 7 -> id = 1: x.5 values),
+    all-zero and constant blocks, a block whose merged values change sign."""
+    w = (rng.standard_normal((m, k)) * 0.05).astype(np.float32)
+    w[0] = 0.0
+    w[1, :32] = 0.125
+    w[2, :32] = (np.arange(32, dtype=np.float32) - 15.5) * 0.4375        # amax = 6.78..: scaled values land near .5 ties
+    w[3, :32] = np.linspace(-7.0, 7.0, 32, dtype=np.float32)
+    w[3, 0:8] = [0.5, 1.5, 2.5, 3.5, -0.5, -1.5, -2.5, -3.5]
+    w[4, :32] = np.linspace(0.0, 15.0, 32, dtype=np.float32)
+    w[4, 1:5] = [0.5, 1.5, 2.5, 14.5]                                      # min 0, max 15: d = id = 1, exact ties
+    return w
+
+
+def lora_ops():
+    """Outputs of the reference LIBRARY for the ops of attach_lora / detach_lora (lib/llama.cpp:697-944): the SIMD row
+    quantisers (quantize_fns[].quantize_row_q), f32 x f32 mul_mat (B*A) and add_inplace of an f32 matrix into a quantised one."""
+    from oracle.pyoracle import REF_GGML_SO
+    from tests import ggml_api as G
+
+    ref = RefGgml()
+    g = G.Ggml(REF_GGML_SO)
+    rng = np.random.default_rng(77)
+    k, m = LORA_SHAPE["k"], LORA_SHAPE["m"]
+    w = lora_inputs(rng, m, k)
+    out = {"w": w}
+    for name, t in (("q4_0", GGML_TYPE_Q4_0), ("q4_1", GGML_TYPE_Q4_1)):
+        out[f"{name}_simd"] = ref.quantize_q4_simd(w, t)
+        base = ref.quantize_q4_reference(w, t)
+        out[f"{name}_base"] = base
+    for r in LORA_SHAPE["ranks"]:
+        a = (rng.standard_normal((k, r)) * 0.3).astype(np.float32)      # loraA: ne = [r, k]
+        b = (rng.standard_normal((m, r)) * 0.3).astype(np.float32)      # loraB: ne = [r, m]
+        out[f"A{r}"], out[f"B{r}"] = a, b
+        for name, t in (("q4_0", G.Q4_0), ("q4_1", G.Q4_1)):
+            ar = g.context(64 << 20)
+            ta = g.new_tensor_2d(ar.ctx, G.F32, r, k); ar.set(ta, a)
+            tb = g.new_tensor_2d(ar.ctx, G.F32, r, m); ar.set(tb, b)
+            tw = g.new_tensor_2d(ar.ctx, t, k, m); ar.set(tw, out[f"{name}_base"])
+            ba = g.mul_mat(ar.ctx, ta, tb)
+            res = g.add_inplace(ar.ctx, tw, ba)
+            gf = G.new_graph()
+            g.build_forward_expand(gf, res)
+            g.graph_compute(ar.ctx, gf)
+            if name == "q4_0":
+                out[f"BA{r}"] = ar.numpy(ba).reshape(m, k).copy()
+            out[f"{name}_merged{r}"] = ar.numpy(tw).reshape(m, -1).copy()
+            # detach: W - BA (scale by -1, add in place)
+            neg = g.scale(ar.ctx, ba, g.new_f32(ar.ctx, -1.0))
+            res2 = g.add_inplace(ar.ctx, tw, neg)
+            gf2 = G.new_graph()
+            g.build_forward_expand(gf2, res2)
+            g.graph_compute(ar.ctx, gf2)
+            out[f"{name}_detached{r}"] = ar.numpy(tw).reshape(m, -1).copy()
+            ar.free()
+    path = os.path.join(OUT, "lora_ops.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     build_oracle()
     ref = RefGgml()
@@ -88,6 +151,7 @@ def main():
         np.savez_compressed(path, **out)
         print("wrote", path, os.path.getsize(path), "bytes")
     llama_toy(ref)
+    lora_ops()
 
 
 if __name__ == "__main__":

@@ -73,6 +73,13 @@ class Oracle:
         L.orc_get_rows_q.restype = C.c_int
         L.orc_quantize_q4.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.orc_quantize_q4.restype = C.c_size_t
+        for name in ("orc_quantize_row_q4_0_simd", "orc_quantize_row_q4_1_simd"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+            getattr(L, name).restype = None
+        L.orc_vec_dot_f32.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_vec_dot_f32.restype = C.c_float
+        L.orc_add_q_f32.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_add_q_f32.restype = C.c_int
 
     # --- row functions -------------------------------------------------------------
     def quantize_q8_0(self, x: np.ndarray, scalar: bool = False) -> np.ndarray:
@@ -92,6 +99,38 @@ class Oracle:
         out = np.empty(n // QK * BLOCK_BYTES[ggml_type], dtype=np.uint8)
         self.lib.orc_quantize_q4(ggml_type, _fptr(x), _fptr(out), n, k)
         return out.reshape(x.shape[:-1] + (k // QK * BLOCK_BYTES[ggml_type],))
+
+    def quantize_q4_simd(self, x: np.ndarray, ggml_type: int) -> np.ndarray:
+        """quantize_fns[type].quantize_row_q: the AVX2 quantisers (lib/ggml.c:739-803, :965-1038), not the _reference ones."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        k = x.shape[-1]
+        rows = x.reshape(-1, k)
+        bb = BLOCK_BYTES[ggml_type]
+        out = np.empty((rows.shape[0], k // QK * bb), dtype=np.uint8)
+        fn = self.lib.orc_quantize_row_q4_0_simd if ggml_type == GGML_TYPE_Q4_0 else self.lib.orc_quantize_row_q4_1_simd
+        for r in range(rows.shape[0]):
+            fn(_fptr(rows[r]), _fptr(out[r]), k)
+        return out.reshape(x.shape[:-1] + (k // QK * bb,))
+
+    def mul_mat_f32(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        """ggml_mul_mat of two f32 matrices: a [Ma, K], b [Mb, K] -> [Mb, Ma] with out[j][i] = vec_dot_f32(a[i], b[j])
+        in the AVX2 build's summation order (lib/ggml.c:2295-2325)."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        out = np.empty((b.shape[0], a.shape[0]), dtype=np.float32)
+        for j in range(b.shape[0]):
+            for i in range(a.shape[0]):
+                out[j, i] = self.lib.orc_vec_dot_f32(a.shape[1], _fptr(a[i]), _fptr(b[j]))
+        return out
+
+    def add_q_f32(self, w: np.ndarray, x: np.ndarray, ggml_type: int) -> np.ndarray:
+        """ggml_compute_forward_add_q_f32 (lib/ggml.c:6414-6520): dequantise, add, re-quantise with the SIMD quantiser."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        rows, k = x.shape
+        w = np.ascontiguousarray(w, dtype=np.uint8).reshape(rows, -1)
+        out = np.empty_like(w)
+        assert self.lib.orc_add_q_f32(ggml_type, rows, k, _fptr(w), _fptr(x), _fptr(out)) == 0
+        return out
 
     def dequantize_q4(self, w: np.ndarray, ggml_type: int, k: int) -> np.ndarray:
         w = np.ascontiguousarray(w, dtype=np.uint8).reshape(-1, k // QK * BLOCK_BYTES[ggml_type])
@@ -177,6 +216,17 @@ class RefGgml:
         bb = BLOCK_BYTES[ggml_type]
         out = np.empty((rows.shape[0], k // QK * bb), dtype=np.uint8)
         fn = self.fns[ggml_type].quantize_row_q_reference
+        for r in range(rows.shape[0]):
+            fn(_fptr(rows[r]), _fptr(out[r]), k)
+        return out.reshape(x.shape[:-1] + (k // QK * bb,))
+
+    def quantize_q4_simd(self, x: np.ndarray, ggml_type: int) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        k = x.shape[-1]
+        rows = x.reshape(-1, k)
+        bb = BLOCK_BYTES[ggml_type]
+        out = np.empty((rows.shape[0], k // QK * bb), dtype=np.uint8)
+        fn = self.fns[ggml_type].quantize_row_q
         for r in range(rows.shape[0]):
             fn(_fptr(rows[r]), _fptr(out[r]), k)
         return out.reshape(x.shape[:-1] + (k // QK * bb,))

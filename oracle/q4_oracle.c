@@ -154,6 +154,97 @@ void orc_quantize_row_q4_1(const float *x, void *vy, int k) {
     }
 }
 
+/* ------------------------------------------------------------------------- */
+/* The SIMD weight quantizers = quantize_fns[type].quantize_row_q, AVX2 branches */
+/*   quantize_row_q4_0 lib/ggml.c:739-803, quantize_row_q4_1 lib/ggml.c:965-1038  */
+/* (what ggml_compute_forward_add_q_f32 :6516-6518 re-quantises a LoRA-merged row */
+/* with).  Differences from the _reference variants above:                       */
+/*   q4_0: id = 7 / amax (not 1 / d), round-half-EVEN (_mm256_round_ps NEAREST), */
+/*         saturating packs to int8, then + 8                                    */
+/*   q4_1: id = d ? 1 / d : 0 as in the reference, but round-half-EVEN and the   */
+/*         saturating int8 packs                                                 */
+/* packNibbles (:473-487) keeps the low 4 bits of every byte pair.               */
+/* ------------------------------------------------------------------------- */
+static inline int orc_sat_i8(int v) { return v > 127 ? 127 : (v < -128 ? -128 : v); }
+
+void orc_quantize_row_q4_0_simd(const float *x, void *vy, int k) {
+    orc_block_q4_0 *y = (orc_block_q4_0 *)vy;
+    const int nb = k / ORC_QK;
+    for (int i = 0; i < nb; i++) {
+        const float *xb = x + i * ORC_QK;
+        float amax = 0.0f;
+        for (int l = 0; l < ORC_QK; l++) {
+            const float a = fabsf(xb[l]);
+            if (a > amax) amax = a;
+        }
+        const float d = amax / 7.0f;
+        const float id = (amax != 0.0f) ? 7.0f / amax : 0.0f;
+        y[i].d = d;
+        uint8_t q[ORC_QK];
+        for (int l = 0; l < ORC_QK; l++) {
+            const int v = orc_sat_i8((int)nearbyintf(xb[l] * id));   /* |x * id| <= 7 (+ rounding), never saturates in practice */
+            q[l] = (uint8_t)((int8_t)(v + 8));                       /* _mm256_add_epi8: wraps modulo 256 */
+        }
+        for (int l = 0; l < ORC_QK; l += 2) y[i].qs[l / 2] = (uint8_t)((q[l] & 0x0F) | ((q[l + 1] & 0x0F) << 4));
+    }
+}
+
+void orc_quantize_row_q4_1_simd(const float *x, void *vy, int k) {
+    orc_block_q4_1 *y = (orc_block_q4_1 *)vy;
+    const int nb = k / ORC_QK;
+    for (int i = 0; i < nb; i++) {
+        const float *xb = x + i * ORC_QK;
+        /* _mm256_max_ps / _mm256_min_ps over finite inputs = plain max / min */
+        float mn = xb[0], mx = xb[0];
+        for (int l = 1; l < ORC_QK; l++) {
+            if (xb[l] < mn) mn = xb[l];
+            if (xb[l] > mx) mx = xb[l];
+        }
+        const float d = (mx - mn) / 15.0f;
+        const float id = d ? 1.0f / d : 0.0f;
+        y[i].m = mn;
+        y[i].d = d;
+        uint8_t q[ORC_QK];
+        for (int l = 0; l < ORC_QK; l++) q[l] = (uint8_t)orc_sat_i8((int)nearbyintf((xb[l] - mn) * id));
+        for (int l = 0; l < ORC_QK; l += 2) y[i].qs[l / 2] = (uint8_t)((q[l] & 0x0F) | ((q[l + 1] & 0x0F) << 4));
+    }
+}
+
+/* ggml_vec_dot_f32 (lib/ggml.c:2295-2325) as the AVX2 + FMA build computes it: 4 accumulators of 8 lanes over steps of 32    */
+/* (GGML_F32_STEP 32, GGML_F32_EPR 8), the GGML_F32x8_REDUCE tree (:1943-1958), then the leftovers as a rounded product     */
+/* plus a rounded add per element (what the compiled reference does; no fma there).                                           */
+float orc_vec_dot_f32(int n, const float *x, const float *y) {
+    float sum[4][8];
+    for (int j = 0; j < 4; j++) for (int l = 0; l < 8; l++) sum[j][l] = 0.0f;
+    const int np = n & ~31;
+    for (int i = 0; i < np; i += 32)
+        for (int j = 0; j < 4; j++)
+            for (int l = 0; l < 8; l++) sum[j][l] = fmaf(x[i + 8 * j + l], y[i + 8 * j + l], sum[j][l]);
+    float t[8];
+    for (int l = 0; l < 8; l++) t[l] = (sum[0][l] + sum[1][l]) + (sum[2][l] + sum[3][l]);
+    float sumf = ((t[0] + t[4]) + (t[1] + t[5])) + ((t[2] + t[6]) + (t[3] + t[7]));
+    for (int i = np; i < n; i++) { const float p = x[i] * y[i]; sumf = sumf + p; }   /* the leftover loop is vectorised by gcc into mul + add, not an fma (pinned by tests/golden/lora_ops.npz) */
+    return sumf;
+}
+
+/* ggml_compute_forward_add_q_f32 (lib/ggml.c:6414-6520): dst row = quantize_row_q(dequantize_row_q(src0 row) + src1 row) */
+void orc_dequantize_row_q4_0(const void *vx, float *y, int k);
+void orc_dequantize_row_q4_1(const void *vx, float *y, int k);
+int orc_add_q_f32(int ggml_type, int rows, int k, const void *src0, const float *src1, void *dst) {
+    const int bb = orc_block_bytes(ggml_type);
+    if (bb < 0 || ggml_type == 6 || k % ORC_QK) return -1;
+    float *w = (float *)malloc(sizeof(float) * (size_t)k);
+    for (int r = 0; r < rows; r++) {
+        const uint8_t *s0 = (const uint8_t *)src0 + (size_t)r * (k / ORC_QK) * bb;
+        uint8_t *d = (uint8_t *)dst + (size_t)r * (k / ORC_QK) * bb;
+        if (ggml_type == 2) orc_dequantize_row_q4_0(s0, w, k); else orc_dequantize_row_q4_1(s0, w, k);
+        for (int i = 0; i < k; i++) w[i] += src1[(size_t)r * k + i];      /* ggml_vec_acc_f32, :2286 */
+        if (ggml_type == 2) orc_quantize_row_q4_0_simd(w, d, k); else orc_quantize_row_q4_1_simd(w, d, k);
+    }
+    free(w);
+    return 0;
+}
+
 /* ggml_quantize_q4_0 / _q4_1 (lib/ggml.c:12122-12166): n floats, rows of k,
  * returns bytes written.  The histogram side effect is not reproduced. */
 size_t orc_quantize_q4(int ggml_type, const float *src, void *dst, int n, int k) {

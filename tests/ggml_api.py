@@ -64,6 +64,7 @@ _SIGS = {
     "ggml_nbytes": (C.c_size_t, [TP]),
     "ggml_nelements": (C.c_int64, [TP]),
     "ggml_add": (TP, [CTX, TP, TP]),
+    "ggml_add_inplace": (TP, [CTX, TP, TP]),
     "ggml_mul": (TP, [CTX, TP, TP]),
     "ggml_repeat": (TP, [CTX, TP, TP]),
     "ggml_silu": (TP, [CTX, TP]),

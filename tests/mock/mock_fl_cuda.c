@@ -24,6 +24,10 @@ void orc_dequantize_row_q4_0(const void *vx, float *y, int k);
 void orc_dequantize_row_q4_1(const void *vx, float *y, int k);
 void orc_vec_dot_q4_0_q8_0(int n, float *s, const void *vx, const void *vy);
 void orc_vec_dot_q4_1_q8_0(int n, float *s, const void *vx, const void *vy);
+void orc_quantize_row_q4_0_simd(const float *x, void *vy, int k);
+void orc_quantize_row_q4_1_simd(const float *x, void *vy, int k);
+float orc_vec_dot_f32(int n, const float *x, const float *y);
+int orc_add_q_f32(int ggml_type, int rows, int k, const void *src0, const float *src1, void *dst);
 
 static int g_ready = 0;
 static uint64_t g_launches = 0;
@@ -128,6 +132,28 @@ int fl_dev_time_mul_mat_q_rot(int t, const void *W, size_t a, int M, int K, cons
 int fl_quantize_rows_q8_0(const float *x, void *y, int k, int n) { return fl_dev_quantize_q8_0(x, (size_t)k * 4, y, k, n); }
 int fl_quantize_row_q8_0(const float *x, void *y, int k) { return fl_quantize_rows_q8_0(x, y, k, 1); }
 int fl_quantize_rows_q4(int t, const float *x, void *y, int k, int n) { return fl_dev_quantize_q4(t, x, y, k, n); }
+int fl_dev_quantize_q4_simd(int type, const float *x, void *y, int k, int nrows) {
+    g_launches++;
+    const int bb = type == 2 ? 20 : 24;
+    for (int r = 0; r < nrows; r++) {
+        if (type == 2) orc_quantize_row_q4_0_simd(x + (size_t)r * k, (char *)y + (size_t)r * (k / 32) * bb, k);
+        else orc_quantize_row_q4_1_simd(x + (size_t)r * k, (char *)y + (size_t)r * (k / 32) * bb, k);
+    }
+    return 0;
+}
+int fl_quantize_rows_q4_simd(int t, const float *x, void *y, int k, int n) { return fl_dev_quantize_q4_simd(t, x, y, k, n); }
+int fl_dev_add_q_f32(int type, const void *W, size_t wrs, int M, int K, const float *X, size_t xrs, void *dst, size_t drs) {
+    g_launches++;
+    for (int r = 0; r < M; r++)
+        if (orc_add_q_f32(type, 1, K, (const char *)W + (size_t)r * wrs, X + (size_t)r * xrs, (char *)dst + (size_t)r * drs)) return -1;
+    return 0;
+}
+int fl_dev_mul_mat_f32_ref(const float *A, size_t lda, int Ma, const float *B, size_t ldb, int Mb, int K, float *out, size_t ldo) {
+    g_launches++;
+    for (int j = 0; j < Mb; j++)
+        for (int i = 0; i < Ma; i++) out[(size_t)j * ldo + i] = orc_vec_dot_f32(K, A + (size_t)i * lda, B + (size_t)j * ldb);
+    return 0;
+}
 int fl_dequantize_rows_q4(int t, const void *x, float *y, int k, int n) { return fl_dev_dequantize_rows(t, x, (size_t)(k / 32) * (t == 2 ? 20 : 24), k, NULL, n, y, (size_t)k); }
 int fl_vec_dot_q4_q8(int t, int n, float *s, const void *x, const void *y) { if (t == 2) orc_vec_dot_q4_0_q8_0(n, s, x, y); else orc_vec_dot_q4_1_q8_0(n, s, x, y); return 0; }
 int fl_mul_mat_q_f32(int t, int M, int K, int N, const void *W, const float *X, float *dst) {
@@ -370,6 +396,7 @@ int fl_token_plan_create(const fl_token_step *steps, int n, void **out) {
 }
 int fl_token_plan_launch(void *plan) { mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_PLAN; o.plan = plan; if (g_capture) record(&o); else run_op(&o); return 0; }
 int fl_token_plan_profile(void *plan, unsigned long long *out, size_t n, int *c) { (void)plan; (void)out; (void)n; *c = 0; return -1; }
+int fl_token_plan_profile2(void *plan, unsigned *out, size_t n) { (void)plan; (void)out; (void)n; return -1; }
 int fl_token_plan_error(void *plan) { (void)plan; return 0; }
 
 int fl_token_plan_destroy(void *plan) { mock_graph *pg = plan; if (pg) { free(pg->ops); free(pg); } return 0; }

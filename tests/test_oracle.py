@@ -90,3 +90,50 @@ def test_live_reference_rowfns(oracle, ref, k):
         assert np.array_equal(oracle.dequantize_q4(wq, t, k), ref.dequantize_q4(wq, t, k))
         a, b = oracle.mul_mat_q(wq, x[:3], t), ref.mul_mat_q(wq, x[:3], t)
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ---- the ops of attach_lora / detach_lora and the SIMD quantiser slot (row a2) ---------------------
+GOLDEN_LORA = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "lora_ops.npz")
+
+
+@pytest.fixture(scope="module")
+def lora_golden():
+    return np.load(GOLDEN_LORA)
+
+
+@pytest.mark.parametrize("name,t", TYPES)
+def test_simd_quantizers_match_golden(oracle, lora_golden, name, t):
+    """quantize_fns[type].quantize_row_q = the AVX2 quantisers (lib/ggml.c:739-803, :965-1038): id = 7/amax and round-half-even,
+    NOT the _reference arithmetic -- the fixture holds rows on which the two differ."""
+    g = lora_golden
+    got = oracle.quantize_q4_simd(g["w"], t)
+    assert np.array_equal(got, g[f"{name}_simd"])
+    assert not np.array_equal(got, g[f"{name}_base"]), "fixture must separate the SIMD and the _reference quantiser"
+
+
+@pytest.mark.parametrize("r", [8, 16, 40, 64])
+def test_f32_mul_mat_order_matches_golden(oracle, lora_golden, r):
+    """B*A of a LoRA adapter: ggml_vec_dot_f32 in the AVX2 + FMA build's order (32-wide SIMD part, tree reduce, fma leftovers)."""
+    g = lora_golden
+    got = oracle.mul_mat_f32(g[f"A{r}"], g[f"B{r}"])
+    assert np.array_equal(got.view(np.uint32), g[f"BA{r}"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name,t", TYPES)
+@pytest.mark.parametrize("r", [8, 64])
+def test_lora_merge_and_detach_match_golden(oracle, lora_golden, name, t, r):
+    g = lora_golden
+    ba = oracle.mul_mat_f32(g[f"A{r}"], g[f"B{r}"])
+    merged = oracle.add_q_f32(g[f"{name}_base"], ba, t)
+    assert np.array_equal(merged, g[f"{name}_merged{r}"])
+    detached = oracle.add_q_f32(merged, -ba, t)
+    assert np.array_equal(detached, g[f"{name}_detached{r}"])
+
+
+@pytest.mark.parametrize("name,t", TYPES)
+def test_simd_quantizers_match_live_reference(oracle, ref, name, t):
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((64, 512)) * rng.choice([1e-3, 1.0, 50.0], size=(64, 1))).astype(np.float32)
+    x[0] = 0
+    x[1, :32] = np.round(x[1, :32] * 2) / 2
+    assert np.array_equal(oracle.quantize_q4_simd(x, t), ref.quantize_q4_simd(x, t))

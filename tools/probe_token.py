@@ -127,4 +127,17 @@ print("\nmean over layers (us):")
 for nm, rows in agg.items():
     r = np.array(rows).mean(axis=0)
     print(f"{nm:>5}: barrier {r[0]:5.2f} (max {r[1]:5.2f})  prologue {r[2]:5.2f} (max {r[3]:5.2f})  tiles {r[4]:5.2f} (max {r[5]:5.2f})  span {r[6]:6.2f}")
+# per-warp cycle breakdown of the tile loops (PROF kernel)
+p2 = np.zeros((len(steps), 148, 16, 8), dtype=np.uint32)
+fl.check(fl.lib.fl_token_plan_profile2(plan, p2.ctypes.data, p2.size))
+print("\nper consumer warp, mean over CTAs and warps (SM cycles): activation fetch | waiting for tiles | dots | reduce+epilogue+loop | rounds | total | tiles per CTA")
+agg2 = {}
+for i, nm in enumerate(names):
+    if nm == "attn":
+        continue
+    agg2.setdefault(nm, []).append(p2[i].reshape(-1, 8).astype(np.float64).mean(axis=0))
+for nm, rows in agg2.items():
+    r = np.array(rows).mean(axis=0)
+    per = (r[2] / r[4], r[3] / r[4]) if r[4] else (0, 0)
+    print(f"{nm:>5}: yfetch {r[0]:7.0f}  wait {r[1]:7.0f}  dots {r[2]:7.0f}  tail {r[3]:7.0f}  rounds {r[4]:5.2f}  total {r[5]:7.0f}  tiles/CTA {r[6]:5.1f}   per round: dots {per[0]:6.0f} tail {per[1]:6.0f}")
 fl.check(fl.lib.fl_token_plan_destroy(plan))
