@@ -198,12 +198,21 @@ def _ref_worker_main(spec_path: str):
         np.save(spec["logits_out"], np.stack(logits))
     n_timed = spec.get("n_timed", 0)
     if n_timed:
-        stamps, seq = [], []
-        m.generate(lambda s: (stamps.append(time.perf_counter()), seq.append(s)), num_tokens=spec.get("n_warm", 2) + n_timed, **greedy)
-        stamps = stamps[spec.get("n_warm", 2):]
-        n = len(stamps) - 1
+        # one generate(1) call per token so that a hopeless thread setting can be abandoned after `budget_s` (the bridge evaluates the
+        # pending token and samples the next one per call, exactly as inside one long generate())
+        budget = float(spec.get("budget_s", 60.0))
+        for _ in range(spec.get("n_warm", 2)):
+            m.generate(lambda s: None, num_tokens=1, **greedy)
+        t_begin = time.perf_counter()
+        n = 0
+        while n < n_timed:
+            m.generate(lambda s: None, num_tokens=1, **greedy)
+            n += 1
+            if time.perf_counter() - t_begin > budget:
+                break
+        dt = time.perf_counter() - t_begin
         res["timed_tokens"] = n
-        res["tps"] = n / (stamps[-1] - stamps[0]) if n > 0 else 0.0
+        res["tps"] = n / dt if dt > 0 else 0.0
     m.close()
     json.dump(res, open(spec["out"], "w"))
 
@@ -224,21 +233,23 @@ def cpu_reference(path: str, size: str, wtype_name: str, steps: int, n_parity: i
     thread pool often peaks below nproc), then the sample proper at the best setting."""
     ncpu = os.cpu_count() or 1
     env = os.environ.get("FASTLLAMA_BENCH_CPU_THREADS")
-    cands = [int(x) for x in env.split(",")] if env else sorted({min(ncpu, 32), max(1, ncpu // 2), ncpu})
+    cands = [int(x) for x in env.split(",")] if env else sorted({t for t in (8, 16, 32, max(1, ncpu // 2), ncpu) if t <= ncpu})
     sweep = {}
     if len(cands) > 1:
-        for t in cands:
-            r = run_ref_worker({"path": path, "threads": t, "prompt": PROMPT, "n_timed": 6, "n_warm": 2})
+        for t in cands:                                   # ascending; every setting is bounded to ~10 s
+            r = run_ref_worker({"path": path, "threads": t, "prompt": PROMPT, "n_timed": 6, "n_warm": 1, "budget_s": 8.0})
             sweep[t] = r["tps"]
             log(f"[bench] reference CPU path, {t} threads: {r['tps']:.2f} tokens/s")
+            if r["tps"] < 0.5 * max(sweep.values()):
+                break                                     # past the knee of the spin-barrier thread pool: more threads only get slower
         best = max(sweep, key=sweep.get)
     else:
         best = cands[0]
-    r = run_ref_worker({"path": path, "threads": best, "prompt": PROMPT, "n_parity": n_parity, "logits_out": logits_out, "n_timed": steps, "n_warm": 2})
+    r = run_ref_worker({"path": path, "threads": best, "prompt": PROMPT, "n_parity": n_parity, "logits_out": logits_out, "n_timed": steps, "n_warm": 2, "budget_s": 60.0})
     sweep[best] = max(sweep.get(best, 0.0), r["tps"])
     cb = {"value": r["tps"], "unit": "tokens/s", "cores": best, "kind": "reference",
           "sample": f"{r['timed_tokens']} greedy decode tokens of the same synthetic {size} {wtype_name} file after 2 warm-up tokens, reference pyfastllama "
-                    f"(oracle/_ref, AVX2 build) with num_threads={best}, the best of the sweep {{{', '.join(f'{k}: {v:.2f}' for k, v in sorted(sweep.items()))}}} tokens/s "
+                    f"(oracle/_ref, AVX2 build) with num_threads={best}, the best of the sweep {{{', '.join(f'{k}: {v:.2f}' for k, v in sorted(sweep.items()))}}} tokens/s (threads: rate; ascending, stopped past the knee) "
                     f"on {ncpu} host cpus; child process, mmap load {r['load_s']:.1f}s not counted",
           "thread_sweep": {str(k): v for k, v in sorted(sweep.items())}, "host_cpus": ncpu}
     return {"cpu_baseline": cb, "parity_tokens": r.get("parity_tokens", [])}
@@ -506,7 +517,7 @@ def main():
         steps = min(args.steps, int(os.environ.get("FASTLLAMA_BENCH_REF_MAX_STEPS", "24")))
         if args.mode == "ingest":
             ncpu = os.cpu_count() or 1
-            r = run_ref_worker({"path": path, "threads": max(1, ncpu // 2), "n_batch": 128, "ingest_chars": 128 + 1 - 2}, timeout=1800)
+            r = run_ref_worker({"path": path, "threads": min(32, ncpu), "n_batch": 128, "ingest_chars": 128 + 1 - 2}, timeout=1800)
             value = 128 / r["ingest_s"]
             cb = {"value": value, "unit": "tokens/s", "cores": r["threads"], "kind": "reference",
                   "sample": f"ONE 128-token eval of the prompt-ingest path (prompt of 129 tokens, the reference evaluates the first chunk inside ingest()), num_threads={r['threads']} of {ncpu}"}

@@ -581,7 +581,7 @@ int flk_mul_mat_q(cudaStream_t st, int type, const void *W, size_t wrs, int M, i
     // 5 / 6 / 7 = column tiles of 32 / 64 / 128; legacy mma.sync path (fl_mma_kernel.cu): impl 3 and small N; tiny N stays on the plain kernel
     if (impl >= 4 && impl <= 7) return flk_mul_mat_q_umma(st, type, W, wrs, M, K, Yq8, N, dst, drs, impl == 4 ? 0 : 16 << (impl - 4));
     {
-        static const int umma_auto = getenv("FASTLLAMA_B200_UMMA") ? atoi(getenv("FASTLLAMA_B200_UMMA")) : 0;
+        static const int umma_auto = getenv("FASTLLAMA_B200_UMMA") ? atoi(getenv("FASTLLAMA_B200_UMMA")) : 1;     // FASTLLAMA_B200_UMMA=0: legacy mma.sync path
         if (impl == 0 && umma_auto && N >= 16 && flk_mul_mat_q_umma_supported(type, W, wrs, M, K, N)) return flk_mul_mat_q_umma(st, type, W, wrs, M, K, Yq8, N, dst, drs, 0);
     }
     if (impl == 3 || (impl == 0 && N >= 4)) return flk_mul_mat_q_mma(st, type, W, wrs, M, K, Yq8, N, dst, drs);

@@ -33,7 +33,10 @@
 #define TK_TG 4                  // tile groups; ring slot s always belongs to group s % 4 (S is a multiple of 4)
 #define TK_WPG 4                 // warps per tile group = kparts * G
 #define TK_GMAX 4                // units (row pairs) per tile at most
-#define TK_THREADS (TK_NT + 32)
+#define TK_PW 4                  // producer warps: warp TK_CW + g streams the tiles of tile group g (its own slots, its own pace)
+#define TK_THREADS (TK_NT + 32 * TK_PW)
+#define TK_REGS_CONSUMER 120      // setmaxnreg: the producer warpgroup hands its registers to the four consumer warpgroups
+#define TK_REGS_PRODUCER 24
 
 enum { TK_PH_MATVEC = 0, TK_PH_ATTN = 1 };
 
@@ -104,13 +107,17 @@ __device__ __forceinline__ void tk_wait_ge(const unsigned *p, unsigned target, b
 // with ld.global.cg only.  xe != 0 extends it across the tensor-parallel GPUs: once the local grid has arrived, CTA 0
 // raises this rank's flag in every peer's memory (sys-scope release over NVLink) and every CTA waits for all peers' flags.
 __device__ __forceinline__ void tk_grid_sync(const tk_params &prm, unsigned target, unsigned xe) {
-    tk_bar_consumers(13);
-    if (threadIdx.x == 0) {
-        unsigned *err = prm.err;
-        // The phase that just ended may have stored to peer memory.  A gpu-scope release per CTA is enough: CTA 0 acquires all of
-        // them and then fences at sys scope before raising the flag, and causality order composes across the two scopes.
+    // Arrival is per WARP (the counter target is 16 per CTA): a warp that has finished its rows publishes them and arrives without
+    // waiting for the slower warps of its CTA.  __syncwarp orders the other lanes' stores before lane 0's release.
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        // The phase that just ended may have stored to peer memory.  A gpu-scope release is enough: CTA 0 acquires all of them and
+        // then fences at sys scope before raising the flag, and causality order composes across the two scopes.
         if (xe && prm.xrelease_sys) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prm.grid_bar) : "memory");
         else asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(prm.grid_bar) : "memory");
+    }
+    if (threadIdx.x == 0) {
+        unsigned *err = prm.err;
         tk_wait_ge(prm.grid_bar, target, false, err, 0x100u);
         if (xe) {
             if (blockIdx.x == 0) {
@@ -170,7 +177,7 @@ struct __align__(16) tk_yblock {
     int c, pad;                  // c = -8 * sum(q) (the q4_0 offset); q4_1 consumers ignore it
 };
 
-// A thread quantises E consecutive values (E = 8: four lanes per block, E = 16: two lanes per block).
+// A thread quantises E consecutive values (E = 8: four lanes per block, E = 16: two lanes per block, E = 32: a whole block).
 template <int E>
 __device__ __forceinline__ void tk_load_vals(const float4 *p4, int u, float v[E], bool cg) {
 #pragma unroll
@@ -213,7 +220,7 @@ __device__ __forceinline__ void tk_quant(const float v[E], int u, bool valid, tk
 #pragma unroll
     for (int k = 0; k < E; k += 2) { m0 = fmaxf(m0, fabsf(v[k])); m1 = fmaxf(m1, fabsf(v[k + 1])); }
     float amax = fmaxf(m0, m1);
-    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    if (E <= 16) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
     if (E == 8) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
     const float d = __fdiv_rn(amax, 127.f);
     const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
@@ -225,7 +232,7 @@ __device__ __forceinline__ void tk_quant(const float v[E], int u, bool valid, tk
         s0 += q[k]; s1 += q[k + 1];
     }
     int sum = s0 + s1;
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    if (E <= 16) sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     if (E == 8) sum += __shfl_xor_sync(0xffffffffu, sum, 2);
     if (valid) {
         constexpr int NW = E / 8;                    // 8-element groups of the block this thread owns
@@ -342,8 +349,10 @@ __device__ __forceinline__ void tk_prologue(const fl_mv_args &A, int K, tk_ybloc
         else tk_prologue_norm<0>(A, K, ysm, red, warp, lane, tid);
     } else if (nu8 <= TK_NT) {
         tk_prologue_nonorm<8>(A, K, ysm, warp, tid);          // short vectors: latency matters, spread over all threads
-    } else {
+    } else if ((K >> 4) <= TK_NT) {
         tk_prologue_nonorm<16>(A, K, ysm, warp, tid);         // long vectors: issue slots matter
+    } else {
+        tk_prologue_nonorm<32>(A, K, ysm, warp, tid);         // K > 8192 (w2): one thread per block, no shuffles, one L2 round trip
     }
 }
 
@@ -463,10 +472,32 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
             __syncwarp();
             if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));
             if (PROF) { const unsigned c = tk_clock(); c_dot += c - c_t; c_t = c; }
-            float totA = fl_warp_sum(accA), totB = fl_warp_sum(accB);
-            if (TYPE == FL_TYPE_Q4_1) {
-                totA = __fadd_rn(totA, fl_warp_sum(accmA));
-                totB = __fadd_rn(totB, fl_warp_sum(accmB));
+            // Both (all four) sums in ONE butterfly: after the xor-16 step lanes 0-15 carry row A and lanes 16-31 row B (q4_1: the xor-8
+            // step splits each half again into the d and the m sums).  Every lane adds exactly the operands fl_warp_sum would add at that
+            // lane, so lane 0 / 16 (/ 8 / 24) end with the bits of fl_warp_sum(accA) / (accB) (/ accmA / accmB).
+            float totA, totB;
+            {
+                const bool up = (lane & 16) != 0;
+                float x = up ? accB : accA, y = up ? accA : accB;
+                x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, y, 16));
+                if (TYPE == FL_TYPE_Q4_1) {
+                    float xm = up ? accmB : accmA, ym = up ? accmA : accmB;
+                    xm = __fadd_rn(xm, __shfl_xor_sync(0xffffffffu, ym, 16));
+                    const bool up8 = (lane & 8) != 0;
+                    const float keep = up8 ? xm : x, give = up8 ? x : xm;
+                    x = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, give, 8));
+                } else {
+                    x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, 8));
+                }
+                x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, 4));
+                x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, 2));
+                x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, 1));
+                totA = x;
+                totB = __shfl_sync(0xffffffffu, x, 16);
+                if (TYPE == FL_TYPE_Q4_1) {
+                    totA = __fadd_rn(totA, __shfl_sync(0xffffffffu, x, 8));
+                    totB = __fadd_rn(totB, __shfl_sync(0xffffffffu, x, 24));
+                }
             }
             if (lane == 0) {
                 const int u = unit0 + g;
@@ -627,9 +658,13 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = fl_smem_u32(bars);
 
-    if (warp == TK_CW) {
-        // ------------------------------ producer: all phases, as far ahead as the ring allows ------------------------------
-        if (lane == 0) {
+    if (warp >= TK_CW) {
+        // ------------------------------ producers: warp TK_CW + g streams the tiles of tile group g, all phases, as far ahead as its slots allow ------
+        // One producer per tile group: the groups drift apart by a tile or two (epilogues differ), and a single in-order producer
+        // made every group wait for the slowest one's slot.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TK_REGS_PRODUCER));
+        const int pg = warp - TK_CW;
+        if (pg == 0 && lane == 0) {
             for (int s = 0; s < S; s++) {
                 fl_mbar_init(bar0 + 8u * s, 1);
                 fl_mbar_init(bar0 + 8u * (S + s), TK_WPG);
@@ -637,15 +672,13 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
             fl_mbar_fence_init();
         }
         __syncwarp();
-        asm volatile("bar.arrive 14, %0;" ::"r"(TK_NT + 32) : "memory");
+        asm volatile("bar.sync 14, %0;" ::"r"(TK_THREADS) : "memory");          // barriers initialised (consumers and the other producers wait here too)
         if (lane == 0) {
             const uint64_t pol = fl_policy_evict_first();
-            int s = 0;
-            uint32_t par = 1;
+            int T0 = 0;                                                          // global index of the phase's first tile (this CTA)
             for (int pi = 0; pi < prm.n_phases; pi++) {
-                // The descriptor lives in global memory and L1 is invalidated by every grid barrier of the consumers, so
-                // everything the tile loop needs is pulled into registers once per phase (one L2 round trip, hidden
-                // because the producer runs ahead).
+                // The descriptor lives in global memory; everything the tile loop needs is pulled into registers once per phase
+                // (one L2 round trip, hidden because the producer runs ahead).
                 const tk_phase *gp = prm.phases + pi;
                 if (__ldg(&gp->kind) != TK_PH_MATVEC) continue;
                 const int G = __ldg(&gp->G), lgG = __ldg(&gp->lgG), swiglu = __ldg(&gp->swiglu);
@@ -655,24 +688,12 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
                 const uint8_t *w1 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[1]);
                 const uint8_t *w2 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[2]);
                 const tk_slice sl = tk_make_slice_u(m0, m1, m2, lgG, prm.grid_magic, prm.grid_shift);
-                // Optional: ask L2 for this CTA's whole share of the phase now (the producer gets here while the consumers are
-                // still about a ring's worth of tiles inside the previous phase).
-                if (prm.l2_prefetch) {
-                    // l2_prefetch = how many tiles beyond the ring to request (the ring itself covers the first S)
-                    for (int t = S; t < min(sl.ntiles, S + prm.l2_prefetch); t++) {
-                        int seg, unit0, nunits;
-                        tk_tile_of(sl, G, t, seg, unit0, nunits);
-                        if (swiglu) {
-                            const uint32_t half = (uint32_t)nunits * row_bytes;
-                            fl_bulk_prefetch_l2(w0 + (size_t)unit0 * row_bytes, half);
-                            fl_bulk_prefetch_l2(w1 + (size_t)unit0 * row_bytes, half);
-                        } else {
-                            const uint8_t *w = seg == 0 ? w0 : seg == 1 ? w1 : w2;
-                            fl_bulk_prefetch_l2(w + (size_t)(2 * unit0) * row_bytes, 2u * (uint32_t)nunits * row_bytes);
-                        }
-                    }
-                }
-                for (int t = 0; t < sl.ntiles; t++) {
+                int t = ((pg - (T0 & 3)) + 4) & 3;                               // first tile of this phase that belongs to group pg
+                int T = T0 + t;
+                const uint32_t rounds = tk_div((uint32_t)T, prm.s_magic, prm.s_shift);
+                int s = T - (int)rounds * S;                                     // slot T % S (S is a multiple of 4: s % 4 == pg)
+                uint32_t par = (rounds & 1u) ^ 1u;
+                for (; t < sl.ntiles; t += TK_TG) {
                     int seg, unit0, nunits;
                     tk_tile_of(sl, G, t, seg, unit0, nunits);
                     fl_mbar_wait(bar0 + 8u * (S + s), par);
@@ -690,21 +711,24 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
                         fl_mbar_expect_tx(bar0 + 8u * s, bytes);
                         fl_bulk_g2s_hint(dst, w + (size_t)(2 * unit0) * row_bytes, bytes, bar0 + 8u * s, pol);
                     }
-                    if (++s == S) { s = 0; par ^= 1u; }
+                    s += TK_TG;
+                    if (s >= S) { s -= S; par ^= 1u; }
                 }
+                T0 += sl.ntiles;
             }
         }
         return;
     }
 
     // ------------------------------ consumers ------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TK_REGS_CONSUMER));
     const int tid = threadIdx.x;
     for (int i = tid; i < S * TK_GMAX; i += TK_NT) cnt[i] = 0;
     static_assert(sizeof(tk_phase) % 4 == 0 && sizeof(tk_phase) / 4 <= TK_NT, "descriptor copy is one word per thread");
     if (warp == TK_CW - 1)
         for (int i = lane; i < (int)(sizeof(tk_phase) / 4); i += 32) ((uint32_t *)&phs[0])[i] = ((const uint32_t *)&prm.phases[0])[i];
     tk_bar_consumers(15);
-    asm volatile("bar.sync 14, %0;" ::"r"(TK_NT + 32) : "memory");     // mbarriers initialised
+    asm volatile("bar.sync 14, %0;" ::"r"(TK_THREADS) : "memory");     // mbarriers initialised
     int T0 = 0;
     unsigned epoch = 0;
     // cross-GPU epochs continue across launches AND plans: the running count lives next to the flags (word 8 * 32 of the
@@ -723,7 +747,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
             epoch++;
             const bool xgpu = ph.kind == TK_PH_MATVEC && ph.a.n_xpeer > 0;   // this phase reads the other GPUs' partial results
             if (xgpu) xepoch++;
-            if (!(prm.diag & 4)) tk_grid_sync(prm, epoch * gridDim.x, xgpu ? xepoch : 0u);   // results of phase pi-1 are visible everywhere
+            if (!(prm.diag & 4)) tk_grid_sync(prm, epoch * gridDim.x * TK_CW, xgpu ? xepoch : 0u);   // results of phase pi-1 are visible everywhere
         }
         if (pr) pr[1] = tk_now();
         // Descriptor pi+1: the load is issued now, the store into phs[(pi+1)&1] (which nobody reads any more: everybody is

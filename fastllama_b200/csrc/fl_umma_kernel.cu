@@ -25,6 +25,7 @@
 //   warp 13     MMA issuer (one lane): tcgen05.mma + tcgen05.commit onto the mbarriers that free operands / publish
 //               accumulators.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "fl_common.cuh"
 #include "fl_kernels.h"
@@ -82,6 +83,7 @@ struct um_params {
     size_t dst_row_stride;
     int M, N, nbp;              // nbp = k-blocks padded to a multiple of UM_KC
     int ntiles;                 // column tiles
+    int diag;                   // FASTLLAMA_B200_UMMA_DIAG (timing experiments only, results are garbage): 1 = no TMEM loads, 2 = no epilogue math
 };
 
 // Synchronisation is per GROUP of KG k-blocks (KG * NT = at most 256 TMEM columns; two groups in flight = all 512 columns):
@@ -269,15 +271,21 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
 #pragma unroll
                     for (int ch = 0; ch < CPT / CW; ch++) {
                         uint32_t v[CW];
+                        if (prm.diag & 1) {
 #pragma unroll
-                        for (int c = 0; c < CW / 16; c++) UM_LD16(taddr + (uint32_t)(ch * CW + 16 * c), (&v[16 * c]));
-                        um_wait_ld();
+                            for (int c = 0; c < CW; c++) v[c] = (uint32_t)(c + kbi);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < CW / 16; c++) UM_LD16(taddr + (uint32_t)(ch * CW + 16 * c), (&v[16 * c]));
+                            um_wait_ld();
+                        }
                         if (i == KG - 1 && ch == CPT / CW - 1) {   // every column of the group's accumulators is in registers: hand them back
                             um_tc_fence_before();
                             __syncwarp();
                             if (lane == 0) fl_mbar_arrive(acc_empty(g));
                         }
                         const float4 *dy4 = (const float4 *)(dys + kbi * NT + c0 + ch * CW);
+                        if (prm.diag & 2) { if (v[0] == 0x7fffffffu) acc[0].x += 1.f; continue; }
 #pragma unroll
                         for (int j = 0; j < CW / 4; j++) {
                             const float4 d4 = dy4[j];
@@ -430,6 +438,7 @@ static int um_launch(cudaStream_t st, const void *W, size_t wrs, int M, int K, c
         attr_done = true;
     }
     um_params p;
+    p.diag = getenv("FASTLLAMA_B200_UMMA_DIAG") ? atoi(getenv("FASTLLAMA_B200_UMMA_DIAG")) : 0;
     p.yq = g_um.yq; p.dy = g_um.dy; p.sy = g_um.sy; p.dst = dst; p.dst_row_stride = drs; p.M = M; p.N = N; p.nbp = nbp; p.ntiles = ntiles;
     k_mul_mat_q_umma<TYPE, NT><<<mtiles * ntiles, UM_THREADS, L::SMEM, st>>>(tm, p);
     fl_count_launch();

@@ -92,9 +92,11 @@ int fl_host_free_pinned(void *p);
 /* activations -> q8_0 rows.  x row r starts at x + r*x_row_stride_bytes; y rows are packed. */
 int fl_dev_quantize_q8_0(const float *x, size_t x_row_stride_bytes, void *y, int k, int nrows);
 
-/* dst[n*dst_row_stride + m] = vec_dot(W row m, Yq8 row n).  impl: 0 = auto (N = 1: ring, N >= 4: tensor cores, else plain),
- * 1 = plain warp-per-row LDG kernel, 2 = TMA-bulk-staged persistent matvec (N = 1 only), 3 = tensor-core kernel
- * (mma.sync m16n8k32 u8 x s8 block sums, fp32 scales; any N). */
+/* dst[n*dst_row_stride + m] = vec_dot(W row m, Yq8 row n).  impl: 0 = auto (N = 1: ring; N >= 16: tcgen05 GEMM; N >= 4: mma.sync kernel;
+ * else plain), 1 = plain warp-per-row LDG kernel, 2 = TMA-bulk-staged persistent matvec (N = 1 only), 3 = legacy tensor-core kernel
+ * (mma.sync m16n8k32 u8 x s8 block sums, fp32 scales; any N), 4 = tcgen05 GEMM (fl_umma_kernel.cu: one tcgen05.mma kind::i8 M = 128,
+ * K = 32 per quant block into TMEM, weights by TMA, exact fp32 block scaling in the epilogue; needs 16-byte aligned W rows), 5 / 6 / 7 = the
+ * same with the column tile forced to 32 / 64 / 128 (7: q4_0 only). */
 int fl_dev_mul_mat_q(int type, const void *W, size_t w_row_stride_bytes, int M, int K, const void *Yq8, int N,
                      float *dst, size_t dst_row_stride_elems, int impl);
 

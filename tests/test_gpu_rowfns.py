@@ -175,3 +175,34 @@ def test_prompt_ingest_tensor_core_kernel(fl, oracle, t, m, k, n):
     assert np.all(np.abs(outs[3][0].astype(np.float64) - outs[1][0]) <= 2 * REORDER_BUDGET * mag + 1e-30)
     for d in (dW, dY, dD):
         fl.free(d)
+
+
+@pytest.mark.parametrize("t", [GGML_TYPE_Q4_0, GGML_TYPE_Q4_1])
+@pytest.mark.parametrize("m,k,n", [(128, 128, 32), (300, 256, 5), (1000, 11008, 37), (1024, 4096, 128), (514, 4096, 200), (4096, 4096, 128)])
+def test_prompt_ingest_tcgen05_kernel(fl, oracle, t, m, k, n):
+    """N > 1 on the Blackwell tensor cores (impl 4 = tile width chosen; 5 / 6 / 7 = column tiles of 32 / 64 / 128): one tcgen05.mma kind::i8 per
+    quant block into TMEM, exact fp32 block scaling in the epilogue -- the same budget against the order-free oracle as every other dot
+    product, ragged M / N / K-block tails included (TMA zero fill), run-to-run deterministic, and every tile width gives the same bits
+    (the per-output arithmetic does not depend on the tiling)."""
+    rng = np.random.default_rng(m + 3 * k + 7 * n)
+    from oracle.pyoracle import np_quantize_q4_0, np_quantize_q4_1
+
+    w = (rng.standard_normal((m, k)) * 0.03).astype(np.float32)
+    wq = (np_quantize_q4_0 if t == GGML_TYPE_Q4_0 else np_quantize_q4_1)(w)
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    ex, mag = oracle.mul_mat_q_exact(wq, x, t)
+    q8 = oracle.quantize_q8_0(x)
+    dW, dY, dD = fl.to_device(wq), fl.to_device(q8), fl.alloc(m * n * 4)
+    outs = []
+    for impl in (4, 4, 5, 6, 7):
+        if impl == 7 and t == GGML_TYPE_Q4_1:
+            continue
+        fl.check(fl.lib.fl_dev_memset(dD, 0xFF, m * n * 4))
+        fl.check(fl.lib.fl_dev_mul_mat_q(t, dW, wq.shape[1], m, k, dY, n, dD, m, impl))
+        got = fl.to_host(dD, (n, m), np.float32)
+        assert _dot_ok(got, ex, mag), f"impl {impl}"
+        outs.append(got)
+    for o in outs[1:]:
+        assert np.array_equal(outs[0].view(np.uint32), o.view(np.uint32))
+    for d in (dW, dY, dD):
+        fl.free(d)

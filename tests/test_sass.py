@@ -41,7 +41,9 @@ def test_token_kernel_uses_bulk_copies_and_dp4a_and_barely_spills():
     assert count(k, "UBLKCP") >= 2                   # weights: global -> shared through the TMA unit
     assert count(k, "IDP.4A") >= 64                  # block dots
     assert count(k, "SYNCS") >= 4                    # mbarrier ring
-    assert count(k, "LDL") + count(k, "STL") <= 24, "the token kernel spills"
+    # the 24-register producer warpgroup (setmaxnreg) may spill a little; the consumer code must not
+    assert count(k, "USETMAXREG") == 2, "producer / consumer register re-allocation (setmaxnreg) is missing"
+    assert count(k, "LDL") + count(k, "STL") <= 40, "the token kernel spills"
 
 
 def test_fused_and_ring_matvecs_use_bulk_copies():
@@ -55,3 +57,18 @@ def test_prompt_ingest_kernel_uses_integer_tensor_core_mma():
     f = sass("fl_mma_kernel.o")
     assert all(count(v, "IMMA") >= 8 for n, v in f.items() if "k_mul_mat_q_mma" in n)
     assert sum(1 for n in f if "k_mul_mat_q_mma" in n) == 2      # q4_0 and q4_1
+
+
+def test_prompt_ingest_gemm_is_a_tcgen05_kernel():
+    """The n_batch > 1 GEMM (fl_umma_kernel.cu): tcgen05.mma kind::i8 (SASS UTCIMMA) into TMEM, accumulators read back with
+    tcgen05.ld (LDTM), weights by a tensor-map TMA copy (UTMALDG), activations by bulk copies (UBLKCP), packed fp32 epilogue math."""
+    f = sass("fl_umma_kernel.o")
+    ks = {n: v for n, v in f.items() if "k_mul_mat_q_umma" in n}
+    assert len(ks) == 5                                   # q4_0 x {32, 64, 128} column tiles, q4_1 x {32, 64}
+    for n, v in ks.items():
+        assert count(v, "UTCIMMA") >= 2, n
+        assert count(v, "LDTM") >= 1, n
+        assert count(v, "UTMALDG") >= 1, n
+        assert count(v, "UBLKCP") >= 2, n
+        assert count(v, "FFMA2") >= 8, n
+        assert count(v, "HMMA") == 0 and count(v, "IMMA.") == 0, n      # no legacy mma.sync in this kernel
