@@ -21,6 +21,8 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -114,9 +116,12 @@ int ggml_cpu_has_cublas(void) { return 0; }
 int64_t ggml_nelements(const struct ggml_tensor *t) { return t->ne[0] * t->ne[1] * t->ne[2] * t->ne[3]; }
 static inline size_t nbytes_of(const struct ggml_tensor *t) { return (size_t)(ggml_nelements(t) * (int64_t)k_tsize[t->type]) / k_blck[t->type]; }
 static void host_access_hook(const struct ggml_tensor *t);
+// number of persistent arenas the device has written since their last host sync: while it is zero the exported ggml_nbytes is a pure
+// function (the reference's loader calls it from several threads, include/file_loader.hpp load_parallel)
+static std::atomic<int> g_dirty_arenas{0};
 // Exported ggml_nbytes doubles as the host-access hook of device-written arenas: see host_access_hook below.
 size_t ggml_nbytes(const struct ggml_tensor *t) {
-    host_access_hook(t);
+    if (g_dirty_arenas.load(std::memory_order_acquire) != 0) host_access_hook(t);
     return nbytes_of(t);
 }
 int ggml_blck_size(enum ggml_type type) { return k_blck[type]; }
@@ -612,6 +617,7 @@ void ensure_backend() {
 }
 
 void drop_mirror(Mirror &m) {
+    if (m.device_dirty) { m.device_dirty = false; g_dirty_arenas.fetch_sub(1, std::memory_order_release); }
     if (m.dev) {
         if (fl_is_initialized()) fl_dev_free(m.dev);
         m.dev = nullptr;
@@ -716,7 +722,7 @@ static void mark_device_write(const void *host, const ggml_context *compute_ctx)
     const int i = find_mirror(host);
     if (i < 0) return;
     Mirror &m = g_mirrors[i];
-    if (m.kind == MK_ARENA && !(compute_ctx && m.host == compute_ctx->mem_buffer)) m.device_dirty = true;
+    if (m.kind == MK_ARENA && !(compute_ctx && m.host == compute_ctx->mem_buffer) && !m.device_dirty) { m.device_dirty = true; g_dirty_arenas.fetch_add(1, std::memory_order_release); }
 }
 // The reference reads and overwrites kv_self.{k,v}->data on the host in KVCacheBuffer::save_state / load_state
 // (reference lib/llama.cpp:57-78) with no ggml call in between -- except ggml_nbytes(k), evaluated as an argument right
@@ -726,6 +732,8 @@ static void mark_device_write(const void *host, const ggml_context *compute_ctx)
 // fires during eval: Model::eval does not call ggml_nbytes on KV tensors, and the flag is clear outside device writes.
 static void host_access_hook(const struct ggml_tensor *t) {
     static const bool off = getenv("FASTLLAMA_B200_NO_HOST_HOOK") != nullptr;      // debugging aid: show what breaks without it
+    static std::mutex hook_mutex;                                                  // the slow path mutates the mirror table
+    std::lock_guard<std::mutex> lock(hook_mutex);
     if (off || !t || !t->data || g_mirrors.empty()) return;
     const int i = find_mirror(t->data);
     if (i < 0) return;
@@ -738,6 +746,7 @@ static void host_access_hook(const struct ggml_tensor *t) {
     if (n) FLC(fl_d2h((void *)m.host, m.dev, n));
     FLC(fl_sync());
     m.device_dirty = false;
+    g_dirty_arenas.fetch_sub(1, std::memory_order_release);
     m.uploaded = 0;              // the host may now change the data (load_state): everything is uploaded again on next use
 }
 
@@ -768,7 +777,7 @@ extern "C" void ggml_b200_release_all(void) {
     for (auto &m : g_mirrors) {
         drop_mirror(m);
         m.uploaded = 0;
-        m.device_dirty = false;
+        if (m.device_dirty) { m.device_dirty = false; g_dirty_arenas.fetch_sub(1, std::memory_order_release); }
         if (m.kind != MK_ARENA) m.alive = false;
     }
     // arenas whose host buffer is gone would never be matched again: forget all records (a live arena re-registers at its next ggml_init,
