@@ -35,7 +35,8 @@
 #define TK_GMAX 4                // units (row pairs) per tile at most
 #define TK_PW 4                  // producer warps: warp TK_CW + g streams the tiles of tile group g (its own slots, its own pace)
 #define TK_THREADS (TK_NT + 32 * TK_PW)
-#define TK_REGS_CONSUMER 120      // setmaxnreg: the producer warpgroup hands its registers to the four consumer warpgroups
+#define TK_REGS_CONSUMER 112      // setmaxnreg: the producer warpgroup hands its registers to the four consumer warpgroups.  The pool is the CTA's
+                                  // LAUNCH allocation (96 x 640 = 61440 registers): 112 x 512 + 24 x 128 = 60416 fits, 120 x 512 would wait forever
 #define TK_REGS_PRODUCER 24
 
 enum { TK_PH_MATVEC = 0, TK_PH_ATTN = 1 };
@@ -63,6 +64,8 @@ struct tk_params {
     unsigned *xflags_local;          // tensor parallel: flags[q * 32] is written by rank q (through its peer mapping of this buffer)
     unsigned *xflags_peer[8];        // rank p's flag array as mapped here
     int rank, world;
+    unsigned *ll_count;              // running number of LL reductions of all earlier launches (word 8 * 32 of the rank's own shared buffer)
+    int n_ll;                        // LL reductions per launch
     int xrelease_sys;                // FASTLLAMA_B200_TP_RELEASE_SYS: every CTA releases at sys scope (measured 644 vs 697 tok/s at TP2)
     const uint16_t *exp_tab;
     unsigned long long *prof;      // optional: [n_phases][gridDim.x][4] globaltimer stamps of thread 0
@@ -191,15 +194,54 @@ __device__ __forceinline__ void tk_zero_vals(float v[E]) {
 #pragma unroll
     for (int k = 0; k < E; k++) v[k] = 0.f;
 }
+// E values of unit u from an LL slot ({value, epoch} words): all loads are issued, then re-issued until every word carries epoch e
+template <int E>
+__device__ __forceinline__ void tk_load_ll(const float *base, int u, float v[E], unsigned e, unsigned *err) {
+    const uint4 *p = (const uint4 *)base + (size_t)(E / 2) * u;
+    unsigned long long t0 = 0;
+    for (unsigned n = 1;; n++) {
+        uint4 t[E / 2];
+#pragma unroll
+        for (int k = 0; k < E / 2; k++)
+            asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t[k].x), "=r"(t[k].y), "=r"(t[k].z), "=r"(t[k].w) : "l"(p + k) : "memory");
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < E / 2; k++) {
+            ok = ok && t[k].y == e && t[k].w == e;
+            v[2 * k] = __uint_as_float(t[k].x);
+            v[2 * k + 1] = __uint_as_float(t[k].z);
+        }
+        if (ok) return;
+        if ((n & 255u) == 0) {                       // bounded like every other spin of this kernel
+            if (*(volatile unsigned *)err) return;
+            const unsigned long long now = tk_now();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) {
+                if (atomicExch(err, 1u) == 0u) { err[1] = 0x300u; err[2] = e; err[3] = t[0].y; err[4] = blockIdx.x; }
+                return;
+            }
+        }
+    }
+}
 // x (+ the other ranks' partial sums, in rank order: slots of the local peer-written buffer) (+ xadd) of unit u
 template <int E>
-__device__ __forceinline__ void tk_load_x(const fl_mv_args &A, int u, float v[E]) {
-    tk_load_vals<E>((const float4 *)A.x, u, v, true);
-    for (int r = 0; r < A.n_xpeer; r++) {
-        float w[E];
-        tk_load_vals<E>((const float4 *)A.xpeer[r], u, w, true);
+__device__ __forceinline__ void tk_load_x(const fl_mv_args &A, int u, float v[E], unsigned ll_epoch, unsigned *err) {
+    if (A.ll && A.n_xpeer > 0) {
+        tk_load_ll<E>(A.x, u, v, ll_epoch, err);
+        for (int r = 0; r < A.n_xpeer; r++) {
+            float w[E];
+            tk_load_ll<E>(A.xpeer[r], u, w, ll_epoch, err);
 #pragma unroll
-        for (int k = 0; k < E; k++) v[k] = __fadd_rn(v[k], w[k]);
+            for (int k = 0; k < E; k++) v[k] = __fadd_rn(v[k], w[k]);
+        }
+    } else {
+        tk_load_vals<E>((const float4 *)A.x, u, v, true);
+        for (int r = 0; r < A.n_xpeer; r++) {
+            float w[E];
+            tk_load_vals<E>((const float4 *)A.xpeer[r], u, w, true);
+#pragma unroll
+            for (int k = 0; k < E; k++) v[k] = __fadd_rn(v[k], w[k]);
+        }
     }
     if (A.xadd) {
         float w[E];
@@ -251,14 +293,14 @@ __device__ __forceinline__ void tk_quant(const float v[E], int u, bool valid, tk
 }
 // plain / silu*mul prologue body for one unit size
 template <int E>
-__device__ __forceinline__ void tk_prologue_nonorm(const fl_mv_args &A, int K, tk_yblock *ysm, int warp, int tid) {
+__device__ __forceinline__ void tk_prologue_nonorm(const fl_mv_args &A, int K, tk_yblock *ysm, int warp, int tid, unsigned lle, unsigned *err) {
     const int nu = K / E;
     for (int u0 = 0; u0 < nu; u0 += TK_NT) {
         if (u0 + warp * 32 >= nu) break;                 // warp-uniform
         const int u = u0 + tid;
         const bool valid = u < nu;
         float v[E];
-        if (valid) tk_load_x<E>(A, u, v); else tk_zero_vals<E>(v);
+        if (valid) tk_load_x<E>(A, u, v, lle, err); else tk_zero_vals<E>(v);
         if (A.sum_out && blockIdx.x == 0 && valid) tk_store_vals<E>(A.sum_out, u, v);
         if (A.pro == FL_PRO_SILUMUL) {
             float bm[E];
@@ -277,7 +319,7 @@ __device__ __forceinline__ void tk_prologue_nonorm(const fl_mv_args &A, int K, t
 // and the quantisation (K <= 8 * RES * TK_NT); RES == 0: two passes over L2.
 // Sum of squares: thread t adds the values of units t, t + NT, ... in order (k_mv_fused uses the same order).
 template <int RES>
-__device__ __forceinline__ void tk_prologue_norm(const fl_mv_args &A, int K, tk_yblock *ysm, double *red, int warp, int lane, int tid) {
+__device__ __forceinline__ void tk_prologue_norm(const fl_mv_args &A, int K, tk_yblock *ysm, double *red, int warp, int lane, int tid, unsigned lle, unsigned *err) {
     constexpr int E = 8, NR = RES > 0 ? RES : 1;
     const int nu = K >> 3;
     float v[NR][E], gm[NR][E];
@@ -286,7 +328,7 @@ __device__ __forceinline__ void tk_prologue_norm(const fl_mv_args &A, int K, tk_
 #pragma unroll
         for (int r = 0; r < NR; r++) {
             const int u = tid + r * TK_NT;
-            if (u < nu) { tk_load_x<E>(A, u, v[r]); tk_load_vals<E>((const float4 *)A.gamma, u, gm[r], false); }
+            if (u < nu) { tk_load_x<E>(A, u, v[r], lle, err); tk_load_vals<E>((const float4 *)A.gamma, u, gm[r], false); }
             else { tk_zero_vals<E>(v[r]); tk_zero_vals<E>(gm[r]); }
         }
 #pragma unroll
@@ -295,7 +337,7 @@ __device__ __forceinline__ void tk_prologue_norm(const fl_mv_args &A, int K, tk_
             for (int k = 0; k < E; k++) acc += (double)__fmul_rn(v[r][k], v[r][k]);
     } else {
         for (int u = tid; u < nu; u += TK_NT) {
-            tk_load_x<E>(A, u, v[0]);
+            tk_load_x<E>(A, u, v[0], lle, err);
 #pragma unroll
             for (int k = 0; k < E; k++) acc += (double)__fmul_rn(v[0][k], v[0][k]);
         }
@@ -330,7 +372,7 @@ __device__ __forceinline__ void tk_prologue_norm(const fl_mv_args &A, int K, tk_
             if (u0 + warp * 32 >= nu) break;
             const int u = u0 + tid;
             const bool valid = u < nu;
-            if (valid) { tk_load_x<E>(A, u, v[0]); tk_load_vals<E>((const float4 *)A.gamma, u, gm[0], false); }
+            if (valid) { tk_load_x<E>(A, u, v[0], lle, err); tk_load_vals<E>((const float4 *)A.gamma, u, gm[0], false); }
             else { tk_zero_vals<E>(v[0]); tk_zero_vals<E>(gm[0]); }
             if (A.sum_out && blockIdx.x == 0 && valid) tk_store_vals<E>(A.sum_out, u, v[0]);
 #pragma unroll
@@ -341,18 +383,18 @@ __device__ __forceinline__ void tk_prologue_norm(const fl_mv_args &A, int K, tk_
     }
 }
 
-__device__ __forceinline__ void tk_prologue(const fl_mv_args &A, int K, tk_yblock *ysm, double *red, int warp, int lane, int tid) {
+__device__ __forceinline__ void tk_prologue(const fl_mv_args &A, int K, tk_yblock *ysm, double *red, int warp, int lane, int tid, unsigned lle, unsigned *err) {
     const int nu8 = K >> 3;
     if (A.pro == FL_PRO_RMSNORM) {
-        if (nu8 <= TK_NT) tk_prologue_norm<1>(A, K, ysm, red, warp, lane, tid);
-        else if (nu8 <= 2 * TK_NT) tk_prologue_norm<2>(A, K, ysm, red, warp, lane, tid);
-        else tk_prologue_norm<0>(A, K, ysm, red, warp, lane, tid);
+        if (nu8 <= TK_NT) tk_prologue_norm<1>(A, K, ysm, red, warp, lane, tid, lle, err);
+        else if (nu8 <= 2 * TK_NT) tk_prologue_norm<2>(A, K, ysm, red, warp, lane, tid, lle, err);
+        else tk_prologue_norm<0>(A, K, ysm, red, warp, lane, tid, lle, err);
     } else if (nu8 <= TK_NT) {
-        tk_prologue_nonorm<8>(A, K, ysm, warp, tid);          // short vectors: latency matters, spread over all threads
+        tk_prologue_nonorm<8>(A, K, ysm, warp, tid, lle, err);          // short vectors: latency matters, spread over all threads
     } else if ((K >> 4) <= TK_NT) {
-        tk_prologue_nonorm<16>(A, K, ysm, warp, tid);         // long vectors: issue slots matter
+        tk_prologue_nonorm<16>(A, K, ysm, warp, tid, lle, err);         // long vectors: issue slots matter
     } else {
-        tk_prologue_nonorm<32>(A, K, ysm, warp, tid);         // K > 8192 (w2): one thread per block, no shuffles, one L2 round trip
+        tk_prologue_nonorm<32>(A, K, ysm, warp, tid, lle, err);         // K > 8192 (w2): one thread per block, no shuffles, one L2 round trip
     }
 }
 
@@ -370,7 +412,7 @@ __device__ __forceinline__ float2 tk_epilogue_preload(const tk_phase &ph, int se
     if (A.epi == FL_EPI_RESADD) return __ldcg((const float2 *)(A.res + r2));
     return make_float2(0.f, 0.f);
 }
-__device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, float a, float b, int n_past, float2 pre) {
+__device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, float a, float b, int n_past, float2 pre, unsigned ll_epoch) {
     const fl_mv_args &A = ph.a;
     if (ph.swiglu) {
         const uint16_t h = __half_as_ushort(__float2half_rn(a));
@@ -396,6 +438,19 @@ __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, 
         a = __fadd_rn(a, pre.x);
         b = __fadd_rn(b, pre.y);
     }
+    if (A.ll && A.n_dst_peer > 0) {
+        // LL: every value travels with the epoch in one 8-byte word; seg_dst[0] and dst_peer[] are LL slots (8 bytes per row)
+        const unsigned e = ll_epoch, ua = __float_as_uint(a), ub = __float_as_uint(b);
+        float *d0 = A.seg_dst[seg] + 2 * r2;
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(d0), "r"(ua), "r"(e) : "memory");
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(d0 + 2), "r"(ub), "r"(e) : "memory");
+        for (int r = 0; r < A.n_dst_peer; r++) {
+            float *d = A.dst_peer[r] + 2 * r2;                                                        // posted stores over NVLink
+            asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(d), "r"(ua), "r"(e) : "memory");
+            asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(d + 2), "r"(ub), "r"(e) : "memory");
+        }
+        return;
+    }
     *(float2 *)dst = make_float2(a, b);
     for (int r = 0; r < A.n_dst_peer; r++) *(float2 *)(A.dst_peer[r] + r2) = make_float2(a, b);     // posted stores over NVLink
 }
@@ -408,7 +463,7 @@ __device__ __forceinline__ unsigned tk_clock() {
 }
 template <int TYPE, int NFULL, bool PROF>
 __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, const tk_yblock *ysm,
-                                           float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw) {
+                                           float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw, unsigned lle) {
     unsigned c_begin = 0, c_wait = 0, c_dot = 0, c_tail = 0, c_rounds = 0, c_t = 0, c_yp = 0;
     if (PROF) c_begin = tk_clock();
     constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
@@ -502,7 +557,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
             if (lane == 0) {
                 const int u = unit0 + g;
                 if (kparts == 1) {
-                    tk_epilogue(ph, seg, u, totA, totB, n_past, pre);
+                    tk_epilogue(ph, seg, u, totA, totB, n_past, pre, lle);
                 } else {
                     volatile float *rb = rowbuf + ((size_t)s * TK_GMAX + g) * 8;      // [2 rows][kparts <= 4]
                     rb[p] = totA;
@@ -514,7 +569,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
                         __threadfence_block();
                         float x0 = rb[0], x1 = rb[4];
                         for (int q = 1; q < kparts; q++) { x0 = __fadd_rn(x0, rb[q]); x1 = __fadd_rn(x1, rb[4 + q]); }
-                        tk_epilogue(ph, seg, u, x0, x1, n_past, pre);
+                        tk_epilogue(ph, seg, u, x0, x1, n_past, pre, lle);
                     }
                 }
             }
@@ -630,12 +685,12 @@ __device__ __forceinline__ void tk_attention_prefetch(const tk_phase &ph, int he
 
 template <int TYPE, bool PROF>
 __device__ __forceinline__ void tk_consume_dispatch(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, const tk_yblock *ysm,
-                                                    float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw) {
+                                                    float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw, unsigned lle) {
     switch (ph.nfull) {
-        case 4: tk_consume<TYPE, 4, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw); break;
-        case 3: tk_consume<TYPE, 3, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw); break;
-        case 2: tk_consume<TYPE, 2, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw); break;
-        default: tk_consume<TYPE, 0, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw); break;
+        case 4: tk_consume<TYPE, 4, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
+        case 3: tk_consume<TYPE, 3, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
+        case 2: tk_consume<TYPE, 2, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
+        default: tk_consume<TYPE, 0, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
     }
 }
 
@@ -735,6 +790,10 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
     // rank's own shared buffer), so flags left behind by earlier launches can never satisfy a later wait
     unsigned xepoch = 0;
     if (prm.world > 1 && tid == 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(xepoch) : "l"(prm.xflags_local + 8 * 32) : "memory");
+    // LL reductions: every element carries (number of LL reductions before this launch) + (index inside the launch) + 1
+    unsigned ll_base = 0;
+    if (prm.n_ll > 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ll_base) : "l"(prm.ll_count) : "memory");
+    unsigned *err = prm.err;
     for (int pi = 0; pi < prm.n_phases; pi++) {
         const tk_phase &ph = phs[pi & 1];
         unsigned long long *pr = (prm.prof && tid == 0) ? prm.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 4 : nullptr;
@@ -743,9 +802,13 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         const bool attn_here = ph.kind == TK_PH_ATTN && (int)blockIdx.x < ph.n_head * ph.head_split;
         const int a_head = attn_here ? (int)blockIdx.x / ph.head_split : 0, a_part = attn_here ? (int)blockIdx.x % ph.head_split : 0;
         if (attn_here) tk_attention_prefetch(ph, a_head, a_part, tid);
-        if (pi > 0) {
+        const bool ll_in = ph.kind == TK_PH_MATVEC && ph.a.ll && ph.a.n_xpeer > 0;    // input arrives element by element with epochs: no barrier at all
+        const unsigned lle = (ph.kind == TK_PH_MATVEC && ph.a.ll) ? ll_base + (unsigned)ph.a.ll_seq + 1u : 0u;
+        if (pi > 0 && ll_in) {
+            tk_bar_consumers(13);                                // only this CTA's warps: the previous phase's tiles have been consumed
+        } else if (pi > 0) {
             epoch++;
-            const bool xgpu = ph.kind == TK_PH_MATVEC && ph.a.n_xpeer > 0;   // this phase reads the other GPUs' partial results
+            const bool xgpu = ph.kind == TK_PH_MATVEC && ph.a.n_xpeer > 0;   // this phase reads the other GPUs' partial results (flag-barrier form)
             if (xgpu) xepoch++;
             if (!(prm.diag & 4)) tk_grid_sync(prm, epoch * gridDim.x * TK_CW, xgpu ? xepoch : 0u);   // results of phase pi-1 are visible everywhere
         }
@@ -764,18 +827,21 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         }
         const int K = ph.nb * 32;
         if (tid == TK_NT - 1) sl_sh = tk_make_slice_u(ph.units[0], ph.units[1], ph.units[2], ph.lgG, prm.grid_magic, prm.grid_shift);
-        if (!(prm.diag & 8)) tk_prologue(ph.a, K, ysm, red, warp, lane, tid);
+        if (!(prm.diag & 8)) tk_prologue(ph.a, K, ysm, red, warp, lane, tid, lle, err);
         if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
         tk_bar_consumers(15);                                    // activations, slice and next descriptor are in shared memory
         if (pr) pr[2] = tk_now();
         const tk_slice &sl = sl_sh;
         unsigned *pw = (PROF && prm.prof2) ? prm.prof2 + (((size_t)pi * gridDim.x + blockIdx.x) * TK_CW + warp) * 8 : nullptr;
-        if (ph.a.type == FL_TYPE_Q4_0) tk_consume_dispatch<FL_TYPE_Q4_0, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw);
-        else                           tk_consume_dispatch<FL_TYPE_Q4_1, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw);
+        if (ph.a.type == FL_TYPE_Q4_0) tk_consume_dispatch<FL_TYPE_Q4_0, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle);
+        else                           tk_consume_dispatch<FL_TYPE_Q4_1, PROF>(ph, prm, sl, T0, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle);
         T0 += sl.ntiles;
         if (pr) pr[3] = tk_now();
     }
-    if (prm.world > 1 && blockIdx.x == 0 && tid == 0) prm.xflags_local[8 * 32] = xepoch;     // next launch continues from here
+    if (prm.world > 1 && blockIdx.x == 0 && tid == 0) {
+        prm.xflags_local[8 * 32] = xepoch;     // next launch continues from here
+        if (prm.n_ll > 0) *prm.ll_count = ll_base + (unsigned)prm.n_ll;
+    }
 }
 
 // =================================================================================================
@@ -931,7 +997,7 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     FL_CUDA_OK(cudaHostAlloc((void **)&pl->h_err, 64, cudaHostAllocMapped));
     memset(pl->h_err, 0, 64);
     FL_CUDA_OK(cudaHostGetDevicePointer((void **)&p.err, pl->h_err, 0));
-    p.rank = 0; p.world = 1; p.xflags_local = nullptr;
+    p.rank = 0; p.world = 1; p.xflags_local = nullptr; p.ll_count = nullptr; p.n_ll = 0;
     p.xrelease_sys = getenv("FASTLLAMA_B200_TP_RELEASE_SYS") ? 1 : 0;
     for (int r = 0; r < 8; r++) p.xflags_peer[r] = nullptr;
     bool uses_peers = false;
@@ -942,6 +1008,9 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
         if (!peers) { flk_token_plan_destroy(pl); fl_set_error("token kernel: steps read peer buffers but fl_comm_shared_alloc was never called"); return -1; }
         p.rank = rank; p.world = world;
         p.xflags_local = (unsigned *)peers[rank];
+        p.ll_count = p.xflags_local + 9 * 32;
+        for (int i = 0; i < n_steps; i++)
+            if (phases[i].kind == TK_PH_MATVEC && phases[i].a.ll && phases[i].a.n_dst_peer > 0) p.n_ll = std::max(p.n_ll, phases[i].a.ll_seq + 1);
         for (int r = 0; r < world; r++) p.xflags_peer[r] = (unsigned *)peers[r];
         for (int i = 0; i < n_steps; i++)
             if (phases[i].kind == TK_PH_MATVEC && phases[i].a.n_xpeer > 0 && phases[i].a.n_xpeer != world - 1) {
@@ -964,6 +1033,10 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     FL_CUDA_OK(cudaFuncSetAttribute(k_decode_token<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
     FL_CUDA_OK(cudaFuncGetAttributes(&fa, k_decode_token<true>));
     FL_CUDA_OK(cudaFuncSetAttribute(k_decode_token<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    // setmaxnreg re-distributes the registers the CTA was LAUNCHED with; an over-subscribed request would spin forever inside the kernel
+    FL_REQUIRE((size_t)TK_REGS_CONSUMER * TK_NT + (size_t)TK_REGS_PRODUCER * 32 * TK_PW <= (size_t)fa.numRegs * TK_THREADS,
+               "token kernel: register re-allocation (%d x %d + %d x %d) exceeds the launch allocation (%d x %d)", TK_REGS_CONSUMER, TK_NT, TK_REGS_PRODUCER,
+               32 * TK_PW, fa.numRegs, TK_THREADS);
     int per_sm = 0;
     FL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_token<false>, TK_THREADS, pl->smem));
     if (per_sm < 1) { const size_t need = pl->smem; flk_token_plan_destroy(pl); fl_set_error("token kernel: one CTA per SM does not fit (smem %zu)", need); return -1; }

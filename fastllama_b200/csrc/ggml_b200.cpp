@@ -918,7 +918,11 @@ void exec_node(ggml_tensor *node, const ggml_context *cctx) {
                 B200_ASSERT(a->nb[0] == k_tsize[a->type] && b->nb[0] == sizeof(float) && node->nb[0] == k_tsize[a->type] && a->ne[0] % 32 == 0);
                 FLC(fl_dev_add_q_f32((int)a->type, dev_ptr(a->data, nbytes_of(a), cctx), a->nb[1], (int)a->ne[1], (int)a->ne[0],
                                      (const float *)dev_ptr(b->data, nbytes_of(b), cctx), b->nb[1] / sizeof(float), dev_ptr(node->data, nbytes_of(node), cctx), node->nb[1]));
-                packed_shards_clear();          // tensor-parallel K-slices packed from the old weights are stale now
+                // the host tensor follows the device (tensor-parallel shards are uploaded from the HOST tensor, and a mirror that is
+                // dropped later would otherwise come back with the unmerged bytes)
+                FLC(fl_d2h(node->data, dev_ptr(node->data, nbytes_of(node), cctx), nbytes_of(node)));
+                FLC(fl_sync());
+                packed_shards_clear();          // shards cut from the old weights are stale now
                 return;
             }
             need_f32(node->src0, k_opname[node->op]); need_f32(node->src1, k_opname[node->op]);
@@ -1026,6 +1030,8 @@ struct DecodeWs {
     // token kernel can sum the ranks' partial results itself (peers[r] = rank r's buffer as mapped on this rank)
     void *peers[8] = {nullptr};
     bool peer_mapped = false;
+    bool use_ll = true;         // reductions in LL form ({value, epoch} words, no barrier); FASTLLAMA_B200_TP_NO_LL=1: plain slots + cross-GPU flag barrier
+    size_t ll_slot_bytes = 0;   // bytes of one rank's slot in an LL buffer (n_embd * 8)
 };
 struct DecodeState {
     DecodePlan plan;            // the plan the captured graph was built from
@@ -1083,12 +1089,18 @@ void ensure_ws(DecodeWs &w, int n_embd, int n_ff, int n_vocab) {
     w.peer_mapped = false;
     if (fl_comm_world() > 1 && getenv("FASTLLAMA_B200_NO_PEER") == nullptr) {
         // collective: every rank gets here on its first decode step
-        // layout of every rank's buffer: 4096 bytes of flags, then part1[world][n_embd], part2[world][n_embd]: slot r is
-        // written by rank r (into its own buffer and, over NVLink, into everybody else's)
+        // layout of every rank's buffer: 4096 bytes of flags / counters, then two reduction buffers (after wo, after w2) of `world` slots each;
+        // slot r is written by rank r (into its own buffer and, over NVLink, into everybody else's).  A slot holds n_embd floats (flag-barrier
+        // form) or n_embd {value, epoch} words (LL form); the buffer is sized for the LL form of the largest model (n_embd 8192).
         const int world = fl_comm_world(), rank = fl_comm_rank();
-        if (fl_comm_shared_alloc(4096 + (size_t)2 * world * std::max(n_embd, 8192) * sizeof(float), w.peers) == 0) {
-            w.part1 = (float *)((char *)w.peers[rank] + 4096) + (size_t)rank * n_embd;
-            w.part2 = w.part1 + (size_t)world * n_embd;
+        w.use_ll = getenv("FASTLLAMA_B200_TP_NO_LL") == nullptr;
+        const size_t slot_cap = (size_t)std::max(n_embd, 8192) * 8;
+        if (fl_comm_shared_alloc(4096 + (size_t)2 * world * slot_cap, w.peers) == 0) {
+            w.ll_slot_bytes = w.use_ll ? (size_t)n_embd * 8 : (size_t)n_embd * 4;
+            if (!w.use_ll) {                    // flag-barrier form: the plain partial-sum vectors live in the peer buffer itself
+                w.part1 = (float *)((char *)w.peers[rank] + 4096) + (size_t)rank * n_embd;
+                w.part2 = w.part1 + (size_t)world * n_embd;
+            }
             w.peer_mapped = true;
         } else if (g_verbose) {
             fprintf(stderr, "[ggml_b200] no peer-mapped buffers (%s): tensor-parallel decode keeps the NCCL path\n", fl_last_error());
@@ -1096,31 +1108,76 @@ void ensure_ws(DecodeWs &w, int n_embd, int n_ff, int n_vocab) {
     }
 }
 
-// K-split shards of wo / w2 (tensor parallelism): blocks [blk0, blk0 + nblk) of every row, packed once
-// into a private matrix with a 16-byte-multiple row stride so each tile is still one bulk copy
-std::unordered_map<const void *, void *> g_packed;
+// ---- tensor-parallel weight shards, uploaded straight from the HOST tensors (reference hook point lib/llama.cpp:257-258) -----------
+// Under tensor parallelism a rank never uploads the model: every weight the fused decode plan touches gets a private device copy of
+// exactly what this rank reads -- a row range (wq/wk/wv/w1/w3/output: contiguous host bytes), a K-slice (wo/w2: blocks
+// [blk0, blk0 + nblk) of every row, gathered on the host into pinned staging so that the device never sees the other ranks' columns;
+// the packed row stride is a 16-byte multiple so every tile is still one bulk copy), or the whole tensor (norm weights, the
+// embedding table).  8 ranks of a 65B model upload 5 GB each instead of 40.6 GB.  The arena / mmap mirrors of the weights are not
+// touched by decode steps at all; a replicated multi-token eval (n_batch > 1) still mirrors what it reads.
+struct ShardKey {
+    const void *host; int kind, a, b;
+    bool operator==(const ShardKey &o) const { return host == o.host && kind == o.kind && a == o.a && b == o.b; }
+};
+struct ShardKeyHash { size_t operator()(const ShardKey &k) const { return std::hash<const void *>()(k.host) ^ ((size_t)k.kind * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.a << 20) ^ (size_t)k.b; } };
+enum { SH_FULL = 0, SH_ROWS = 1, SH_COLS = 2 };
+std::unordered_map<ShardKey, void *, ShardKeyHash> g_packed;
+char *g_shard_staging = nullptr;
+size_t g_shard_staging_cap = 0, g_shard_bytes = 0;
 }  // namespace
 static void packed_shards_clear() {
     if (g_packed.empty()) return;
     if (fl_is_initialized()) fl_sync();
     for (auto &kv : g_packed) fl_dev_free(kv.second);
     g_packed.clear();
+    g_shard_bytes = 0;
 }
 namespace {
-const void *packed_shard(const ggml_tensor *w, const void *w_dev, int blk0, int nblk, size_t &stride_out) {
+// device copy of (kind SH_FULL) the whole tensor, (SH_ROWS) rows [a, a + b), (SH_COLS) blocks [a, a + b) of every row with row stride *stride_out
+const void *tp_shard(const ggml_tensor *w, int kind, int a, int b, size_t *stride_out = nullptr) {
     const size_t bb = k_tsize[w->type];
-    stride_out = ((size_t)nblk * bb + 15) & ~(size_t)15;
-    auto it = g_packed.find(w_dev);
+    const size_t stride = kind == SH_COLS ? (((size_t)b * bb + 15) & ~(size_t)15) : w->nb[1];
+    if (stride_out) *stride_out = stride;
+    const ShardKey key{w->data, kind, a, b};
+    auto it = g_packed.find(key);
     if (it != g_packed.end()) return it->second;
-    void *dst = fl_dev_malloc(stride_out * (size_t)w->ne[1] + 256);
-    if (!dst) B200_FAIL("tensor-parallel shard: %s", fl_last_error());
-    FLC(fl_dev_pack_cols((int)w->type, w_dev, w->nb[1], (int)w->ne[1], blk0, nblk, dst, stride_out));
-    g_packed[w_dev] = dst;
+    ensure_backend();
+    const size_t rows = (size_t)nrows(w);
+    const size_t bytes = kind == SH_FULL ? nbytes_of(w) : kind == SH_ROWS ? (size_t)b * w->nb[1] : stride * rows;
+    void *dst = fl_dev_malloc(bytes + 256);
+    if (!dst) B200_FAIL("tensor-parallel shard of %zu bytes: %s", bytes, fl_last_error());
+    if (kind == SH_COLS) {
+        // gather the K-slice on the host: the other ranks' columns never cross PCIe
+        if (g_shard_staging_cap < bytes) {
+            if (g_shard_staging) { FLC(fl_sync()); FLC(fl_host_free_pinned(g_shard_staging)); }
+            g_shard_staging_cap = bytes + bytes / 4;
+            g_shard_staging = (char *)fl_host_alloc_pinned(g_shard_staging_cap);
+            if (!g_shard_staging) B200_FAIL("shard staging: %s", fl_last_error());
+        }
+        FLC(fl_sync());                                               // the previous shard has left the staging buffer
+        const size_t slice = (size_t)b * bb;
+        for (size_t r = 0; r < rows; r++) {
+            char *d = g_shard_staging + r * stride;
+            memcpy(d, (const char *)w->data + r * w->nb[1] + (size_t)a * bb, slice);
+            if (stride > slice) memset(d + slice, 0, stride - slice);
+        }
+        FLC(fl_h2d(dst, g_shard_staging, bytes));
+    } else {
+        FLC(fl_h2d(dst, (const char *)w->data + (kind == SH_ROWS ? (size_t)a * w->nb[1] : 0), bytes));
+    }
+    g_packed[key] = dst;
+    g_shard_bytes += bytes;
+    if (g_verbose && (g_packed.size() & 63) == 0) fprintf(stderr, "[ggml_b200] tensor-parallel shards: %zu tensors, %zu MiB on the device\n", g_packed.size(), g_shard_bytes >> 20);
     return dst;
 }
 
 bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, DecodeWs &W, DecodeOutputs &O) {
     const int world = fl_comm_world(), rank = fl_comm_rank();
+    // weights: one GPU -> the arena / mmap mirror; tensor parallel -> only this rank's shard, uploaded from the host tensor (tp_shard)
+    auto wfull = [&](const ggml_tensor *t) -> const void * { return world == 1 ? (const void *)dp<const void>(t, ctx) : tp_shard(t, SH_FULL, 0, 0); };
+    auto wrows = [&](const ggml_tensor *t, int row0, int n) -> const void * {
+        return world == 1 ? (const void *)((const char *)dp<const void>(t, ctx) + (size_t)row0 * t->nb[1]) : tp_shard(t, SH_ROWS, row0, n);
+    };
     PM(g->n_nodes >= 4 + 37 && (g->n_nodes - 4) % 37 == 0);
     Cur c{g, 0, true};
     ggml_tensor *n0 = c.next(GGML_OP_GET_ROWS);
@@ -1130,7 +1187,7 @@ bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, Decode
     P.n_embd = n_embd;
     P.n_layer = (g->n_nodes - 4) / 37;
     P.emb_type = (int)n0->src0->type; P.emb_K = n_embd; P.emb_stride = n0->src0->nb[1];
-    P.emb_w = dp<const void>(n0->src0, ctx);
+    P.emb_w = wfull(n0->src0);
     O.token = *(const int32_t *)n0->src1->data;
     P.layers.resize(P.n_layer);
     ggml_tensor *x = n0;
@@ -1197,6 +1254,7 @@ bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, Decode
         PM(fl_dev_mv_fused_supported((int)wq->type, n_embd, 3 * n_embd) && fl_dev_mv_fused_supported((int)wo->type, n_embd, n_embd) &&
            fl_dev_mv_fused_supported((int)w1->type, n_embd, 2 * n_ff) && fl_dev_mv_fused_supported((int)w2->type, n_ff, n_embd));
 
+        if (world > 1) PM(n_head % world == 0 && n_ff % (32 * world) == 0 && (n_embd / world) % 32 == 0 && g->nodes[g->n_nodes - 1]->ne[0] % (2 * world) == 0);
         if (il == 0) {
             ensure_ws(W, n_embd, n_ff, (int)g->nodes[g->n_nodes - 1]->ne[0]);
             P.emb_ids = W.d_tok; P.emb_dst = W.xa;
@@ -1211,47 +1269,45 @@ bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, Decode
         // wq|wk|wv: rms_norm prologue, rope + cache-store epilogue
         mv_base(L.qkv, (int)wq->type, n_embd);
         L.qkv.nseg = 3;
-        L.qkv.seg_w[0] = dp<const void>(wq, ctx); L.qkv.seg_w[1] = dp<const void>(wk, ctx); L.qkv.seg_w[2] = dp<const void>(wv, ctx);
+        const int nl_rows = n_embd / world;                              // this rank's rows of wq / wk / wv (whole heads)
+        L.qkv.seg_w[0] = wrows(wq, rank * nl_rows, nl_rows); L.qkv.seg_w[1] = wrows(wk, rank * nl_rows, nl_rows); L.qkv.seg_w[2] = wrows(wv, rank * nl_rows, nl_rows);
         L.qkv.seg_rows[0] = L.qkv.seg_rows[1] = L.qkv.seg_rows[2] = n_embd;
         L.qkv.seg_dst[0] = (float *)L.q;
-        L.qkv.pro = FL_PRO_RMSNORM; L.qkv.x = xin; L.qkv.gamma = dp<const float>(b->src0, ctx);
+        L.qkv.pro = FL_PRO_RMSNORM; L.qkv.x = xin; L.qkv.gamma = (const float *)wfull(b->src0);
         L.qkv.epi = FL_EPI_QKV; L.qkv.n_ctx = n_ctx; L.qkv.n_embd = n_embd; L.qkv.head_dim = hd;
         L.qkv.kcache = (float *)L.kcache; L.qkv.vcache = (float *)L.vcache;
         // wo: plain prologue, residual epilogue
         mv_base(L.wo, (int)wo->type, n_embd);
-        L.wo.nseg = 1; L.wo.seg_w[0] = dp<const void>(wo, ctx); L.wo.seg_rows[0] = n_embd; L.wo.seg_dst[0] = W.ff;
+        L.wo.nseg = 1; L.wo.seg_w[0] = world == 1 ? wfull(wo) : nullptr; L.wo.seg_rows[0] = n_embd; L.wo.seg_dst[0] = W.ff;
         L.wo.pro = FL_PRO_PLAIN; L.wo.x = L.att; L.wo.epi = FL_EPI_RESADD; L.wo.res = xin;
         // w1|w3: rms_norm prologue
         mv_base(L.w13, (int)w1->type, n_embd);
-        L.w13.nseg = 2; L.w13.seg_w[0] = dp<const void>(w1, ctx); L.w13.seg_w[1] = dp<const void>(w3, ctx);
+        const int fl_rows = n_ff / world;
+        L.w13.nseg = 2; L.w13.seg_w[0] = wrows(w1, rank * fl_rows, fl_rows); L.w13.seg_w[1] = wrows(w3, rank * fl_rows, fl_rows);
         L.w13.seg_rows[0] = L.w13.seg_rows[1] = n_ff; L.w13.seg_dst[0] = W.m1; L.w13.seg_dst[1] = W.m3;
-        L.w13.pro = FL_PRO_RMSNORM; L.w13.x = W.ff; L.w13.gamma = dp<const float>(d->src0, ctx); L.w13.epi = FL_EPI_STORE;
+        L.w13.pro = FL_PRO_RMSNORM; L.w13.x = W.ff; L.w13.gamma = (const float *)wfull(d->src0); L.w13.epi = FL_EPI_STORE;
         // w2: silu*mul prologue, residual epilogue
         mv_base(L.w2, (int)w2->type, n_ff);
-        L.w2.nseg = 1; L.w2.seg_w[0] = dp<const void>(w2, ctx); L.w2.seg_rows[0] = n_embd; L.w2.seg_dst[0] = xout;
+        L.w2.nseg = 1; L.w2.seg_w[0] = world == 1 ? wfull(w2) : nullptr; L.w2.seg_rows[0] = n_embd; L.w2.seg_dst[0] = xout;
         L.w2.pro = FL_PRO_SILUMUL; L.w2.x = L.w13.seg_dst[0]; L.w2.b = L.w13.seg_dst[1]; L.w2.epi = FL_EPI_RESADD; L.w2.res = L.w13.x;
         if (world > 1) {
             // ---- tensor-parallel wiring: wq/wk/wv/w1/w3 row-split by heads / n_ff slices, wo/w2 K-split,
             // fp32 all-reduce of n_embd after wo and after w2; the residual adds move into the next prologue (xadd).
-            PM(n_head % world == 0 && n_ff % (32 * world) == 0 && (n_embd / world) % 32 == 0);
             const int nl = n_embd / world, fl = n_ff / world;
-            const size_t rb_e = (size_t)(n_embd / 32) * k_tsize[wq->type];          // dense row bytes, K = n_embd
             L.part1 = W.part1; L.part2 = W.part2;
             L.kcache += (size_t)rank * nl; L.vcache += (size_t)rank * nl * n_ctx;   // this rank's heads
-            for (int i = 0; i < 3; i++) { L.qkv.seg_w[i] = (const char *)L.qkv.seg_w[i] + (size_t)rank * nl * rb_e; L.qkv.seg_rows[i] = nl; }
+            for (int i = 0; i < 3; i++) L.qkv.seg_rows[i] = nl;                         // seg_w[] already point at this rank's rows (wrows)
             L.qkv.kcache = (float *)L.kcache; L.qkv.vcache = (float *)L.vcache;
             if (il == 0) { L.qkv.x = W.xa; }
             else { L.qkv.x = W.part2; L.qkv.xadd = W.ff; L.qkv.sum_out = W.xa; }    // x_l = w2 partial sum + ff of the previous layer
             size_t st = 0;
             mv_base(L.wo, (int)wo->type, nl);
-            L.wo.nseg = 1; L.wo.seg_w[0] = packed_shard(wo, dp<const void>(wo, ctx), rank * (nl / 32), nl / 32, st); L.wo.row_stride_bytes = st;
+            L.wo.nseg = 1; L.wo.seg_w[0] = tp_shard(wo, SH_COLS, rank * (nl / 32), nl / 32, &st); L.wo.row_stride_bytes = st;
             L.wo.seg_rows[0] = n_embd; L.wo.seg_dst[0] = W.part1; L.wo.pro = FL_PRO_PLAIN; L.wo.x = W.att; L.wo.epi = FL_EPI_STORE;
-            const size_t rb1 = (size_t)(n_embd / 32) * k_tsize[w1->type];
-            L.w13.seg_w[0] = (const char *)L.w13.seg_w[0] + (size_t)rank * fl * rb1; L.w13.seg_w[1] = (const char *)L.w13.seg_w[1] + (size_t)rank * fl * rb1;
             L.w13.seg_rows[0] = L.w13.seg_rows[1] = fl;
             L.w13.x = W.part1; L.w13.xadd = W.xa; L.w13.sum_out = W.ff;              // ff = wo partial sum + x
             mv_base(L.w2, (int)w2->type, fl);
-            L.w2.nseg = 1; L.w2.seg_w[0] = packed_shard(w2, dp<const void>(w2, ctx), rank * (fl / 32), fl / 32, st); L.w2.row_stride_bytes = st;
+            L.w2.nseg = 1; L.w2.seg_w[0] = tp_shard(w2, SH_COLS, rank * (fl / 32), fl / 32, &st); L.w2.row_stride_bytes = st;
             L.w2.seg_rows[0] = n_embd; L.w2.seg_dst[0] = W.part2; L.w2.pro = FL_PRO_SILUMUL; L.w2.x = W.m1; L.w2.b = W.m3; L.w2.epi = FL_EPI_STORE;
         }
         x = xo;
@@ -1261,16 +1317,15 @@ bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, Decode
     PM(c.ok && c.i == g->n_nodes && e->src0 == x && f->src1 == e && is_vec(f->src0, n_embd) && is_qw(lg->src0) && lg->src1 == f &&
        lg->src0->ne[0] == n_embd && lg->src0->ne[1] % 2 == 0 && fl_dev_mv_fused_supported((int)lg->src0->type, n_embd, (int)lg->src0->ne[1]));
     mv_base(P.head, (int)lg->src0->type, n_embd);
-    P.head.nseg = 1; P.head.seg_w[0] = dp<const void>(lg->src0, ctx); P.head.seg_rows[0] = (int)lg->src0->ne[1]; P.head.seg_dst[0] = W.logits;
+    P.head.nseg = 1; P.head.seg_w[0] = wrows(lg->src0, rank * (int)(lg->src0->ne[1] / world), (int)(lg->src0->ne[1] / world)); P.head.seg_rows[0] = (int)lg->src0->ne[1]; P.head.seg_dst[0] = W.logits;
     PM(W.n_vocab == (int)lg->src0->ne[1] && is_vec(lg, W.n_vocab) && is_vec(f, n_embd));
-    P.head.pro = FL_PRO_RMSNORM; P.head.x = xin; P.head.gamma = dp<const float>(f->src0, ctx); P.head.normed_out = W.emb;
+    P.head.pro = FL_PRO_RMSNORM; P.head.x = xin; P.head.gamma = (const float *)wfull(f->src0); P.head.normed_out = W.emb;
     O.logits_host = lg->data; O.logits_bytes = (size_t)W.n_vocab * 4; O.emb_host = f->data; O.emb_bytes = (size_t)n_embd * 4;
     P.world = world; P.heads_local = n_head / world;
     if (world > 1) {
         PM(W.n_vocab % (2 * world) == 0);
         const int vl = W.n_vocab / world;
-        const size_t rbv = (size_t)(n_embd / 32) * k_tsize[lg->src0->type];
-        P.head.seg_w[0] = (const char *)P.head.seg_w[0] + (size_t)rank * vl * rbv; P.head.seg_rows[0] = vl; P.head.seg_dst[0] = W.logits_local;
+        P.head.seg_rows[0] = vl; P.head.seg_dst[0] = W.logits_local;                 // seg_w[0] already points at this rank's rows
         P.head.x = W.part2; P.head.xadd = W.ff;                                    // final residual add of the last layer
         P.vocab_local = vl; P.logits_local = W.logits_local; P.logits_all = W.logits;
     }
@@ -1339,24 +1394,29 @@ void *make_token_plan(const DecodePlan &P, const DecodeWs &W, const int *d_npast
     // tensor parallel: a K-split step also pushes its partial sums into the other ranks' buffers, and a step that used
     // to read the all-reduced vector reads the ranks' slots of the LOCAL buffer instead, in rank order
     const int rank = fl_comm_rank();
-    auto slot0 = [&](const float *mine) { return (const char *)mine - (size_t)rank * W.n_embd * sizeof(float); };   // slot of rank 0 in my buffer
+    // which[0] = the reduction after wo (W.part1), which[1] = after w2 (W.part2); slot r of reduction k inside rank q's buffer:
+    auto slot = [&](int q, int k, int r) { return (char *)W.peers[q] + 4096 + ((size_t)k * P.world + r) * W.ll_slot_bytes; };
+    int ll_next = 0, ll_last[2] = {-1, -1};
     auto mv = [&](const fl_mv_args &a0) {
         fl_token_step s;
         memset(&s, 0, sizeof(s));
         s.kind = 0;
         s.mv = a0;
-        if (P.world > 1 && (a0.x == W.part1 || a0.x == W.part2)) {
-            const char *base = slot0(a0.x);
-            s.mv.x = (const float *)base;
-            for (int r = 1; r < P.world; r++) s.mv.xpeer[r - 1] = (const float *)(base + (size_t)r * W.n_embd * sizeof(float));
+        const int kin = a0.x == W.part1 ? 0 : a0.x == W.part2 ? 1 : -1;
+        if (P.world > 1 && kin >= 0) {                       // consumer of an all-reduced vector: the ranks' slots of MY buffer, rank order
+            s.mv.x = (const float *)slot(rank, kin, 0);
+            for (int r = 1; r < P.world; r++) s.mv.xpeer[r - 1] = (const float *)slot(rank, kin, r);
             s.mv.n_xpeer = P.world - 1;
+            if (W.use_ll) { s.mv.ll = 1; s.mv.ll_seq = ll_last[kin]; }
         }
-        if (P.world > 1 && a0.nseg == 1 && (a0.seg_dst[0] == W.part1 || a0.seg_dst[0] == W.part2)) {
-            const size_t off = (const char *)a0.seg_dst[0] - (const char *)W.peers[rank];
+        const int kout = (a0.nseg == 1 && a0.seg_dst[0] == W.part1) ? 0 : (a0.nseg == 1 && a0.seg_dst[0] == W.part2) ? 1 : -1;
+        if (P.world > 1 && kout >= 0) {                      // K-split step: slot `rank` of every rank's buffer
+            s.mv.seg_dst[0] = (float *)slot(rank, kout, rank);
             int n = 0;
             for (int r = 0; r < P.world; r++)
-                if (r != rank) s.mv.dst_peer[n++] = (float *)((char *)W.peers[r] + off);
+                if (r != rank) s.mv.dst_peer[n++] = (float *)slot(r, kout, rank);
             s.mv.n_dst_peer = n;
+            if (W.use_ll) { s.mv.ll = 1; s.mv.ll_seq = ll_next; ll_last[kout] = ll_next++; }
         }
         steps.push_back(s);
     };

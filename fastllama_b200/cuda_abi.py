@@ -43,7 +43,7 @@ class FlMvArgs(C.Structure):          # struct fl_mv_args, include/fl_cuda.h
                 ("normed_out", C.c_void_p), ("xadd", C.c_void_p), ("sum_out", C.c_void_p), ("row_stride_bytes", C.c_size_t),
                 ("silu_tab", C.c_void_p), ("epi", C.c_int), ("res", C.c_void_p), ("n_past", C.c_void_p),
                 ("n_ctx", C.c_int), ("n_embd", C.c_int), ("head_dim", C.c_int), ("rope_cs", C.c_void_p), ("kcache", C.c_void_p),
-                ("vcache", C.c_void_p), ("xpeer", C.c_void_p * 7), ("n_xpeer", C.c_int), ("dst_peer", C.c_void_p * 7), ("n_dst_peer", C.c_int)]
+                ("vcache", C.c_void_p), ("xpeer", C.c_void_p * 7), ("n_xpeer", C.c_int), ("dst_peer", C.c_void_p * 7), ("n_dst_peer", C.c_int), ("ll", C.c_int), ("ll_seq", C.c_int)]
 
 
 class FlTokenStep(C.Structure):       # struct fl_token_step, include/fl_cuda.h

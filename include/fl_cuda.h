@@ -187,6 +187,13 @@ typedef struct fl_mv_args {
     int n_xpeer;
     float *dst_peer[7];
     int n_dst_peer;
+    /* ll != 0: the reduction buffers of this step are in "LL" form -- every float travels with an epoch in one 8-byte word
+     * {value, epoch}, so arrival is detected per element and NO barrier (local or cross-GPU) separates the K-split step from its
+     * consumer.  Producer (n_dst_peer > 0): seg_dst[0] and dst_peer[] are LL slots (8 bytes per row).  Consumer (n_xpeer > 0): x and
+     * xpeer[] are LL slots; it polls until every element carries this token's epoch for reduction number ll_seq (the library keeps
+     * the running epoch next to the buffers), then adds the slots in rank order. */
+    int ll;
+    int ll_seq;
 } fl_mv_args;
 int fl_dev_mv_fused_supported(int type, int K, int mtot);
 int fl_dev_mv_fused(const fl_mv_args *args);

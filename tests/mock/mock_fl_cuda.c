@@ -299,9 +299,10 @@ static void run_mv(const fl_mv_args *a) {
     const int K = a->K, nb = K / 32, bb = a->type == 2 ? 20 : 24;
     const size_t rstride = a->row_stride_bytes ? a->row_stride_bytes : (size_t)nb * bb;
     float *v = malloc(sizeof(float) * K), *xin = malloc(sizeof(float) * K);
+    const int ist = (a->ll && a->n_xpeer > 0) ? 2 : 1;                      /* LL slots: {value, epoch} words */
     for (int i = 0; i < K; i++) {
-        float t = a->x[i];
-        for (int r = 0; r < a->n_xpeer; r++) t += a->xpeer[r][i];          /* the ranks' slots, rank order */
+        float t = a->x[ist * i];
+        for (int r = 0; r < a->n_xpeer; r++) t += a->xpeer[r][ist * i];    /* the ranks' slots, rank order */
         xin[i] = a->xadd ? t + a->xadd[i] : t;
     }
     if (a->sum_out) memcpy(a->sum_out, xin, sizeof(float) * K);
@@ -335,8 +336,9 @@ static void run_mv(const fl_mv_args *a) {
             }
         } else for (int r = 0; r < a->seg_rows[sg]; r++) {
             const float o = a->epi == FL_EPI_RESADD ? tmp[r] + a->res[r] : tmp[r];
-            a->seg_dst[sg][r] = o;
-            for (int pr = 0; pr < a->n_dst_peer; pr++) a->dst_peer[pr][r] = o;             /* push into the peers' buffers */
+            const int ost = (a->ll && a->n_dst_peer > 0) ? 2 : 1;
+            a->seg_dst[sg][ost * r] = o;
+            for (int pr = 0; pr < a->n_dst_peer; pr++) a->dst_peer[pr][ost * r] = o;       /* push into the peers' buffers */
         }
         free(tmp);
     }
