@@ -86,29 +86,27 @@ struct um_params {
     int diag;                   // FASTLLAMA_B200_UMMA_DIAG (timing experiments only, results are garbage): 1 = no TMEM loads, 2 = no epilogue math
 };
 
-// Pipeline depth (all rings are mbarrier rings):
-//   raw stage   4 slots of UM_KC = 4 k-blocks: TMA -> {unpack warps, MMA (B tiles), epilogue (d_y / s_y and the d_w / m_w the unpack warps peel off)}
-//   A tile      UM_NA = 8 slots of one k-block: unpack warps -> MMA; freed by tcgen05.commit
-//   accumulator 4 slots of 128 TMEM columns = KG = 128 / NT k-blocks each: MMA -> epilogue; freed when the epilogue has loaded them
-// so the unpack warps run up to 8 k-blocks ahead of the tensor core and the tensor core up to 4 accumulator slots ahead of the epilogue,
-// which is the stage that limits throughput (2 CUDA-core instructions per output element and k-block).
-#define UM_NA 8
-#define UM_NACC 4
+// Synchronisation is per GROUP of KG k-blocks (KG * NT = at most 256 TMEM columns; two groups in flight = all 512 columns):
+// one a_full / acc_full / acc_empty / a_empty round per group instead of per k-block.  Measured alternatives (7B, 128 tokens, all
+// matmuls): per-k-block rounds 16.0 ms; this 9.6 ms; deeper rings (8-12 operand tiles, 4 accumulator slots of 128 columns, row scales
+// travelling with the TMA stage) 14.0 - 14.4 ms -- every extra mbarrier operation costs the single MMA-issuing thread and the
+// epilogue warps ~100 cycles, which outweighs the extra slack.
 template <int TYPE, int NT>
 struct um_layout {
     static constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
-    static constexpr int KG = 128 / NT;                                  // k-blocks per accumulator slot
+    static constexpr int KG = (NT == 128) ? 2 : 4;                       // k-blocks per accumulator group
+    static constexpr int GPS = UM_KC / KG;                               // groups per TMA stage
     static constexpr int RAW_A = UM_M * UM_KC * BB;                      // TMA box: 128 rows x KC blocks
     static constexpr int RAW_B = UM_KC * NT * 32;
     static constexpr int RAW_S = UM_KC * NT * 4;
-    static constexpr int NSC = (TYPE == FL_TYPE_Q4_1) ? 2 : 1;           // scale arrays per stage (dy [, sy]) and per row (d_w [, m_w])
-    static constexpr int OFF_DW = RAW_A + RAW_B + NSC * RAW_S;           // [NSC][UM_KC][UM_M] floats written by the unpack warps
-    static constexpr int STAGE = OFF_DW + NSC * UM_KC * UM_M * 4;
-    static constexpr int TX = RAW_A + RAW_B + NSC * RAW_S;               // bytes the TMA delivers per stage
+    static constexpr int NSC = (TYPE == FL_TYPE_Q4_1) ? 2 : 1;           // scale arrays per stage (dy [, sy])
+    static constexpr int STAGE = RAW_A + RAW_B + NSC * RAW_S;
     static constexpr int ATILE = UM_M * 32;                              // unpacked operand of one k-block
+    static constexpr int ASLOT = ATILE + NSC * UM_M * 4;                 // + d_w [, m_w] per row
+    static constexpr int AGROUP = KG * ASLOT;
     static constexpr int OFF_A = UM_STAGES * STAGE;
-    static constexpr int OFF_BAR = OFF_A + UM_NA * ATILE;
-    static constexpr int NBAR = 3 * UM_STAGES + 2 * UM_NA + 2 * UM_NACC;
+    static constexpr int OFF_BAR = OFF_A + 2 * AGROUP;
+    static constexpr int NBAR = 2 * UM_STAGES + 8;
     static constexpr int SMEM = OFF_BAR + NBAR * 8 + 16;
     static constexpr int CPT = NT / 2;                                   // columns per epilogue thread
     static constexpr int TCOLS = 512;
@@ -151,7 +149,7 @@ __global__ void k_umma_prep(const fl_block_q8_0 *__restrict__ Y, int N, int nb, 
 template <int TYPE, int NT>
 __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_constant__ CUtensorMap tmap_w, const um_params prm) {
     using L = um_layout<TYPE, NT>;
-    constexpr int BB = L::BB, KG = L::KG;
+    constexpr int BB = L::BB, KG = L::KG, GPS = L::GPS;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_base_sh;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,29 +159,24 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
 
     const uint32_t sm0 = fl_smem_u32(smem);
     const uint32_t bar0 = sm0 + L::OFF_BAR;
+    // barrier map (8 bytes each); g = accumulator / operand group slot (0, 1)
     auto raw_full = [&](int s) { return bar0 + 8u * s; };
     auto raw_empty = [&](int s) { return bar0 + 8u * (UM_STAGES + s); };
-    auto dw_full = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + s); };
-    auto a_full = [&](int t) { return bar0 + 8u * (3 * UM_STAGES + t); };
-    auto a_empty = [&](int t) { return bar0 + 8u * (3 * UM_STAGES + UM_NA + t); };
-    auto acc_full = [&](int a) { return bar0 + 8u * (3 * UM_STAGES + 2 * UM_NA + a); };
-    auto acc_empty = [&](int a) { return bar0 + 8u * (3 * UM_STAGES + 2 * UM_NA + UM_NACC + a); };
+    auto a_full = [&](int g) { return bar0 + 8u * (2 * UM_STAGES + g); };
+    auto a_empty = [&](int g) { return bar0 + 8u * (2 * UM_STAGES + 2 + g); };
+    auto acc_full = [&](int g) { return bar0 + 8u * (2 * UM_STAGES + 4 + g); };
+    auto acc_empty = [&](int g) { return bar0 + 8u * (2 * UM_STAGES + 6 + g); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < UM_STAGES; s++) {
             fl_mbar_init(raw_full(s), 1);
-            // unpack warps (raw weights in registers) + epilogue warps (scales read; they only let go after the accumulators of the stage's
-            // last k-block arrived, i.e. after every MMA that reads the stage's B tiles has completed)
-            fl_mbar_init(raw_empty(s), UM_UNPACK_WARPS + UM_EPI_WARPS);
-            fl_mbar_init(dw_full(s), UM_UNPACK_WARPS);
+            fl_mbar_init(raw_empty(s), UM_UNPACK_WARPS + UM_EPI_WARPS);     // the MMAs that read a stage's B tiles are complete before the epilogue lets go of it
         }
-        for (int t = 0; t < UM_NA; t++) {
-            fl_mbar_init(a_full(t), UM_UNPACK_WARPS);
-            fl_mbar_init(a_empty(t), 1);                                    // tcgen05.commit
-        }
-        for (int a = 0; a < UM_NACC; a++) {
-            fl_mbar_init(acc_full(a), 1);                                   // tcgen05.commit
-            fl_mbar_init(acc_empty(a), UM_EPI_WARPS);
+        for (int g = 0; g < 2; g++) {
+            fl_mbar_init(a_full(g), UM_UNPACK_WARPS);
+            fl_mbar_init(a_empty(g), UM_EPI_WARPS);                         // same: the epilogue has waited for the group's MMAs
+            fl_mbar_init(acc_full(g), 1);
+            fl_mbar_init(acc_empty(g), UM_EPI_WARPS);
         }
         fl_mbar_fence_init();
     }
@@ -202,51 +195,47 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
         for (int st = 0; st < nstages; st++) {
             const int s = st % UM_STAGES;
             um_wait(raw_full(s), (uint32_t)(st / UM_STAGES) & 1u);
-            uint8_t *stage = smem + (size_t)s * L::STAGE;
             // this row's KC blocks: 80 (q4_0) / 96 (q4_1) contiguous bytes, 16-byte aligned
             uint32_t w[UM_KC * BB / 4];
-            const uint4 *src = (const uint4 *)(stage + (size_t)r * (UM_KC * BB));
+            const uint4 *src = (const uint4 *)(smem + (size_t)s * L::STAGE + (size_t)r * (UM_KC * BB));
 #pragma unroll
             for (int i = 0; i < UM_KC * BB / 16; i++) {
                 const uint4 v = src[i];
                 w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
             }
-            constexpr int WPB = BB / 4;                            // words per block
-            constexpr int QOFF = WPB - 4;                          // first qs word
-            // the per-row block scales of the whole stage, for the epilogue warps
-            float *dw = (float *)(stage + L::OFF_DW);
-#pragma unroll
-            for (int kbi = 0; kbi < UM_KC; kbi++) {
-                dw[kbi * UM_M + r] = __uint_as_float(w[kbi * WPB]);
-                if (TYPE == FL_TYPE_Q4_1) dw[(UM_KC + kbi) * UM_M + r] = __uint_as_float(w[kbi * WPB + 1]);
-            }
             __syncwarp();
-            if (lane == 0) {
-                fl_mbar_arrive(dw_full(s));
-                fl_mbar_arrive(raw_empty(s));                      // the raw weights of this stage are in registers
-            }
+            if (lane == 0) fl_mbar_arrive(raw_empty(s));          // the raw weights of this stage are in registers
 #pragma unroll
-            for (int kbi = 0; kbi < UM_KC; kbi++) {
-                const int kb = st * UM_KC + kbi;
-                const int t = kb % UM_NA;
-                um_wait(a_empty(t), ((uint32_t)(kb / UM_NA) & 1u) ^ 1u);
-                uint8_t *slot = smem + L::OFF_A + (size_t)t * L::ATILE;
-                uint32_t lo[4], hi[4];
+            for (int gs = 0; gs < GPS; gs++) {
+                const int gi = st * GPS + gs;                      // group index; slot gi & 1, use gi >> 1
+                const int g = gi & 1;
+                um_wait(a_empty(g), ((uint32_t)(gi >> 1) & 1u) ^ 1u);
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t q = w[kbi * WPB + QOFF + j];
-                    lo[j] = q & 0x0F0F0F0Fu;
-                    hi[j] = (q >> 4) & 0x0F0F0F0Fu;
-                    if (TYPE == FL_TYPE_Q4_0) {                    // (x - 8) as s8, per byte, no carries: (x + 0x78) ^ 0x80
-                        lo[j] = (lo[j] + 0x78787878u) ^ 0x80808080u;
-                        hi[j] = (hi[j] + 0x78787878u) ^ 0x80808080u;
+                for (int i = 0; i < KG; i++) {
+                    const int kbi = gs * KG + i;
+                    uint8_t *slot = smem + L::OFF_A + (size_t)g * L::AGROUP + (size_t)i * L::ASLOT;
+                    constexpr int WPB = BB / 4;                    // words per block
+                    constexpr int QOFF = WPB - 4;                  // first qs word
+                    uint32_t lo[4], hi[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t q = w[kbi * WPB + QOFF + j];
+                        lo[j] = q & 0x0F0F0F0Fu;
+                        hi[j] = (q >> 4) & 0x0F0F0F0Fu;
+                        if (TYPE == FL_TYPE_Q4_0) {                // (x - 8) as s8, per byte, no carries: (x + 0x78) ^ 0x80
+                            lo[j] = (lo[j] + 0x78787878u) ^ 0x80808080u;
+                            hi[j] = (hi[j] + 0x78787878u) ^ 0x80808080u;
+                        }
                     }
+                    *(uint4 *)(slot + (size_t)r * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);                 // k = 0..15: low nibbles = even elements
+                    *(uint4 *)(slot + (size_t)UM_M * 16 + (size_t)r * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);   // k = 16..31: high nibbles = odd elements
+                    float *dw = (float *)(slot + L::ATILE);
+                    dw[r] = __uint_as_float(w[kbi * WPB]);
+                    if (TYPE == FL_TYPE_Q4_1) dw[UM_M + r] = __uint_as_float(w[kbi * WPB + 1]);
                 }
-                *(uint4 *)(slot + (size_t)r * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);                 // k = 0..15: low nibbles = even elements
-                *(uint4 *)(slot + (size_t)UM_M * 16 + (size_t)r * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);   // k = 16..31: high nibbles = odd elements
                 um_fence_proxy_async();                            // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) fl_mbar_arrive(a_full(t));
+                if (lane == 0) fl_mbar_arrive(a_full(g));
             }
         }
     } else if (warp < UM_UNPACK_WARPS + UM_EPI_WARPS) {
@@ -265,67 +254,70 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
         for (int j = 0; j < ((TYPE == FL_TYPE_Q4_1) ? CPT / 2 : 1); j++) accm[j] = make_float2(0.f, 0.f);
         for (int st = 0; st < nstages; st++) {
             const int s = st % UM_STAGES;
-            const uint32_t spar = (uint32_t)(st / UM_STAGES) & 1u;
-            um_wait(raw_full(s), spar);                            // the stage's d_y / s_y have landed
-            um_wait(dw_full(s), spar);                             // and the unpack warps have peeled off its d_w / m_w
-            const uint8_t *stage = smem + (size_t)s * L::STAGE;
-            const float *dys = (const float *)(stage + L::RAW_A + L::RAW_B);
-            const float *dws = (const float *)(stage + L::OFF_DW);
+            um_wait(raw_full(s), (uint32_t)(st / UM_STAGES) & 1u);          // the stage's d_y / s_y have landed
+            const float *dys = (const float *)(smem + (size_t)s * L::STAGE + L::RAW_A + L::RAW_B);
+#pragma unroll 1
+            for (int gs = 0; gs < GPS; gs++) {
+                const int gi = st * GPS + gs;
+                const int g = gi & 1;
+                const uint32_t par = (uint32_t)(gi >> 1) & 1u;
+                um_wait(a_full(g), par);                           // acquire the unpack warps' d_w stores
+                um_wait(acc_full(g), par);
+                um_tc_fence_after();
 #pragma unroll
-            for (int kbi = 0; kbi < UM_KC; kbi++) {
-                const int kb = st * UM_KC + kbi;
-                const int gi = kb / KG, a = gi % UM_NACC, i = kb % KG;          // accumulator slot and position inside it
-                if (i == 0) {
-                    um_wait(acc_full(a), (uint32_t)(gi / UM_NACC) & 1u);
-                    um_tc_fence_after();
+                for (int i = 0; i < KG; i++) {
+                    const int kbi = gs * KG + i;
+                    const float *dwp = (const float *)(smem + L::OFF_A + (size_t)g * L::AGROUP + (size_t)i * L::ASLOT + L::ATILE);
+                    const float dwm = dwp[row];
+                    const float2 dw2 = make_float2(dwm, dwm);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 256 + i * NT + c0);
+#pragma unroll
+                    for (int ch = 0; ch < CPT / CW; ch++) {
+                        uint32_t v[CW];
+                        if (prm.diag & 1) {
+#pragma unroll
+                            for (int c = 0; c < CW; c++) v[c] = (uint32_t)(c + kbi);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < CW / 16; c++) UM_LD16(taddr + (uint32_t)(ch * CW + 16 * c), (&v[16 * c]));
+                            um_wait_ld();
+                        }
+                        if (i == KG - 1 && ch == CPT / CW - 1) {   // every column of the group's accumulators is in registers: hand them back
+                            um_tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) fl_mbar_arrive(acc_empty(g));
+                        }
+                        const float4 *dy4 = (const float4 *)(dys + kbi * NT + c0 + ch * CW);
+                        if (prm.diag & 2) { if (v[0] == 0x7fffffffu) acc[0].x += 1.f; continue; }
+#pragma unroll
+                        for (int j = 0; j < CW / 4; j++) {
+                            const float4 d4 = dy4[j];
+                            // packed fp32 (FMUL2 / FFMA2): element-wise IEEE round-to-nearest, the same results as the scalar forms
+                            const float2 s01 = __fmul2_rn(dw2, make_float2(d4.x, d4.y)), s23 = __fmul2_rn(dw2, make_float2(d4.z, d4.w));
+                            const float2 i01 = make_float2(__int2float_rn((int)v[4 * j + 0]), __int2float_rn((int)v[4 * j + 1]));
+                            const float2 i23 = make_float2(__int2float_rn((int)v[4 * j + 2]), __int2float_rn((int)v[4 * j + 3]));
+                            float2 *a = acc + (ch * CW + 4 * j) / 2;
+                            a[0] = __ffma2_rn(s01, i01, a[0]);
+                            a[1] = __ffma2_rn(s23, i23, a[1]);
+                        }
+                    }
+                    if (TYPE == FL_TYPE_Q4_1) {
+                        const float mwm = dwp[UM_M + row];
+                        const float2 mw2 = make_float2(mwm, mwm);
+                        const float4 *sy4 = (const float4 *)(dys + UM_KC * NT + kbi * NT + c0);
+#pragma unroll
+                        for (int j = 0; j < CPT / 4; j++) {
+                            const float4 s4 = sy4[j];
+                            accm[2 * j] = __ffma2_rn(mw2, make_float2(s4.x, s4.y), accm[2 * j]);
+                            accm[2 * j + 1] = __ffma2_rn(mw2, make_float2(s4.z, s4.w), accm[2 * j + 1]);
+                        }
+                    }
                 }
-                const float dwm = dws[kbi * UM_M + row];
-                const float2 dw2 = make_float2(dwm, dwm);
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * 128 + i * NT + c0);
-#pragma unroll
-                for (int ch = 0; ch < CPT / CW; ch++) {
-                    uint32_t v[CW];
-                    if (prm.diag & 1) {
-#pragma unroll
-                        for (int c = 0; c < CW; c++) v[c] = (uint32_t)(c + kbi);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < CW / 16; c++) UM_LD16(taddr + (uint32_t)(ch * CW + 16 * c), (&v[16 * c]));
-                        um_wait_ld();
-                    }
-                    if (i == KG - 1 && ch == CPT / CW - 1) {       // every column of the slot's accumulators is in registers: hand it back
-                        um_tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) fl_mbar_arrive(acc_empty(a));
-                    }
-                    const float4 *dy4 = (const float4 *)(dys + kbi * NT + c0 + ch * CW);
-                    if (prm.diag & 2) { if (v[0] == 0x7fffffffu) acc[0].x += 1.f; continue; }
-#pragma unroll
-                    for (int j = 0; j < CW / 4; j++) {
-                        const float4 d4 = dy4[j];
-                        // packed fp32 (FMUL2 / FFMA2): element-wise IEEE round-to-nearest, the same results as the scalar forms
-                        const float2 s01 = __fmul2_rn(dw2, make_float2(d4.x, d4.y)), s23 = __fmul2_rn(dw2, make_float2(d4.z, d4.w));
-                        const float2 i01 = make_float2(__int2float_rn((int)v[4 * j + 0]), __int2float_rn((int)v[4 * j + 1]));
-                        const float2 i23 = make_float2(__int2float_rn((int)v[4 * j + 2]), __int2float_rn((int)v[4 * j + 3]));
-                        float2 *ac = acc + (ch * CW + 4 * j) / 2;
-                        ac[0] = __ffma2_rn(s01, i01, ac[0]);
-                        ac[1] = __ffma2_rn(s23, i23, ac[1]);
-                    }
-                }
-                if (TYPE == FL_TYPE_Q4_1) {
-                    const float mwm = dws[(UM_KC + kbi) * UM_M + row];
-                    const float2 mw2 = make_float2(mwm, mwm);
-                    const float4 *sy4 = (const float4 *)(dys + UM_KC * NT + kbi * NT + c0);
-#pragma unroll
-                    for (int j = 0; j < CPT / 4; j++) {
-                        const float4 s4 = sy4[j];
-                        accm[2 * j] = __ffma2_rn(mw2, make_float2(s4.x, s4.y), accm[2 * j]);
-                        accm[2 * j + 1] = __ffma2_rn(mw2, make_float2(s4.z, s4.w), accm[2 * j + 1]);
-                    }
-                }
+                __syncwarp();
+                if (lane == 0) fl_mbar_arrive(a_empty(g));         // d_w / m_w of the group have been read (and its MMAs are long complete)
             }
             __syncwarp();
-            if (lane == 0) fl_mbar_arrive(raw_empty(s));           // scales of the stage have been read (and its MMAs are complete)
+            if (lane == 0) fl_mbar_arrive(raw_empty(s));           // d_y / s_y of the stage have been read
         }
         // store: column n of the output is M contiguous floats; a warp writes 32 consecutive rows of one column
         if (m0 + row < prm.M) {
@@ -333,9 +325,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
             for (int j = 0; j < CPT; j++) {
                 const int col = n0 + c0 + j;
                 if (col < prm.N) {
-                    const float av = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
-                    float o = av;
-                    if (TYPE == FL_TYPE_Q4_1) o = __fadd_rn(av, (j & 1) ? accm[j / 2].y : accm[j / 2].x);
+                    const float a = (j & 1) ? acc[j / 2].y : acc[j / 2].x;
+                    float o = a;
+                    if (TYPE == FL_TYPE_Q4_1) o = __fadd_rn(a, (j & 1) ? accm[j / 2].y : accm[j / 2].x);
                     prm.dst[(size_t)col * prm.dst_row_stride + (size_t)(m0 + row)] = o;
                 }
             }
@@ -351,7 +343,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
                 um_wait(raw_empty(s), ((uint32_t)(st / UM_STAGES) & 1u) ^ 1u);
                 const uint32_t dst = sm0 + (uint32_t)(s * L::STAGE);
                 const int kb0 = st * UM_KC;
-                fl_mbar_expect_tx(raw_full(s), (uint32_t)L::TX);
+                fl_mbar_expect_tx(raw_full(s), (uint32_t)L::STAGE);
                 um_tma_2d(dst, &tmap_w, kb0 * (BB / 4), m0, raw_full(s));                                   // 128 rows x KC blocks of raw q4
                 fl_bulk_g2s(dst + L::RAW_A, yq + (size_t)kb0 * (NT * 32), (uint32_t)L::RAW_B, raw_full(s));
                 fl_bulk_g2s(dst + L::RAW_A + L::RAW_B, dy + (size_t)kb0 * NT, (uint32_t)L::RAW_S, raw_full(s));
@@ -367,18 +359,21 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_mul_mat_q_umma(const __grid_c
                 const int s = st % UM_STAGES;
                 um_wait(raw_full(s), (uint32_t)(st / UM_STAGES) & 1u);
                 const uint32_t bstage = sm0 + (uint32_t)(s * L::STAGE + L::RAW_A);
-#pragma unroll
-                for (int kbi = 0; kbi < UM_KC; kbi++) {
-                    const int kb = st * UM_KC + kbi;
-                    const int t = kb % UM_NA, gi = kb / KG, a = gi % UM_NACC, i = kb % KG;
-                    um_wait(a_full(t), (uint32_t)(kb / UM_NA) & 1u);
-                    if (i == 0) um_wait(acc_empty(a), ((uint32_t)(gi / UM_NACC) & 1u) ^ 1u);
+                for (int gs = 0; gs < GPS; gs++) {
+                    const int gi = st * GPS + gs;
+                    const int g = gi & 1;
+                    const uint32_t par = (uint32_t)(gi >> 1) & 1u;
+                    um_wait(a_full(g), par);
+                    um_wait(acc_empty(g), par ^ 1u);
                     um_tc_fence_after();
-                    const uint64_t adesc = um_smem_desc(sm0 + (uint32_t)(L::OFF_A + t * L::ATILE), UM_M * 16, 128);
-                    const uint64_t bdesc = um_smem_desc(bstage + (uint32_t)(kbi * NT * 32), NT * 16, 128);
-                    um_mma_i8(tmem_base + (uint32_t)(a * 128 + i * NT), adesc, bdesc, idesc);
-                    um_commit(a_empty(t));                         // the operand tile may be overwritten once this MMA has read it
-                    if (i == KG - 1) um_commit(acc_full(a));       // arrives when every MMA of the slot (and everything before) is complete
+#pragma unroll
+                    for (int i = 0; i < KG; i++) {
+                        const int kbi = gs * KG + i;
+                        const uint64_t adesc = um_smem_desc(sm0 + (uint32_t)(L::OFF_A + g * L::AGROUP + i * L::ASLOT), UM_M * 16, 128);
+                        const uint64_t bdesc = um_smem_desc(bstage + (uint32_t)(kbi * NT * 32), NT * 16, 128);
+                        um_mma_i8(tmem_base + (uint32_t)(g * 256 + i * NT), adesc, bdesc, idesc);
+                    }
+                    um_commit(acc_full(g));                        // arrives when the group's MMAs (and everything before them) are complete
                 }
             }
         }

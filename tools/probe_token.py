@@ -139,5 +139,5 @@ for i, nm in enumerate(names):
 for nm, rows in agg2.items():
     r = np.array(rows).mean(axis=0)
     per = (r[2] / r[4], r[3] / r[4]) if r[4] else (0, 0)
-    print(f"{nm:>5}: yfetch {r[0]:7.0f}  wait {r[1]:7.0f}  dots {r[2]:7.0f}  tail {r[3]:7.0f}  rounds {r[4]:5.2f}  total {r[5]:7.0f}  tiles/CTA {r[6]:5.1f}   per round: dots {per[0]:6.0f} tail {per[1]:6.0f}")
+    print(f"{nm:>5}: yfetch {r[0]:7.0f}  wait {r[1]:7.0f}  dots {r[2]:7.0f}  tail {r[3]:7.0f}  rounds {r[4]:5.2f}  total {r[5]:7.0f}  tiles/warp {r[6]:5.1f}  wait of round 1 {r[7]:6.0f}   per round: dots {per[0]:6.0f} tail {per[1]:6.0f}")
 fl.check(fl.lib.fl_token_plan_destroy(plan))
