@@ -46,7 +46,6 @@ struct tk_phase {
     int nb, kparts, G, lgG, P, nfull;
     int swiglu;                  // pair = (seg 0 row u, seg 1 row u); epilogue writes silu(a) * b to seg_dst[0][u]
     int units[3];                // pairs per segment (swiglu: one segment of seg_rows[0] pairs)
-    int gt[3];                   // cumulative tile counts over the segments (tiles of G units that never straddle a segment); gt[2] = tiles of the phase
     uint32_t row_bytes;
     fl_mv_args a;
     // attention
@@ -61,7 +60,6 @@ struct tk_params {
     const tk_phase *phases;
     int n_phases;
     unsigned *grid_bar;              // [0] arrival counter (zeroed per launch)
-    unsigned *tile_ctr;              // [n_phases] next unclaimed tile of every phase (zeroed per launch): tiles are handed out dynamically
     unsigned *err;                   // error block in pinned, device-mapped HOST memory: [0] flag, [1..4] details (the host reads it without a copy)
     unsigned *xflags_local;          // tensor parallel: flags[q * 32] is written by rank q (through its peer mapping of this buffer)
     unsigned *xflags_peer[8];        // rank p's flag array as mapped here
@@ -77,7 +75,7 @@ struct tk_params {
     uint32_t slot_bytes;
     int l2_prefetch;
     int diag;                        // FASTLLAMA_B200_TK_DIAG (timing experiments only; results are garbage): 1 = no weight copies, 2 = no dot products, 4 = no grid barriers, 8 = no prologue
-    uint32_t off_y, off_red, off_rowbuf, off_cnt, off_sc, off_desc, off_stage0;
+    uint32_t off_y, off_red, off_rowbuf, off_cnt, off_sc, off_stage0;
 };
 
 __device__ __forceinline__ unsigned long long tk_now() {
@@ -294,6 +292,19 @@ __device__ __forceinline__ void tk_quant(const float v[E], int u, bool valid, tk
 template <int E>
 __device__ __forceinline__ void tk_prologue_nonorm(const fl_mv_args &A, int K, tk_yblock *ysm, int warp, int tid, unsigned lle, unsigned *err) {
     const int nu = K / E;
+    if (E == 16 && A.pro != FL_PRO_SILUMUL && nu > TK_NT && nu <= 2 * TK_NT) {
+        // two units per thread (K = 11008: 688 half blocks on 512 threads), BOTH loads in flight before either is quantised: one L2
+        // round trip instead of two on the critical path behind the grid barrier
+        const int ua = tid, ub = tid + TK_NT;
+        const bool vb = ub < nu, wb = TK_NT + warp * 32 < nu;          // wb: warp-uniform
+        float va[E], vv[E];
+        tk_load_x<E>(A, ua, va, lle, err);
+        if (vb) tk_load_x<E>(A, ub, vv, lle, err); else tk_zero_vals<E>(vv);
+        if (A.sum_out && blockIdx.x == 0) { tk_store_vals<E>(A.sum_out, ua, va); if (vb) tk_store_vals<E>(A.sum_out, ub, vv); }
+        tk_quant<E>(va, ua, true, ysm);
+        if (wb) tk_quant<E>(vv, ub, vb, ysm);
+        return;
+    }
     for (int u0 = 0; u0 < nu; u0 += TK_NT) {
         if (u0 + warp * 32 >= nu) break;                 // warp-uniform
         const int u = u0 + tid;
@@ -452,15 +463,6 @@ __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, 
     for (int r = 0; r < A.n_dst_peer; r++) *(float2 *)(A.dst_peer[r] + r2) = make_float2(a, b);     // posted stores over NVLink
 }
 
-// tile tau of a phase -> segment, first unit, units (tiles of G units that never straddle a segment)
-__device__ __forceinline__ void tk_tile_global(int gt0, int gt1, int m0, int m1, int m2, int lgG, int tau, int &seg, int &unit0, int &nunits) {
-    seg = (tau < gt0) ? 0 : (tau < gt1) ? 1 : 2;
-    const int j = tau - (seg == 0 ? 0 : seg == 1 ? gt0 : gt1);
-    const int n = seg == 0 ? m0 : seg == 1 ? m1 : m2;
-    unit0 = j << lgG;
-    nunits = min(1 << lgG, n - unit0);
-}
-
 // ---- main loop of a matvec phase for one consumer warp ------------------------------------------------
 __device__ __forceinline__ unsigned tk_clock() {
     unsigned c;
@@ -468,9 +470,9 @@ __device__ __forceinline__ unsigned tk_clock() {
     return c;
 }
 template <int TYPE, int NFULL, bool PROF>
-__device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const int4 *sdesc, int &ks, uint32_t &kpar, unsigned &kround, const tk_yblock *ysm,
+__device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, unsigned &kround, const tk_yblock *ysm,
                                            float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw, unsigned lle) {
-    unsigned c_begin = 0, c_wait = 0, c_dot = 0, c_tail = 0, c_rounds = 0, c_t = 0, c_yp = 0, c_wait1 = 0;
+    unsigned c_begin = 0, c_wait = 0, c_dot = 0, c_tail = 0, c_rounds = 0, c_t = 0, c_yp = 0;
     if (PROF) c_begin = tk_clock();
     constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
     const fl_mv_args &A = ph.a;
@@ -501,27 +503,18 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
         }
     }
     const int n_past = (A.epi == FL_EPI_QKV) ? *A.n_past : 0;
+    const int ntiles = sl.ntiles;
     if (PROF) { c_t = tk_clock(); c_yp = c_t - c_begin; }
-    // Tiles are handed out DYNAMICALLY (the group's producer claims them from the phase's global counter), so a CTA that is served
-    // faster by L2 / HBM simply takes more of them and all CTAs reach the grid barrier together.  The group's slots tg, tg + 4, ... are
-    // used round-robin (ks = next slot, kpar = its parity, both carried across phases); the producer describes every tile in sdesc[slot]
-    // and closes the phase with an end marker (nunits == 0).
-    int s = ks;
-    uint32_t par = kpar;
-    unsigned ntiles = 0;
-    for (;;) {
+    int t = ((tg - (T0 & 3)) + 4) & 3;                 // first tile of this phase owned by the warp's tile group
+    int T = T0 + t;
+    const uint32_t rounds = tk_div((uint32_t)T, prm.s_magic, prm.s_shift);
+    int s = T - (int)rounds * S;
+    uint32_t par = rounds & 1u;
+    for (; t < ntiles; t += TK_TG) {
+        int seg, unit0, nunits;
+        tk_tile_of(sl, G, t, seg, unit0, nunits);
         fl_mbar_wait(bar0 + 8u * s, par);
-        const int4 td = sdesc[s];
-        const int seg = td.x, unit0 = td.y, nunits = td.z;
-        if (PROF) { const unsigned c = tk_clock(); if (c_rounds == 0) c_wait1 = c - c_t; c_wait += c - c_t; c_t = c; c_rounds++; }
-        if (nunits == 0) {                                     // end of the phase for this group
-            __syncwarp();
-            if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));
-            s += TK_TG;
-            if (s >= S) { s -= S; par ^= 1u; }
-            break;
-        }
-        ntiles++;
+        if (PROF) { const unsigned c = tk_clock(); c_wait += c - c_t; c_t = c; c_rounds++; }
         if (g < nunits && !(prm.diag & 2)) {
             const uint8_t *tile = stage0 + (size_t)s * prm.slot_bytes;
             // default: pair rows are adjacent; swiglu: [nunits rows of w1][nunits rows of w3]
@@ -576,8 +569,8 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
                 } else {
                     // K-split combine state is per (tile group, tile parity), NOT per ring slot: a warp hands its slot back right after its
                     // dot products, so with one slot per group a fast warp could already be combining the NEXT tile of the same slot while a
-                    // slow warp is still combining this one.  A warp can be at most one tile ahead of the slowest warp of its group (the next
-                    // tile only arrives once everybody released this one), hence two buffers.
+                    // slow warp is still combining this one (seen with 24 KB q4_1 tiles, where only 4 slots fit).  A warp can be at most one
+                    // tile ahead of the slowest warp of its group (the next tile only arrives once everybody released this one): two buffers.
                     const int cb = (tg * 2 + (int)(kround & 1u)) * TK_GMAX + g;
                     volatile float *rb = rowbuf + (size_t)cb * 8;                     // [2 rows][kparts <= 4]
                     rb[p] = totA;
@@ -602,10 +595,8 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
         if (s >= S) { s -= S; par ^= 1u; }
         if (PROF) { const unsigned c = tk_clock(); c_tail += c - c_t; c_t = c; }
     }
-    ks = s;
-    kpar = par;
     if (PROF && lane == 0 && pw) {
-        pw[0] = c_yp; pw[1] = c_wait; pw[2] = c_dot; pw[3] = c_tail; pw[4] = c_rounds; pw[5] = tk_clock() - c_begin; pw[6] = ntiles; pw[7] = c_wait1;
+        pw[0] = c_yp; pw[1] = c_wait; pw[2] = c_dot; pw[3] = c_tail; pw[4] = c_rounds; pw[5] = tk_clock() - c_begin; pw[6] = (unsigned)ntiles; pw[7] = 0;
     }
 }
 
@@ -707,13 +698,13 @@ __device__ __forceinline__ void tk_attention_prefetch(const tk_phase &ph, int he
 }
 
 template <int TYPE, bool PROF>
-__device__ __forceinline__ void tk_consume_dispatch(const tk_phase &ph, const tk_params &prm, const int4 *sdesc, int &ks, uint32_t &kpar, unsigned &kround, const tk_yblock *ysm,
+__device__ __forceinline__ void tk_consume_dispatch(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, unsigned &kround, const tk_yblock *ysm,
                                                     float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw, unsigned lle) {
     switch (ph.nfull) {
-        case 4: tk_consume<TYPE, 4, PROF>(ph, prm, sdesc, ks, kpar, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
-        case 3: tk_consume<TYPE, 3, PROF>(ph, prm, sdesc, ks, kpar, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
-        case 2: tk_consume<TYPE, 2, PROF>(ph, prm, sdesc, ks, kpar, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
-        default: tk_consume<TYPE, 0, PROF>(ph, prm, sdesc, ks, kpar, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
+        case 4: tk_consume<TYPE, 4, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
+        case 3: tk_consume<TYPE, 3, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
+        case 2: tk_consume<TYPE, 2, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
+        default: tk_consume<TYPE, 0, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
     }
 }
 
@@ -731,6 +722,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
     // global would put a chain of L2 round trips right behind each grid barrier.  Descriptor pi+1 is copied in
     // by warp 15 while phase pi runs and becomes visible through the next barrier's bar.sync.
     __shared__ __align__(16) tk_phase phs[2];
+    __shared__ tk_slice sl_sh;                                // this CTA's slice of the current phase (computed once, read by all)
     const int S = prm.S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = fl_smem_u32(bars);
@@ -752,36 +744,28 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         asm volatile("bar.sync 14, %0;" ::"r"(TK_THREADS) : "memory");          // barriers initialised (consumers and the other producers wait here too)
         if (lane == 0) {
             const uint64_t pol = fl_policy_evict_first();
-            int4 *sdesc = (int4 *)(smem + prm.off_desc);
-            int s = pg;                                                          // this group's slots: pg, pg + 4, ... round-robin
-            uint32_t par = 1;
+            int T0 = 0;                                                          // global index of the phase's first tile (this CTA)
             for (int pi = 0; pi < prm.n_phases; pi++) {
                 // The descriptor lives in global memory; everything the tile loop needs is pulled into registers once per phase
                 // (one L2 round trip, hidden because the producer runs ahead).
                 const tk_phase *gp = prm.phases + pi;
                 if (__ldg(&gp->kind) != TK_PH_MATVEC) continue;
-                const int lgG = __ldg(&gp->lgG), swiglu = __ldg(&gp->swiglu);
+                const int G = __ldg(&gp->G), lgG = __ldg(&gp->lgG), swiglu = __ldg(&gp->swiglu);
                 const int m0 = __ldg(&gp->units[0]), m1 = __ldg(&gp->units[1]), m2 = __ldg(&gp->units[2]);
-                const int gt0 = __ldg(&gp->gt[0]), gt1 = __ldg(&gp->gt[1]), ntot = __ldg(&gp->gt[2]);
                 const uint32_t row_bytes = __ldg(&gp->row_bytes);
                 const uint8_t *w0 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[0]);
                 const uint8_t *w1 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[1]);
                 const uint8_t *w2 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[2]);
-                unsigned *ctr = prm.tile_ctr + pi;
-                for (;;) {
-                    // claim the next tile of the phase (all CTAs and groups draw from one counter), then wait for a free slot
-                    const int tau = (int)atomicAdd(ctr, 1u);
-                    fl_mbar_wait(bar0 + 8u * (S + s), par);
-                    if (tau >= ntot) {                                           // phase exhausted: end marker for this group, no data
-                        sdesc[s] = make_int4(0, 0, 0, 0);
-                        fl_mbar_arrive(bar0 + 8u * s);
-                        s += TK_TG;
-                        if (s >= S) { s -= S; par ^= 1u; }
-                        break;
-                    }
+                const tk_slice sl = tk_make_slice_u(m0, m1, m2, lgG, prm.grid_magic, prm.grid_shift);
+                int t = ((pg - (T0 & 3)) + 4) & 3;                               // first tile of this phase that belongs to group pg
+                int T = T0 + t;
+                const uint32_t rounds = tk_div((uint32_t)T, prm.s_magic, prm.s_shift);
+                int s = T - (int)rounds * S;                                     // slot T % S (S is a multiple of 4: s % 4 == pg)
+                uint32_t par = (rounds & 1u) ^ 1u;
+                for (; t < sl.ntiles; t += TK_TG) {
                     int seg, unit0, nunits;
-                    tk_tile_global(gt0, gt1, m0, m1, m2, lgG, tau, seg, unit0, nunits);
-                    sdesc[s] = make_int4(seg, unit0, nunits, tau);
+                    tk_tile_of(sl, G, t, seg, unit0, nunits);
+                    fl_mbar_wait(bar0 + 8u * (S + s), par);
                     const uint32_t dst = fl_smem_u32(stage0 + (size_t)s * prm.slot_bytes);
                     if (prm.diag & 1) {
                         fl_mbar_arrive(bar0 + 8u * s);
@@ -799,6 +783,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
                     s += TK_TG;
                     if (s >= S) { s -= S; par ^= 1u; }
                 }
+                T0 += sl.ntiles;
             }
         }
         return;
@@ -813,9 +798,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         for (int i = lane; i < (int)(sizeof(tk_phase) / 4); i += 32) ((uint32_t *)&phs[0])[i] = ((const uint32_t *)&prm.phases[0])[i];
     tk_bar_consumers(15);
     asm volatile("bar.sync 14, %0;" ::"r"(TK_THREADS) : "memory");     // mbarriers initialised
-    const int4 *sdesc = (const int4 *)(smem + prm.off_desc);
-    int ks = warp / TK_WPG;                                  // the warp's tile group starts at slot tg, parity 0
-    uint32_t kpar = 0;
+    int T0 = 0;
     unsigned kround = 0;                                     // tiles this warp's group has processed (selects the K-split combine buffer)
     unsigned epoch = 0;
     // cross-GPU epochs continue across launches AND plans: the running count lives next to the flags (word 8 * 32 of the
@@ -858,13 +841,16 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
             continue;
         }
         const int K = ph.nb * 32;
+        if (tid == TK_NT - 1) sl_sh = tk_make_slice_u(ph.units[0], ph.units[1], ph.units[2], ph.lgG, prm.grid_magic, prm.grid_shift);
         if (!(prm.diag & 8)) tk_prologue(ph.a, K, ysm, red, warp, lane, tid, lle, err);
         if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
         tk_bar_consumers(15);                                    // activations, slice and next descriptor are in shared memory
         if (pr) pr[2] = tk_now();
+        const tk_slice &sl = sl_sh;
         unsigned *pw = (PROF && prm.prof2) ? prm.prof2 + (((size_t)pi * gridDim.x + blockIdx.x) * TK_CW + warp) * 8 : nullptr;
-        if (ph.a.type == FL_TYPE_Q4_0) tk_consume_dispatch<FL_TYPE_Q4_0, PROF>(ph, prm, sdesc, ks, kpar, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle);
-        else                           tk_consume_dispatch<FL_TYPE_Q4_1, PROF>(ph, prm, sdesc, ks, kpar, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle);
+        if (ph.a.type == FL_TYPE_Q4_0) tk_consume_dispatch<FL_TYPE_Q4_0, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle);
+        else                           tk_consume_dispatch<FL_TYPE_Q4_1, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle);
+        T0 += sl.ntiles;
         if (pr) pr[3] = tk_now();
     }
     if (prm.world > 1 && blockIdx.x == 0 && tid == 0) {
@@ -926,10 +912,6 @@ static int tk_geometry(tk_phase &ph, size_t &tile_bytes) {
     }
     FL_REQUIRE(a.epi != FL_EPI_RESADD || ((uintptr_t)a.res & 7) == 0, "token kernel: residual is not 8-byte aligned");
     FL_REQUIRE((long)ph.units[0] + ph.units[1] + ph.units[2] < (1 << 23), "token kernel: too many rows");
-    {
-        int acc = 0;
-        for (int i = 0; i < 3; i++) { acc += (ph.units[i] + G - 1) / G; ph.gt[i] = acc; }
-    }
     ph.kind = TK_PH_MATVEC;
     ph.nb = nb; ph.kparts = kparts; ph.G = G; ph.lgG = (G == 4) ? 2 : (G == 2) ? 1 : 0; ph.P = P; ph.nfull = nfull; ph.row_bytes = (uint32_t)row_bytes;
     tile_bytes = (size_t)2 * G * row_bytes;
@@ -1007,8 +989,7 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
         const size_t ncomb = (size_t)std::max(S, 2 * TK_TG) * TK_GMAX;          // K-split combine buffers: (tile group, tile parity, unit)
         p.off_cnt = (p.off_rowbuf + ncomb * 8 * sizeof(float) + 127) & ~(size_t)127;
         p.off_sc = (p.off_cnt + ncomb * sizeof(int) + 127) & ~(size_t)127;
-        p.off_desc = (p.off_sc + ((size_t)max_ctx + FD_PV_SUBS * 256) * sizeof(float) + 127) & ~(size_t)127;
-        off = (p.off_desc + (size_t)S * sizeof(int4) + 127) & ~(size_t)127;
+        off = (p.off_sc + ((size_t)max_ctx + FD_PV_SUBS * 256) * sizeof(float) + 127) & ~(size_t)127;
         if (off + (size_t)S * slot <= (size_t)optin - 1024) break;
     }
     p.off_stage0 = (uint32_t)off;
@@ -1025,11 +1006,10 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     pl->smem = off + (size_t)S * slot;
     FL_CUDA_OK(cudaMalloc((void **)&pl->d_phases, sizeof(tk_phase) * (size_t)n_steps));
     FL_CUDA_OK(cudaMemcpy(pl->d_phases, phases.data(), sizeof(tk_phase) * (size_t)n_steps, cudaMemcpyHostToDevice));
-    FL_CUDA_OK(cudaMalloc((void **)&pl->d_bar, 256 + sizeof(unsigned) * (size_t)n_steps));
+    FL_CUDA_OK(cudaMalloc((void **)&pl->d_bar, 256));
     p.phases = pl->d_phases;
     p.grid_bar = pl->d_bar;
-    p.tile_ctr = pl->d_bar + 64;
-    FL_CUDA_OK(cudaMemset(pl->d_bar, 0, 256 + sizeof(unsigned) * (size_t)n_steps));
+    FL_CUDA_OK(cudaMemset(pl->d_bar, 0, 256));
     FL_CUDA_OK(cudaHostAlloc((void **)&pl->h_err, 64, cudaHostAllocMapped));
     memset(pl->h_err, 0, 64);
     FL_CUDA_OK(cudaHostGetDevicePointer((void **)&p.err, pl->h_err, 0));
@@ -1083,7 +1063,7 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
 
 int flk_token_plan_launch(cudaStream_t st, void *plan) {
     fl_token_plan_impl *pl = (fl_token_plan_impl *)plan;
-    FL_CUDA_OK(cudaMemsetAsync(pl->d_bar, 0, 256 + sizeof(unsigned) * (size_t)pl->prm.n_phases, st));      // barrier counter + the phases' tile counters
+    FL_CUDA_OK(cudaMemsetAsync(pl->d_bar, 0, 4, st));
     void *args[] = {(void *)&pl->prm};
     // cooperative launch: all 148 CTAs are guaranteed co-resident, which the grid barrier needs
     const void *fn = pl->prm.prof2 ? (const void *)k_decode_token<true> : (const void *)k_decode_token<false>;
