@@ -469,6 +469,14 @@ def compare_parity(ref_tokens, ref_logits, our_tokens, our_logits):
             gaps.append(float((srt[-1] - srt[-2]) / np.abs(ref_logits[i]).max()))
         out["reference_top1_top2_gap_min"] = min(gaps)
         out["reference_top1_top2_gap_median"] = float(np.median(gaps))
+        if first is not None:
+            out["reference_top1_top2_gap_at_divergence"] = gaps[first]
+            out["logits_maxabs_at_divergence"] = rel[first]
+        out["note"] = ("every activation is re-quantised to q8_0 before every matmul (reference lib/ggml.c:8105-8119): a dense relative perturbation d becomes "
+                       "sqrt(d * step) after one quantised matmul (step = 1/127 of a block's amax), so ANY implementation whose fp32 operation order differs "
+                       "from the reference's by one ulp settles at a few per cent of max|logit| on this random-weight model within a layer or two -- the CPU "
+                       "stand-in with bit-identical matmuls (tests/mock) shows 1.3e-2 after ONE 7B-width layer; DESIGN.md section 5.  Greedy ids agree until the "
+                       "reference's own top-1/top-2 gap drops below that level.")
     return out
 
 
