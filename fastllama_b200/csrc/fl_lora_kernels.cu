@@ -8,6 +8,7 @@
 //   q4_0: id = 7 / amax (not 1 / (amax / 7)), round-half-EVEN; q4_1: round-half-EVEN.
 // Everything here is bit-exact against the reference's x86 build (tests/golden/lora_ops.npz, produced by the reference library).
 #include "fl_common.cuh"
+#include "fl_exact.cuh"
 #include "fl_kernels.h"
 
 // lane = element of the block; returns the 4-bit code of this lane's value and writes the block header from lane 0
@@ -107,7 +108,9 @@ __global__ void k_mul_mat_f32_ref(const float *__restrict__ A, size_t lda, int M
         float p = __fadd_rn(u, __shfl_down_sync(0xffffffffu, u, 1));               // lane 0: u0 + u1, lane 2: u2 + u3
         float s = __fadd_rn(p, __shfl_down_sync(0xffffffffu, p, 2));               // lane 0
         if (lane == 0) {
-            for (int k = np; k < K; k++) s = __fadd_rn(s, __fmul_rn(a[k], b[k]));
+            const int nma = np + fx_left_nma(K - np);
+            for (int k = np; k < nma; k++) s = __fadd_rn(s, __fmul_rn(a[k], b[k]));
+            for (int k = nma; k < K; k++) s = __fmaf_rn(a[k], b[k], s);
             out[(size_t)j * ldo + i] = s;
         }
     }
@@ -120,7 +123,9 @@ __global__ void k_mul_mat_f32_ref_small(const float *__restrict__ A, size_t lda,
         const long j = t / Ma;
         const float *a = A + (size_t)i * lda, *b = B + (size_t)j * ldb;
         float s = 0.0f;
-        for (int k = 0; k < K; k++) s = __fadd_rn(s, __fmul_rn(a[k], b[k]));
+        const int nma = fx_left_nma(K);
+        for (int k = 0; k < nma; k++) s = __fadd_rn(s, __fmul_rn(a[k], b[k]));
+        for (int k = nma; k < K; k++) s = __fmaf_rn(a[k], b[k], s);
         out[(size_t)j * ldo + i] = s;
     }
 }

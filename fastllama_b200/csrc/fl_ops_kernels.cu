@@ -12,9 +12,10 @@
 //   soft_max      :8521-8589  p = fp16_table_exp[fp16(x - max)], double sum, y = p * (float)(1/sum)
 //   rope          :8609-8697  mode 0 adjacent pairs; cos/sin table built on the host with libm
 //   cpy/dup f32   :5942-6257  logical-order element copy between arbitrary strided views
-//   mul_mat f32   :7482-7680  dst[i0,i1,i2,i3] = dot(src0 row i0, src1 row i1) per (i2,i3)
-// fp32 reductions use warp/block trees, so sums differ from the reference's AVX lane order in the
-// last ulps (tolerances are stated in tests/test_gpu_ops.py); everything table-driven is exact.
+//   mul_mat f32   :7482-7680  dst[i0,i1,i2,i3] = dot(src0 row i0, src1 row i1) per (i2,i3), in ggml_vec_dot_f32's order (fl_exact_kernels.cu)
+// rms_norm adds the squares in double in a different order than the reference's scalar loop (the float mean can differ only when
+// the double sum sits within ~1e-14 relative of a rounding boundary); soft_max's double sum is EXACT in any order (every term is an
+// fp16 value <= 1, i.e. a multiple of 2^-24); everything table-driven is exact.
 #include <cuda_fp16.h>
 
 #include "fl_common.cuh"
@@ -273,37 +274,10 @@ int flk_cpy_f32(cudaStream_t st, const fl_view &src, const fl_view &dst) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// mul_mat f32 x f32 (attention scores and weighted values): one warp per output element.
-// src0 rows must be contiguous (nb00 == 4), src1 rows contiguous (nb10 == 4), like the reference.
+// mul_mat f32 x f32 (attention scores and weighted values of a multi-token eval): the reference-order kernel of
+// fl_exact_kernels.cu (one warp per output group, lane l = element l of ggml_vec_dot_f32's 32-float step).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_mul_mat_f32(const fl_view a, const fl_view b, const fl_view d, int64_t nout) {
-    const int lane = threadIdx.x & 31;
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int K = (int)a.ne[0];
-    for (int64_t o = wid; o < nout; o += nw) {
-        int64_t r = o;
-        const int64_t i0 = r % d.ne[0]; r /= d.ne[0];     // src0 row
-        const int64_t i1 = r % d.ne[1]; r /= d.ne[1];     // src1 row
-        const int64_t i2 = r % d.ne[2];
-        const int64_t i3 = r / d.ne[2];
-        const float *x = (const float *)((const char *)a.data + fl_off4(a, 0, i0, i2, i3));
-        const float *y = (const float *)((const char *)b.data + fl_off4(b, 0, i1, i2, i3));
-        float acc = 0.0f;
-        for (int i = lane; i < K; i += 32) acc = __fmaf_rn(x[i], y[i], acc);
-        acc = fl_warp_sum(acc);
-        if (lane == 0) *(float *)((char *)d.data + fl_off4(d, i0, i1, i2, i3)) = acc;
-    }
-}
 int flk_mul_mat_f32(cudaStream_t st, const fl_view &src0, const fl_view &src1, const fl_view &dst) {
-    FL_REQUIRE(src0.nb[0] == 4 && src1.nb[0] == 4, "mul_mat_f32: operand rows must be contiguous f32");
     FL_REQUIRE(src0.ne[0] == src1.ne[0], "mul_mat_f32: inner dimensions differ");
-    const int64_t nout = nelem(dst);
-    if (nout <= 0) return 0;
-    long g = (nout + 7) / 8;
-    if (g > (long)flk_sm_count() * 16) g = (long)flk_sm_count() * 16;
-    k_mul_mat_f32<<<(int)g, 256, 0, st>>>(src0, src1, dst, nout);
-    fl_count_launch();
-    FL_CUDA_OK(cudaGetLastError());
-    return 0;
+    return flk_mul_mat_f32_ref4(st, src0, src1, dst);
 }

@@ -13,6 +13,7 @@
 // which the per-block terms are added in fp32 differs (lane-strided + shuffle tree here, 8 AVX
 // lanes there).
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -565,25 +566,31 @@ int flk_mul_mat_q(cudaStream_t st, int type, const void *W, size_t wrs, int M, i
     FL_REQUIRE(K > 0 && K % FL_QK == 0, "mul_mat_q: K=%d is not a multiple of 32", K);
     FL_REQUIRE(((uintptr_t)W & 3) == 0 && (wrs & 3) == 0, "mul_mat_q: weight rows must be 4-byte aligned");
     if (M <= 0 || N <= 0) return 0;
-    fl_ring_params p;
-    int threads = 0;
-    size_t smem = 0;
-    int nfull = 0;
-    const bool ring_ok = (N == 1) && ring_config(type, W, wrs, M, K, p, threads, smem, nfull);
-    if (impl == 2) FL_REQUIRE(ring_ok, "mul_mat_q: shape M=%d K=%d N=%d does not qualify for the ring kernel", M, K, N);
-    if ((impl == 0 || impl == 2) && ring_ok) {
+    // impl 0 (what the graph executor passes): results carry the reference's bits -- the reference-order kernel of fl_exact_kernels.cu --
+    // except for multi-token evals of N >= 16 columns, which go to the tcgen05 GEMM (same per-block arithmetic, block terms added in
+    // another fp32 order: within the stated budget, not bit-identical) unless FASTLLAMA_B200_INGEST=exact.
+    // The other kernels stay selectable for measurements and their own tests: 1 plain, 2 TMA ring matvec, 3 mma.sync,
+    // 4-7 tcgen05 (column tile chosen / 32 / 64 / 128), 8 reference order.
+    if (impl == 0) {
+        static const int umma_auto = getenv("FASTLLAMA_B200_UMMA") ? atoi(getenv("FASTLLAMA_B200_UMMA")) : 1;     // FASTLLAMA_B200_UMMA=0: no tensor-core path
+        static const bool exact_ingest = getenv("FASTLLAMA_B200_INGEST") && !strcmp(getenv("FASTLLAMA_B200_INGEST"), "exact");
+        if (umma_auto && !exact_ingest && N >= 16 && flk_mul_mat_q_umma_supported(type, W, wrs, M, K, N)) return flk_mul_mat_q_umma(st, type, W, wrs, M, K, Yq8, N, dst, drs, 0);
+        return flk_mul_mat_q_ref(st, type, W, wrs, M, K, Yq8, N, dst, drs);
+    }
+    if (impl == 8) return flk_mul_mat_q_ref(st, type, W, wrs, M, K, Yq8, N, dst, drs);
+    if (impl >= 4 && impl <= 7) return flk_mul_mat_q_umma(st, type, W, wrs, M, K, Yq8, N, dst, drs, impl == 4 ? 0 : 16 << (impl - 4));
+    if (impl == 3) return flk_mul_mat_q_mma(st, type, W, wrs, M, K, Yq8, N, dst, drs);
+    if (impl == 2) {
+        fl_ring_params p;
+        int threads = 0;
+        size_t smem = 0;
+        int nfull = 0;
+        const bool ring_ok = (N == 1) && ring_config(type, W, wrs, M, K, p, threads, smem, nfull);
+        FL_REQUIRE(ring_ok, "mul_mat_q: shape M=%d K=%d N=%d does not qualify for the ring kernel", M, K, N);
         p.W = (const uint8_t *)W;
         p.Y = (const fl_block_q8_0 *)Yq8;
         p.dst = dst;
         return launch_ring(st, type, nfull, p, threads, smem);
     }
-    // N > 1 (prompt ingest): the block dots go to the tensor cores.  tcgen05 path (fl_umma_kernel.cu): impl 4 (tile width chosen),
-    // 5 / 6 / 7 = column tiles of 32 / 64 / 128; legacy mma.sync path (fl_mma_kernel.cu): impl 3 and small N; tiny N stays on the plain kernel
-    if (impl >= 4 && impl <= 7) return flk_mul_mat_q_umma(st, type, W, wrs, M, K, Yq8, N, dst, drs, impl == 4 ? 0 : 16 << (impl - 4));
-    {
-        static const int umma_auto = getenv("FASTLLAMA_B200_UMMA") ? atoi(getenv("FASTLLAMA_B200_UMMA")) : 1;     // FASTLLAMA_B200_UMMA=0: legacy mma.sync path
-        if (impl == 0 && umma_auto && N >= 16 && flk_mul_mat_q_umma_supported(type, W, wrs, M, K, N)) return flk_mul_mat_q_umma(st, type, W, wrs, M, K, Yq8, N, dst, drs, 0);
-    }
-    if (impl == 3 || (impl == 0 && N >= 4)) return flk_mul_mat_q_mma(st, type, W, wrs, M, K, Yq8, N, dst, drs);
     return launch_plain(st, type, W, wrs, M, K, Yq8, N, dst, drs);
 }

@@ -158,6 +158,7 @@ extern "C" void fl_shutdown(void) {
     if (g.tab_silu) cudaFree(g.tab_silu);
     if (g.tab_exp) cudaFree(g.tab_exp);
     if (g.rope_cs) cudaFree(g.rope_cs);
+    flk_exact_release();
     cudaStreamDestroy(g.stream);
     g = State();
 }
@@ -848,7 +849,7 @@ extern "C" int fl_vec_dot_q4_q8(int type, int n, float *s, const void *x, const 
     if (scratch_get(0, rb, &dw) || scratch_get(1, qb, &dq) || scratch_get(2, 16, &dd)) return -1;
     FL_CUDA_OK(cudaMemcpyAsync(dw, x, rb, cudaMemcpyHostToDevice, g.stream));
     FL_CUDA_OK(cudaMemcpyAsync(dq, y, qb, cudaMemcpyHostToDevice, g.stream));
-    if (flk_mul_mat_q(g.stream, type, dw, rb, 1, n, dq, 1, (float *)dd, 1, 1)) return -1;
+    if (flk_mul_mat_q(g.stream, type, dw, rb, 1, n, dq, 1, (float *)dd, 1, 0)) return -1;
     FL_CUDA_OK(cudaMemcpyAsync(s, dd, sizeof(float), cudaMemcpyDeviceToHost, g.stream));
     FL_CUDA_OK(cudaStreamSynchronize(g.stream));
     return 0;

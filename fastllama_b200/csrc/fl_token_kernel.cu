@@ -8,13 +8,18 @@
 // mbarrier ring, running ahead of the consumers across phase boundaries: while the grid synchronises
 // and the next activation vector is quantised, the next matrices are already landing in shared memory.
 //
-// Work unit = a PAIR of rows handled by one warp (both rows against the same prepared activations):
+// Work unit = a PAIR of rows (both rows against the same prepared activations):
 //   * default: rows (2u, 2u+1) of a matrix;
 //   * wq|wk|wv: the pair is a rope pair, so rope + KV-cache store need no cross-warp staging;
 //   * w1|w3 ("SwiGLU" phases, detected at plan creation): the pair is (w1 row u, w3 row u) and the
 //     epilogue writes silu(w1.x) * (w3.x) directly, so w2's prologue is a plain quantisation.
-// Per-row arithmetic (block dot, lane mapping, K-slice combine order, epilogues) is exactly that of
-// k_mv_fused / k_attn_decode, so results are bit-identical to the multi-kernel path.
+// ARITHMETIC: every fp32 operation happens in the reference's own order (fl_exact.cuh): a warp owns a TASK of four units (eight
+// rows), four lanes per row, lane jj carrying the reference's accumulators 2jj and 2jj+1 through ALL blocks of the row in order;
+// attention scores and the value mix follow ggml_vec_dot_f32's 32-lane order.  The logits of a token are therefore the bits the
+// reference's x86 build produces (the one known exception: rms_norm's double sum, see fl_ops_kernels.cu).
+// A task's rows are streamed in K-chunks of TK_CHB blocks: tile = (task, chunk) = 8 row pieces of <= 1280 (q4_0) / 1536 (q4_1)
+// bytes, each copied by its own bulk copy to a row pitch of chunk + 16 bytes, which makes the 32 lanes' weight words fall into
+// 32 different banks.  The four consumer warps of a tile group take the tiles of their group's stream in turn.
 // Activations move between phases through L2: they are read with ld.global.cg (L1 is not coherent
 // across SMs inside a kernel) and published by a gpu-scope release before the barrier arrive.
 #include <cuda_fp16.h>
@@ -26,24 +31,28 @@
 #include "fl_common.cuh"
 #include "fl_decode.h"
 #include "fl_decode_dev.cuh"
+#include "fl_exact.cuh"
 #include "fl_kernels.h"
 
 #define TK_CW 16                 // consumer warps
 #define TK_NT (TK_CW * 32)
 #define TK_TG 4                  // tile groups; ring slot s always belongs to group s % 4 (S is a multiple of 4)
-#define TK_WPG 4                 // warps per tile group = kparts * G
-#define TK_GMAX 4                // units (row pairs) per tile at most
+#define TK_WPG 4                 // consumer warps per tile group
+#define TK_GMAX 4                // units (row pairs) per task
+#define TK_CHB 64                // blocks per K-chunk of a task (one tile = 8 row pieces of one chunk)
 #define TK_PW 4                  // producer warps: warp TK_CW + g streams the tiles of tile group g (its own slots, its own pace)
 #define TK_THREADS (TK_NT + 32 * TK_PW)
-#define TK_REGS_CONSUMER 112      // setmaxnreg: the producer warpgroup hands its registers to the four consumer warpgroups.  The pool is the CTA's
-                                  // LAUNCH allocation (96 x 640 = 61440 registers): 112 x 512 + 24 x 128 = 60416 fits, 120 x 512 would wait forever
-#define TK_REGS_PRODUCER 24
+#define TK_REGS_CONSUMER 104      // setmaxnreg: the producer warpgroup hands registers to the four consumer warpgroups.  The pool is the CTA's
+                                  // LAUNCH allocation (96 x 640 = 61440 registers): 104 x 512 + 56 x 128 = 60416 fits; a request beyond the pool
+                                  // waits forever (checked on the host at plan creation)
+#define TK_REGS_PRODUCER 56
 
 enum { TK_PH_MATVEC = 0, TK_PH_ATTN = 1 };
 
 struct tk_phase {
     int kind;
-    int nb, kparts, G, lgG, P, nfull;
+    int nb, nchunks;             // blocks per row, K-chunks per task
+    uint32_t srow;               // pitch of a row piece in a ring slot: chunk bytes + 16
     int swiglu;                  // pair = (seg 0 row u, seg 1 row u); epilogue writes silu(a) * b to seg_dst[0][u]
     int units[3];                // pairs per segment (swiglu: one segment of seg_rows[0] pairs)
     uint32_t row_bytes;
@@ -70,8 +79,8 @@ struct tk_params {
     const uint16_t *exp_tab;
     unsigned long long *prof;      // optional: [n_phases][gridDim.x][4] globaltimer stamps of thread 0
     unsigned *prof2;               // optional (PROF kernel only): [n_phases][gridDim.x][TK_CW][8] cycle counts of every consumer warp's tile loop
-    int S;
-    uint32_t grid_magic, grid_shift, s_magic, s_shift;  // n / d == umulhi(n, magic) >> shift (magic 0: d is a power of two, n >> shift); exact for n < 2^31
+    int S, Sg;                       // ring slots in total and per tile group (S = 4 * Sg)
+    uint32_t grid_magic, grid_shift, s_magic, s_shift;  // n / d == umulhi(n, magic) >> shift (magic 0: d is a power of two, n >> shift); exact for n < 2^31; s_*: d = Sg
     uint32_t slot_bytes;
     int l2_prefetch;
     int diag;                        // FASTLLAMA_B200_TK_DIAG (timing experiments only; results are garbage): 1 = no weight copies, 2 = no dot products, 4 = no grid barriers, 8 = no prologue
@@ -166,16 +175,13 @@ __device__ __forceinline__ void tk_tile_of(const tk_slice &sl, int G, int t, int
 }
 
 // ---- prologue: the phase's activations, q8_0-quantised and prepared for the block dot, into shared memory ----
-// Same arithmetic as quantize_row_q8_0 + fd_prep_y (so the same bits as k_mv_fused), different work split: one
+// Same arithmetic as quantize_row_q8_0 (bit-exact, tests/test_gpu_rowfns.py), different work split: one
 // thread quantises one HALF block (16 consecutive values, two lanes per block), which needs one shuffle per
 // reduction and two divisions per block pair instead of per float4 group -- 2.5x fewer issue slots than the
 // float4-group scheme, and this code runs redundantly in every CTA behind every grid barrier.
-// A prepared block is 48 bytes: ye[4] | yo[4] | d, s, c, pad (three conflict-free LDS.128 per lane in the consumers).
-struct __align__(16) tk_yblock {
-    uint32_t ye[4], yo[4];       // even / odd elements of each 8-element group, as in fd_yprep
-    float d, s;
-    int c, pad;                  // c = -8 * sum(q) (the q4_0 offset); q4_1 consumers ignore it
-};
+// A prepared block is an fl_yx (fl_exact.cuh, 80 bytes): per lane-of-four jj the two 4-value words and their biases (one LDS.128),
+// then the block's d and s (one LDS.64).
+typedef fl_yx tk_yblock;
 
 // A thread quantises E consecutive values (E = 8: four lanes per block, E = 16: two lanes per block, E = 32: a whole block).
 template <int E>
@@ -252,9 +258,9 @@ __device__ __forceinline__ void tk_store_vals(float *dst, int u, const float v[E
 #pragma unroll
     for (int k = 0; k < E / 4; k++) ((float4 *)dst)[(E / 4) * u + k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
-// v: the E final values of unit u (all lanes of the warp call this; `valid` lanes store)
+// v: the E final values of unit u (all lanes of the warp call this; `valid` lanes store); off = 8 for q4_0 weights, 0 for q4_1
 template <int E>
-__device__ __forceinline__ void tk_quant(const float v[E], int u, bool valid, tk_yblock *ysm) {
+__device__ __forceinline__ void tk_quant(const float v[E], int u, bool valid, tk_yblock *ysm, int off) {
     float m0 = 0.f, m1 = 0.f;                        // two chains: max is order-independent
 #pragma unroll
     for (int k = 0; k < E; k += 2) { m0 = fmaxf(m0, fabsf(v[k])); m1 = fmaxf(m1, fabsf(v[k + 1])); }
@@ -280,17 +286,18 @@ __device__ __forceinline__ void tk_quant(const float v[E], int u, bool valid, tk
         const int part = u % UPB;
 #pragma unroll
         for (int j = 0; j < NW; j++) {
-            const uint32_t ye = (uint32_t)(q[8 * j + 0] & 0xFF) | ((uint32_t)(q[8 * j + 2] & 0xFF) << 8) | ((uint32_t)(q[8 * j + 4] & 0xFF) << 16) | ((uint32_t)(q[8 * j + 6] & 0xFF) << 24);
-            const uint32_t yo = (uint32_t)(q[8 * j + 1] & 0xFF) | ((uint32_t)(q[8 * j + 3] & 0xFF) << 8) | ((uint32_t)(q[8 * j + 5] & 0xFF) << 16) | ((uint32_t)(q[8 * j + 7] & 0xFF) << 24);
-            yb->ye[NW * part + j] = ye;
-            yb->yo[NW * part + j] = yo;
+            const uint32_t ya = (uint32_t)(q[8 * j + 0] & 0xFF) | ((uint32_t)(q[8 * j + 1] & 0xFF) << 8) | ((uint32_t)(q[8 * j + 2] & 0xFF) << 16) | ((uint32_t)(q[8 * j + 3] & 0xFF) << 24);
+            const uint32_t yb4 = (uint32_t)(q[8 * j + 4] & 0xFF) | ((uint32_t)(q[8 * j + 5] & 0xFF) << 8) | ((uint32_t)(q[8 * j + 6] & 0xFF) << 16) | ((uint32_t)(q[8 * j + 7] & 0xFF) << 24);
+            const int sa = q[8 * j + 0] + q[8 * j + 1] + q[8 * j + 2] + q[8 * j + 3], sb = q[8 * j + 4] + q[8 * j + 5] + q[8 * j + 6] + q[8 * j + 7];
+            *(uint4 *)yb->q[NW * part + j] = make_uint4(ya, yb4, (uint32_t)(FX_MAGIC_I - off * sa), (uint32_t)(FX_MAGIC_I - off * sb));
         }
-        if (part == 0) *(uint4 *)&yb->d = make_uint4(__float_as_uint(d), __float_as_uint(__fmul_rn(d, (float)sum)), (uint32_t)(-8 * sum), 0u);
+        if (part == 0) *(float2 *)&yb->d = make_float2(d, __fmul_rn(d, (float)sum));
     }
 }
 // plain / silu*mul prologue body for one unit size
 template <int E>
 __device__ __forceinline__ void tk_prologue_nonorm(const fl_mv_args &A, int K, tk_yblock *ysm, int warp, int tid, unsigned lle, unsigned *err) {
+    const int qoff = (A.type == FL_TYPE_Q4_0) ? 8 : 0;
     const int nu = K / E;
     if (E == 16 && A.pro != FL_PRO_SILUMUL && nu > TK_NT && nu <= 2 * TK_NT) {
         // two units per thread (K = 11008: 688 half blocks on 512 threads), BOTH loads in flight before either is quantised: one L2
@@ -301,8 +308,8 @@ __device__ __forceinline__ void tk_prologue_nonorm(const fl_mv_args &A, int K, t
         tk_load_x<E>(A, ua, va, lle, err);
         if (vb) tk_load_x<E>(A, ub, vv, lle, err); else tk_zero_vals<E>(vv);
         if (A.sum_out && blockIdx.x == 0) { tk_store_vals<E>(A.sum_out, ua, va); if (vb) tk_store_vals<E>(A.sum_out, ub, vv); }
-        tk_quant<E>(va, ua, true, ysm);
-        if (wb) tk_quant<E>(vv, ub, vb, ysm);
+        tk_quant<E>(va, ua, true, ysm, qoff);
+        if (wb) tk_quant<E>(vv, ub, vb, ysm, qoff);
         return;
     }
     for (int u0 = 0; u0 < nu; u0 += TK_NT) {
@@ -321,7 +328,7 @@ __device__ __forceinline__ void tk_prologue_nonorm(const fl_mv_args &A, int K, t
                 v[k] = __fmul_rn(__half2float(__ushort_as_half(__ldg(A.silu_tab + hh))), bm[k]);
             }
         }
-        tk_quant<E>(v, u, valid, ysm);
+        tk_quant<E>(v, u, valid, ysm, qoff);
     }
 }
 
@@ -330,6 +337,7 @@ __device__ __forceinline__ void tk_prologue_nonorm(const fl_mv_args &A, int K, t
 // Sum of squares: thread t adds the values of units t, t + NT, ... in order (k_mv_fused uses the same order).
 template <int RES>
 __device__ __forceinline__ void tk_prologue_norm(const fl_mv_args &A, int K, tk_yblock *ysm, double *red, int warp, int lane, int tid, unsigned lle, unsigned *err) {
+    const int qoff = (A.type == FL_TYPE_Q4_0) ? 8 : 0;
     constexpr int E = 8, NR = RES > 0 ? RES : 1;
     const int nu = K >> 3;
     float v[NR][E], gm[NR][E];
@@ -374,7 +382,7 @@ __device__ __forceinline__ void tk_prologue_norm(const fl_mv_args &A, int K, tk_
 #pragma unroll
                 for (int k = 0; k < E; k++) v[r][k] = __fmul_rn(gm[r][k], __fmul_rn(v[r][k], scale));
                 if (A.normed_out && blockIdx.x == 0 && valid) tk_store_vals<E>(A.normed_out, u, v[r]);
-                tk_quant<E>(v[r], u, valid, ysm);
+                tk_quant<E>(v[r], u, valid, ysm, qoff);
             }
         }
     } else {
@@ -388,7 +396,7 @@ __device__ __forceinline__ void tk_prologue_norm(const fl_mv_args &A, int K, tk_
 #pragma unroll
             for (int k = 0; k < E; k++) v[0][k] = __fmul_rn(gm[0][k], __fmul_rn(v[0][k], scale));
             if (A.normed_out && blockIdx.x == 0 && valid) tk_store_vals<E>(A.normed_out, u, v[0]);
-            tk_quant<E>(v[0], u, valid, ysm);
+            tk_quant<E>(v[0], u, valid, ysm, qoff);
         }
     }
 }
@@ -463,147 +471,98 @@ __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, 
     for (int r = 0; r < A.n_dst_peer; r++) *(float2 *)(A.dst_peer[r] + r2) = make_float2(a, b);     // posted stores over NVLink
 }
 
+// ---- the tile stream of a tile group --------------------------------------------------------------
+// Tasks (4 units = 8 rows; tk_tile_of) of a phase are dealt to the tile groups round robin, continuing where the previous phase
+// stopped (T0), and inside a group to its four consumer warps: the group's k-th task goes to warp k % 4.  The group's tiles are
+// streamed round by round (a round = up to four tasks, one per warp), chunk by chunk, warp by warp, so the four warps advance
+// through K together.  Producer and consumers enumerate the same sequence from the same closed forms; position idx of the group's
+// stream (counted over the whole launch) lives in slot 4 * (idx % Sg) + g with parity (idx / Sg) & 1.
+struct tk_stream {
+    int first, n_g;              // first task of this group in the phase, number of its tasks
+};
+__device__ __forceinline__ tk_stream tk_stream_of(int g, int T0, int ntasks) {
+    tk_stream st;
+    st.first = ((g - (T0 & 3)) + 4) & 3;
+    st.n_g = st.first < ntasks ? (ntasks - st.first + 3) >> 2 : 0;
+    return st;
+}
+__device__ __forceinline__ void tk_slot_of(const tk_params &prm, int g, uint32_t idx, int &s, uint32_t &par) {
+    const uint32_t q = tk_div(idx, prm.s_magic, prm.s_shift);          // idx / Sg
+    s = (int)(idx - q * (uint32_t)prm.Sg) * TK_TG + g;
+    par = q & 1u;
+}
+
 // ---- main loop of a matvec phase for one consumer warp ------------------------------------------------
 __device__ __forceinline__ unsigned tk_clock() {
     unsigned c;
     asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
     return c;
 }
-template <int TYPE, int NFULL, bool PROF>
-__device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, unsigned &kround, const tk_yblock *ysm,
-                                           float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw, unsigned lle) {
-    unsigned c_begin = 0, c_wait = 0, c_dot = 0, c_tail = 0, c_rounds = 0, c_t = 0, c_yp = 0;
-    if (PROF) c_begin = tk_clock();
-    constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24;
+template <int TYPE, bool PROF>
+__device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, uint32_t &cg, const tk_yblock *ysm,
+                                           uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw, unsigned lle) {
+    unsigned c_begin = 0, c_wait = 0, c_dot = 0, c_tail = 0, c_rounds = 0, c_t = 0;
+    if (PROF) { c_begin = tk_clock(); c_t = c_begin; }
+    constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24, QOFF = (TYPE == FL_TYPE_Q4_0) ? 4 : 8;
     const fl_mv_args &A = ph.a;
-    const int S = prm.S, kparts = ph.kparts, G = ph.G;
-    const int tg = warp / TK_WPG, wl = warp % TK_WPG;
-    const int p = wl % kparts, g = wl / kparts;
-    const int b0 = p * ph.P;
-    const int b1 = min(ph.nb, b0 + ph.P);
-    const uint32_t row_bytes = ph.row_bytes;
+    const int S = prm.S;
+    const int g = warp / TK_WPG, wl = warp % TK_WPG;
+    const int r = lane >> 2, jj = lane & 3;
     const bool swiglu = ph.swiglu != 0;
-
-    fd_yprep yp[FD_NBL];
-    bool valid[FD_NBL];
-#pragma unroll
-    for (int j = 0; j < FD_NBL; j++) {
-        const int ib = b0 + lane + 32 * j;
-        valid[j] = (j < NFULL) || ib < b1;
-        if (valid[j]) {
-            const uint4 e = *(const uint4 *)ysm[ib].ye, o = *(const uint4 *)ysm[ib].yo, m = *(const uint4 *)&ysm[ib].d;
-            yp[j].ye[0] = e.x; yp[j].ye[1] = e.y; yp[j].ye[2] = e.z; yp[j].ye[3] = e.w;
-            yp[j].yo[0] = o.x; yp[j].yo[1] = o.y; yp[j].yo[2] = o.z; yp[j].yo[3] = o.w;
-            yp[j].d = __uint_as_float(m.x); yp[j].s = __uint_as_float(m.y);
-            yp[j].c = (TYPE == FL_TYPE_Q4_0) ? (int)m.z : 0;
-        } else {
-            yp[j].d = 0.f; yp[j].s = 0.f; yp[j].c = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) { yp[j].ye[q] = 0; yp[j].yo[q] = 0; }
-        }
-    }
+    const int C = ph.nchunks, nb = ph.nb;
+    const tk_stream st = tk_stream_of(g, T0, sl.ntiles);
     const int n_past = (A.epi == FL_EPI_QKV) ? *A.n_past : 0;
-    const int ntiles = sl.ntiles;
-    if (PROF) { c_t = tk_clock(); c_yp = c_t - c_begin; }
-    int t = ((tg - (T0 & 3)) + 4) & 3;                 // first tile of this phase owned by the warp's tile group
-    int T = T0 + t;
-    const uint32_t rounds = tk_div((uint32_t)T, prm.s_magic, prm.s_shift);
-    int s = T - (int)rounds * S;
-    uint32_t par = rounds & 1u;
-    for (; t < ntiles; t += TK_TG) {
+    // the lane that runs the epilogue of pair p: default rows (2p, 2p+1) -> lane 8p; swiglu rows (p, p + 4) -> lane 4p
+    const bool leader = swiglu ? ((lane & 3) == 0 && lane < 16) : ((lane & 7) == 0);
+    const int pr = swiglu ? (lane >> 2) : (lane >> 3);
+    const uint32_t row_off = (uint32_t)r * ph.srow + (uint32_t)(QOFF + 4 * jj);
+    for (int k = wl; k < st.n_g; k += TK_WPG) {
+        const int k0 = k - wl, n_r = min(TK_WPG, st.n_g - k0);
         int seg, unit0, nunits;
-        tk_tile_of(sl, G, t, seg, unit0, nunits);
-        fl_mbar_wait(bar0 + 8u * s, par);
-        if (PROF) { const unsigned c = tk_clock(); c_wait += c - c_t; c_t = c; c_rounds++; }
-        if (g < nunits && !(prm.diag & 2)) {
-            const uint8_t *tile = stage0 + (size_t)s * prm.slot_bytes;
-            // default: pair rows are adjacent; swiglu: [nunits rows of w1][nunits rows of w3]
-            const uint8_t *rowA = tile + (size_t)(swiglu ? g : 2 * g) * row_bytes + (size_t)(b0 + lane) * BB;
-            const uint8_t *rowB = rowA + (size_t)(swiglu ? nunits : 1) * row_bytes;
-            float accA = 0.0f, accmA = 0.0f, accB = 0.0f, accmB = 0.0f;
-            float2 pre = make_float2(0.f, 0.f);
-            if (lane == 0) pre = tk_epilogue_preload(ph, seg, unit0 + g, n_past);
-#pragma unroll
-            for (int j = 0; j < FD_NBL; j++) {
-                if (j < NFULL || valid[j]) {
-                    fd_block<TYPE>(rowA + (size_t)(32 * j) * BB, yp[j], accA, accmA);
-                    fd_block<TYPE>(rowB + (size_t)(32 * j) * BB, yp[j], accB, accmB);
+        tk_tile_of(sl, TK_GMAX, st.first + 4 * k, seg, unit0, nunits);
+        float2 pre = make_float2(0.f, 0.f);
+        if (leader && pr < nunits) pre = tk_epilogue_preload(ph, seg, unit0 + pr, n_past);
+        float a0 = 0.0f, a1 = 0.0f, sm = 0.0f;
+        for (int c = 0; c < C; c++) {
+            int s;
+            uint32_t par;
+            tk_slot_of(prm, g, cg + (uint32_t)(k0 * C + c * n_r + wl), s, par);
+            fl_mbar_wait(bar0 + 8u * s, par);
+            if (PROF) { const unsigned t = tk_clock(); c_wait += t - c_t; c_t = t; c_rounds++; }
+            if (!(prm.diag & 2)) {
+                const uint8_t *wp = stage0 + (size_t)s * prm.slot_bytes + row_off;
+                const tk_yblock *yp = ysm + c * TK_CHB;
+                const int nbc = min(TK_CHB, nb - c * TK_CHB);
+#pragma unroll 4
+                for (int i = 0; i < nbc; i++) {
+                    const uint32_t w = *(const uint32_t *)(wp + i * BB);
+                    const float dx = *(const float *)(wp + i * BB - (QOFF + 4 * jj));
+                    const uint4 y = *(const uint4 *)yp[i].q[jj];
+                    const float2 ds = *(const float2 *)&yp[i].d;
+                    if (TYPE == FL_TYPE_Q4_1) sm = __fmaf_rn(*(const float *)(wp + i * BB - (QOFF + 4 * jj) + 4), ds.y, sm);
+                    fx_block(w, __fmul_rn(dx, ds.x), y, a0, a1);
                 }
             }
-            // the tile has been read (the sums above consumed every shared load of the warp): hand the slot back to the
-            // producer before the reduction and the epilogue, whose latency then overlaps the refill
+            // the tile has been read (the chains above consumed every shared load of the warp): hand the slot back
             __syncwarp();
             if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));
-            if (PROF) { const unsigned c = tk_clock(); c_dot += c - c_t; c_t = c; }
-            // Both (all four) sums in ONE butterfly: after the xor-16 step lanes 0-15 carry row A and lanes 16-31 row B (q4_1: the xor-8
-            // step splits each half again into the d and the m sums).  Every lane adds exactly the operands fl_warp_sum would add at that
-            // lane, so lane 0 / 16 (/ 8 / 24) end with the bits of fl_warp_sum(accA) / (accB) (/ accmA / accmB).
-            float totA, totB;
-            {
-                const bool up = (lane & 16) != 0;
-                float x = up ? accB : accA, y = up ? accA : accB;
-                x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, y, 16));
-                if (TYPE == FL_TYPE_Q4_1) {
-                    float xm = up ? accmB : accmA, ym = up ? accmA : accmB;
-                    xm = __fadd_rn(xm, __shfl_xor_sync(0xffffffffu, ym, 16));
-                    const bool up8 = (lane & 8) != 0;
-                    const float keep = up8 ? xm : x, give = up8 ? x : xm;
-                    x = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, give, 8));
-                } else {
-                    x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, 8));
-                }
-                x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, 4));
-                x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, 2));
-                x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, 1));
-                totA = x;
-                totB = __shfl_sync(0xffffffffu, x, 16);
-                if (TYPE == FL_TYPE_Q4_1) {
-                    totA = __fadd_rn(totA, __shfl_sync(0xffffffffu, x, 8));
-                    totB = __fadd_rn(totB, __shfl_sync(0xffffffffu, x, 24));
-                }
-            }
-            if (lane == 0) {
-                const int u = unit0 + g;
-                if (kparts == 1) {
-                    tk_epilogue(ph, seg, u, totA, totB, n_past, pre, lle);
-                } else {
-                    // K-split combine state is per (tile group, tile parity), NOT per ring slot: a warp hands its slot back right after its
-                    // dot products, so with one slot per group a fast warp could already be combining the NEXT tile of the same slot while a
-                    // slow warp is still combining this one (seen with 24 KB q4_1 tiles, where only 4 slots fit).  A warp can be at most one
-                    // tile ahead of the slowest warp of its group (the next tile only arrives once everybody released this one): two buffers.
-                    const int cb = (tg * 2 + (int)(kround & 1u)) * TK_GMAX + g;
-                    volatile float *rb = rowbuf + (size_t)cb * 8;                     // [2 rows][kparts <= 4]
-                    rb[p] = totA;
-                    rb[4 + p] = totB;
-                    __threadfence_block();
-                    const int old = atomicAdd(&cnt[cb], 1);
-                    if (old == kparts - 1) {                                            // last arriver combines, parts in index order
-                        cnt[cb] = 0;
-                        __threadfence_block();
-                        float x0 = rb[0], x1 = rb[4];
-                        for (int q = 1; q < kparts; q++) { x0 = __fadd_rn(x0, rb[q]); x1 = __fadd_rn(x1, rb[4 + q]); }
-                        tk_epilogue(ph, seg, u, x0, x1, n_past, pre, lle);
-                    }
-                }
-            }
-        } else {
-            __syncwarp();
-            if (lane == 0) fl_mbar_arrive(bar0 + 8u * (S + s));      // no unit of this tile for the warp
+            if (PROF) { const unsigned t = tk_clock(); c_dot += t - c_t; c_t = t; }
         }
-        kround++;
-        s += TK_TG;
-        if (s >= S) { s -= S; par ^= 1u; }
-        if (PROF) { const unsigned c = tk_clock(); c_tail += c - c_t; c_t = c; }
+        float tot = fx_reduce(a0, a1);                                  // valid in lane 4r
+        if (TYPE == FL_TYPE_Q4_1) tot = __fadd_rn(tot, sm);
+        const float other = __shfl_down_sync(0xffffffffu, tot, swiglu ? 16 : 4);
+        if (leader && pr < nunits) tk_epilogue(ph, seg, unit0 + pr, tot, other, n_past, pre, lle);
+        if (PROF) { const unsigned t = tk_clock(); c_tail += t - c_t; c_t = t; }
     }
+    cg += (uint32_t)(st.n_g * C);
     if (PROF && lane == 0 && pw) {
-        pw[0] = c_yp; pw[1] = c_wait; pw[2] = c_dot; pw[3] = c_tail; pw[4] = c_rounds; pw[5] = tk_clock() - c_begin; pw[6] = (unsigned)ntiles; pw[7] = 0;
+        pw[0] = 0; pw[1] = c_wait; pw[2] = c_dot; pw[3] = c_tail; pw[4] = c_rounds; pw[5] = tk_clock() - c_begin; pw[6] = (unsigned)sl.ntiles; pw[7] = 0;
     }
 }
 
 // ---- attention phase: one head, all consumer threads of the CTA ------------------------------------
 __device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params &prm, float *sc, double *red, int head, int part_id, int warp, int lane, int tid) {
     float *redf = (float *)(red + 20);                // [16] floats; red[0..16] are the double partials
-    float *part = sc + ph.n_ctx;                      // [FD_PV_SUBS][dims of this CTA]
     const int hd = ph.head_dim;
     const int n_pos = *ph.a.n_past + 1;
     const float *q = ph.q + (size_t)head * hd;
@@ -626,7 +585,7 @@ __device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
-                const float a = fl_warp_sum(acc[u]);
+                const float a = fx_reduce_f32(acc[u]);             // ggml_vec_dot_f32's order: lane l = element l of its 32-float step
                 if (lane == 0 && j0 + u < n_pos) sc[j0 + u] = __fmul_rn(a, ph.scale);
             }
         }
@@ -640,7 +599,7 @@ __device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const float a = fl_warp_sum(acc[u]);
+                const float a = fx_reduce_f32(acc[u]);
                 if (lane == 0 && j0 + u < n_pos) sc[j0 + u] = __fmul_rn(a, ph.scale);
             }
         }
@@ -669,17 +628,23 @@ __device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params
     // each thread normalises exactly the entries it wrote above, so no barrier is needed in between
     for (int j = tid; j < n_pos; j += TK_NT) sc[j] = __fmul_rn(sc[j], inv);
     tk_bar_consumers(12);
-    // P*V in the canonical order of fd_pv_partials; this CTA owns dpc = head_dim / head_split output dimensions
+    // P*V, one warp per output dimension, in ggml_vec_dot_f32's order (src0 row = the dimension's cached values over the positions,
+    // src1 row = the probabilities): 32-float steps into lane-wise accumulators, the reference's reduction tree, then the
+    // n_pos % 32 leftovers one by one (fx_left_nma).  This CTA owns dpc = head_dim / head_split dimensions.
     const int dpc = hd / ph.head_split;
-    const int tpd = TK_NT / dpc;                        // threads per dimension (<= FD_PV_SUBS)
-    const int ns = FD_PV_SUBS / tpd;
-    {
-        const int dl = tid % dpc, sub0 = (tid / dpc) * ns;
+    const int np = n_pos & ~31, rem = n_pos - np, nma = fx_left_nma(rem);
+    for (int dl = warp; dl < dpc; dl += TK_CW) {
         const int d = part_id * dpc + dl;
-        fd_pv_store_partials<4>(ph.vcache + ((size_t)head * hd + d) * ph.n_ctx, sc, n_pos, sub0, ns, part, dpc, dl);
+        const float *vrow = ph.vcache + ((size_t)head * hd + d) * ph.n_ctx;
+        float acc = 0.0f;
+        const float lx = (lane < rem) ? __ldcg(vrow + np + lane) : 0.0f, ly = (lane < rem) ? sc[np + lane] : 0.0f;
+        const float lv = __fmul_rn(lx, ly);
+        for (int k = lane; k < np; k += 32) acc = __fmaf_rn(__ldcg(vrow + k), sc[k], acc);
+        float o = fx_reduce_f32(acc);
+        for (int k = 0; k < nma; k++) o = __fadd_rn(o, __shfl_sync(0xffffffffu, lv, k));
+        for (int k = nma; k < rem; k++) o = __fmaf_rn(__shfl_sync(0xffffffffu, lx, k), __shfl_sync(0xffffffffu, ly, k), o);
+        if (lane == 0) ph.out[(size_t)head * hd + d] = o;
     }
-    tk_bar_consumers(12);
-    if (tid < dpc) ph.out[(size_t)head * hd + part_id * dpc + tid] = fd_pv_combine(part, dpc, tid);
 }
 // pull the cached positions of this head towards L2 while the grid is still finishing the previous phase
 __device__ __forceinline__ void tk_attention_prefetch(const tk_phase &ph, int head, int part_id, int tid) {
@@ -697,25 +662,12 @@ __device__ __forceinline__ void tk_attention_prefetch(const tk_phase &ph, int he
     }
 }
 
-template <int TYPE, bool PROF>
-__device__ __forceinline__ void tk_consume_dispatch(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, unsigned &kround, const tk_yblock *ysm,
-                                                    float *rowbuf, int *cnt, uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw, unsigned lle) {
-    switch (ph.nfull) {
-        case 4: tk_consume<TYPE, 4, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
-        case 3: tk_consume<TYPE, 3, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
-        case 2: tk_consume<TYPE, 2, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
-        default: tk_consume<TYPE, 0, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle); break;
-    }
-}
-
 template <bool PROF>
 __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = (uint64_t *)smem;
     tk_yblock *ysm = (tk_yblock *)(smem + prm.off_y);
     double *red = (double *)(smem + prm.off_red);            // 32 doubles
-    float *rowbuf = (float *)(smem + prm.off_rowbuf);        // [S][TK_GMAX][2][4]
-    int *cnt = (int *)(smem + prm.off_cnt);                  // [S][TK_GMAX]
     float *sc = (float *)(smem + prm.off_sc);                // attention: [n_ctx] + [256]
     uint8_t *stage0 = smem + prm.off_stage0;
     // Phase descriptors are read from shared memory: every gpu-scope acquire invalidates L1, so reading them from
@@ -735,54 +687,61 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         const int pg = warp - TK_CW;
         if (pg == 0 && lane == 0) {
             for (int s = 0; s < S; s++) {
-                fl_mbar_init(bar0 + 8u * s, 1);
-                fl_mbar_init(bar0 + 8u * (S + s), TK_WPG);
+                fl_mbar_init(bar0 + 8u * s, 1);                  // full: the producer's expect_tx arrival + the copies' bytes
+                fl_mbar_init(bar0 + 8u * (S + s), 1);            // empty: the one consumer warp that owns the tile
             }
             fl_mbar_fence_init();
         }
         __syncwarp();
         asm volatile("bar.sync 14, %0;" ::"r"(TK_THREADS) : "memory");          // barriers initialised (consumers and the other producers wait here too)
-        if (lane == 0) {
+        {
+            // All 32 lanes walk the stream; lane 0 waits for the slot and posts the byte count, lanes 0-7 issue one row piece each.
             const uint64_t pol = fl_policy_evict_first();
-            int T0 = 0;                                                          // global index of the phase's first tile (this CTA)
+            int T0 = 0;                                                          // tasks of all earlier phases (this CTA): rotates the groups
+            uint32_t cg = 0;                                                     // tiles of all earlier phases in this group's stream
             for (int pi = 0; pi < prm.n_phases; pi++) {
                 // The descriptor lives in global memory; everything the tile loop needs is pulled into registers once per phase
                 // (one L2 round trip, hidden because the producer runs ahead).
                 const tk_phase *gp = prm.phases + pi;
                 if (__ldg(&gp->kind) != TK_PH_MATVEC) continue;
-                const int G = __ldg(&gp->G), lgG = __ldg(&gp->lgG), swiglu = __ldg(&gp->swiglu);
+                const int swiglu = __ldg(&gp->swiglu), C = __ldg(&gp->nchunks), nb = __ldg(&gp->nb), type = __ldg(&gp->a.type);
                 const int m0 = __ldg(&gp->units[0]), m1 = __ldg(&gp->units[1]), m2 = __ldg(&gp->units[2]);
-                const uint32_t row_bytes = __ldg(&gp->row_bytes);
+                const uint32_t row_bytes = __ldg(&gp->row_bytes), srow = __ldg(&gp->srow);
+                const uint32_t bb = (type == FL_TYPE_Q4_0) ? 20u : 24u;
                 const uint8_t *w0 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[0]);
                 const uint8_t *w1 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[1]);
                 const uint8_t *w2 = (const uint8_t *)__ldg((const unsigned long long *)&gp->a.seg_w[2]);
-                const tk_slice sl = tk_make_slice_u(m0, m1, m2, lgG, prm.grid_magic, prm.grid_shift);
-                int t = ((pg - (T0 & 3)) + 4) & 3;                               // first tile of this phase that belongs to group pg
-                int T = T0 + t;
-                const uint32_t rounds = tk_div((uint32_t)T, prm.s_magic, prm.s_shift);
-                int s = T - (int)rounds * S;                                     // slot T % S (S is a multiple of 4: s % 4 == pg)
-                uint32_t par = (rounds & 1u) ^ 1u;
-                for (; t < sl.ntiles; t += TK_TG) {
-                    int seg, unit0, nunits;
-                    tk_tile_of(sl, G, t, seg, unit0, nunits);
-                    fl_mbar_wait(bar0 + 8u * (S + s), par);
-                    const uint32_t dst = fl_smem_u32(stage0 + (size_t)s * prm.slot_bytes);
-                    if (prm.diag & 1) {
-                        fl_mbar_arrive(bar0 + 8u * s);
-                    } else if (swiglu) {
-                        const uint32_t half = (uint32_t)nunits * row_bytes;
-                        fl_mbar_expect_tx(bar0 + 8u * s, 2 * half);
-                        fl_bulk_g2s_hint(dst, w0 + (size_t)unit0 * row_bytes, half, bar0 + 8u * s, pol);
-                        fl_bulk_g2s_hint(dst + half, w1 + (size_t)unit0 * row_bytes, half, bar0 + 8u * s, pol);
-                    } else {
-                        const uint32_t bytes = 2u * (uint32_t)nunits * row_bytes;
-                        const uint8_t *w = seg == 0 ? w0 : seg == 1 ? w1 : w2;
-                        fl_mbar_expect_tx(bar0 + 8u * s, bytes);
-                        fl_bulk_g2s_hint(dst, w + (size_t)(2 * unit0) * row_bytes, bytes, bar0 + 8u * s, pol);
+                const tk_slice sl = tk_make_slice_u(m0, m1, m2, 2, prm.grid_magic, prm.grid_shift);
+                const tk_stream st = tk_stream_of(pg, T0, sl.ntiles);
+                for (int k0 = 0; k0 < st.n_g; k0 += TK_WPG) {
+                    const int n_r = min(TK_WPG, st.n_g - k0);
+                    for (int c = 0; c < C; c++) {
+                        const uint32_t cbytes = (uint32_t)min(TK_CHB, nb - c * TK_CHB) * bb;
+                        for (int wl = 0; wl < n_r; wl++) {
+                            int seg, unit0, nunits;
+                            tk_tile_of(sl, TK_GMAX, st.first + 4 * (k0 + wl), seg, unit0, nunits);
+                            int s;
+                            uint32_t par;
+                            tk_slot_of(prm, pg, cg + (uint32_t)(k0 * C + c * n_r + wl), s, par);
+                            // row piece of this lane: default rows 2*unit0 .. 2*unit0 + 2*nunits - 1 of the segment's matrix;
+                            // swiglu: lanes 0-3 rows unit0.. of w1, lanes 4-7 the same rows of w3
+                            const uint8_t *src = nullptr;
+                            if (lane < 8) {
+                                if (swiglu) { if ((lane & 3) < nunits) src = ((lane < 4) ? w0 : w1) + (size_t)(unit0 + (lane & 3)) * row_bytes; }
+                                else if (lane < 2 * nunits) src = (seg == 0 ? w0 : seg == 1 ? w1 : w2) + (size_t)(2 * unit0 + lane) * row_bytes;
+                            }
+                            if (lane == 0) {
+                                fl_mbar_wait(bar0 + 8u * (S + s), par ^ 1u);
+                                if (prm.diag & 1) fl_mbar_arrive(bar0 + 8u * s);
+                                else fl_mbar_expect_tx(bar0 + 8u * s, 2u * (uint32_t)nunits * cbytes);
+                            }
+                            __syncwarp();
+                            if (src && !(prm.diag & 1))
+                                fl_bulk_g2s_hint(fl_smem_u32(stage0 + (size_t)s * prm.slot_bytes + (size_t)lane * srow), src + (size_t)c * (TK_CHB * bb), cbytes, bar0 + 8u * s, pol);
+                        }
                     }
-                    s += TK_TG;
-                    if (s >= S) { s -= S; par ^= 1u; }
                 }
+                cg += (uint32_t)(st.n_g * C);
                 T0 += sl.ntiles;
             }
         }
@@ -792,14 +751,13 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
     // ------------------------------ consumers ------------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TK_REGS_CONSUMER));
     const int tid = threadIdx.x;
-    for (int i = tid; i < max(S, 2 * TK_TG) * TK_GMAX; i += TK_NT) cnt[i] = 0;
     static_assert(sizeof(tk_phase) % 4 == 0 && sizeof(tk_phase) / 4 <= TK_NT, "descriptor copy is one word per thread");
     if (warp == TK_CW - 1)
         for (int i = lane; i < (int)(sizeof(tk_phase) / 4); i += 32) ((uint32_t *)&phs[0])[i] = ((const uint32_t *)&prm.phases[0])[i];
     tk_bar_consumers(15);
     asm volatile("bar.sync 14, %0;" ::"r"(TK_THREADS) : "memory");     // mbarriers initialised
     int T0 = 0;
-    unsigned kround = 0;                                     // tiles this warp's group has processed (selects the K-split combine buffer)
+    uint32_t cg = 0;                                         // tiles of all earlier phases in this warp's group's stream
     unsigned epoch = 0;
     // cross-GPU epochs continue across launches AND plans: the running count lives next to the flags (word 8 * 32 of the
     // rank's own shared buffer), so flags left behind by earlier launches can never satisfy a later wait
@@ -841,15 +799,15 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
             continue;
         }
         const int K = ph.nb * 32;
-        if (tid == TK_NT - 1) sl_sh = tk_make_slice_u(ph.units[0], ph.units[1], ph.units[2], ph.lgG, prm.grid_magic, prm.grid_shift);
+        if (tid == TK_NT - 1) sl_sh = tk_make_slice_u(ph.units[0], ph.units[1], ph.units[2], 2, prm.grid_magic, prm.grid_shift);
         if (!(prm.diag & 8)) tk_prologue(ph.a, K, ysm, red, warp, lane, tid, lle, err);
         if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
         tk_bar_consumers(15);                                    // activations, slice and next descriptor are in shared memory
         if (pr) pr[2] = tk_now();
         const tk_slice &sl = sl_sh;
         unsigned *pw = (PROF && prm.prof2) ? prm.prof2 + (((size_t)pi * gridDim.x + blockIdx.x) * TK_CW + warp) * 8 : nullptr;
-        if (ph.a.type == FL_TYPE_Q4_0) tk_consume_dispatch<FL_TYPE_Q4_0, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle);
-        else                           tk_consume_dispatch<FL_TYPE_Q4_1, PROF>(ph, prm, sl, T0, kround, ysm, rowbuf, cnt, stage0, bar0, warp, lane, pw, lle);
+        if (ph.a.type == FL_TYPE_Q4_0) tk_consume<FL_TYPE_Q4_0, PROF>(ph, prm, sl, T0, cg, ysm, stage0, bar0, warp, lane, pw, lle);
+        else                           tk_consume<FL_TYPE_Q4_1, PROF>(ph, prm, sl, T0, cg, ysm, stage0, bar0, warp, lane, pw, lle);
         T0 += sl.ntiles;
         if (pr) pr[3] = tk_now();
     }
@@ -887,16 +845,10 @@ static int tk_geometry(tk_phase &ph, size_t &tile_bytes) {
     const int nb = a.K / 32;
     const size_t row_bytes = a.row_stride_bytes ? a.row_stride_bytes : (size_t)nb * bb;
     FL_REQUIRE(bb > 0 && a.K > 0 && a.K % 32 == 0 && row_bytes % 16 == 0, "token kernel: unsupported matrix K=%d", a.K);
-    int kparts = 1;
-    while (kparts * 128 < nb) kparts *= 2;
-    FL_REQUIRE(kparts <= TK_WPG, "token kernel: K=%d needs %d K-slices (max %d)", a.K, kparts, TK_WPG);
-    const int P = (nb + kparts - 1) / kparts;
-    const int last = nb - (kparts - 1) * P;
-    FL_REQUIRE(last > 0, "token kernel: K=%d splits badly", a.K);
-    int nfull = std::min(P, last) / 32;
-    if (nfull > FD_NBL) nfull = FD_NBL;
-    if (nfull == 1) nfull = 0;
-    const int G = TK_WPG / kparts;
+    // the 32 lanes of a warp (8 rows x 4 lanes) hit 32 different banks when the row pitch is an odd multiple of 16 bytes
+    const uint32_t chunk_bytes = (uint32_t)std::min(nb, TK_CHB) * bb;
+    FL_REQUIRE(chunk_bytes % 16 == 0 && ((size_t)nb * bb) % 16 == 0, "token kernel: K=%d gives row pieces that are not multiples of 16 bytes", a.K);
+    const uint32_t srow = (chunk_bytes / 16) % 2 ? chunk_bytes : chunk_bytes + 16;
     ph.units[0] = ph.units[1] = ph.units[2] = 0;
     if (ph.swiglu) {
         ph.units[0] = a.seg_rows[0];
@@ -913,8 +865,8 @@ static int tk_geometry(tk_phase &ph, size_t &tile_bytes) {
     FL_REQUIRE(a.epi != FL_EPI_RESADD || ((uintptr_t)a.res & 7) == 0, "token kernel: residual is not 8-byte aligned");
     FL_REQUIRE((long)ph.units[0] + ph.units[1] + ph.units[2] < (1 << 23), "token kernel: too many rows");
     ph.kind = TK_PH_MATVEC;
-    ph.nb = nb; ph.kparts = kparts; ph.G = G; ph.lgG = (G == 4) ? 2 : (G == 2) ? 1 : 0; ph.P = P; ph.nfull = nfull; ph.row_bytes = (uint32_t)row_bytes;
-    tile_bytes = (size_t)2 * G * row_bytes;
+    ph.nb = nb; ph.nchunks = (nb + TK_CHB - 1) / TK_CHB; ph.srow = srow; ph.row_bytes = (uint32_t)row_bytes;
+    tile_bytes = (size_t)2 * TK_GMAX * srow;
     return 0;
 }
 
@@ -979,23 +931,22 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     fl_token_plan_impl *pl = new fl_token_plan_impl();
     tk_params &p = pl->prm;
     const size_t slot = (max_tile + 127) & ~(size_t)127;
-    int S = 16;
+    int S = 64;
     size_t off = 0;
     for (;; S -= 4) {
-        if (S < 4) { flk_token_plan_destroy(pl); fl_set_error("token kernel: tiles of %zu bytes do not fit shared memory", slot); return -1; }
+        if (S < 8) { flk_token_plan_destroy(pl); fl_set_error("token kernel: tiles of %zu bytes do not fit shared memory", slot); return -1; }
         p.off_y = ((size_t)(2 * S) * 8 + 127) & ~(size_t)127;
         p.off_red = (p.off_y + max_y + 127) & ~(size_t)127;
-        p.off_rowbuf = (p.off_red + 32 * sizeof(double) + 127) & ~(size_t)127;
-        const size_t ncomb = (size_t)std::max(S, 2 * TK_TG) * TK_GMAX;          // K-split combine buffers: (tile group, tile parity, unit)
-        p.off_cnt = (p.off_rowbuf + ncomb * 8 * sizeof(float) + 127) & ~(size_t)127;
-        p.off_sc = (p.off_cnt + ncomb * sizeof(int) + 127) & ~(size_t)127;
-        off = (p.off_sc + ((size_t)max_ctx + FD_PV_SUBS * 256) * sizeof(float) + 127) & ~(size_t)127;
+        p.off_sc = (p.off_red + 32 * sizeof(double) + 127) & ~(size_t)127;
+        off = (p.off_sc + ((size_t)max_ctx + 32) * sizeof(float) + 127) & ~(size_t)127;
         if (off + (size_t)S * slot <= (size_t)optin - 1024) break;
     }
+    p.off_rowbuf = p.off_cnt = 0;
     p.off_stage0 = (uint32_t)off;
     p.S = S;
+    p.Sg = S / TK_TG;
     tk_magic((uint32_t)sm, p.grid_magic, p.grid_shift);
-    tk_magic((uint32_t)S, p.s_magic, p.s_shift);
+    tk_magic((uint32_t)p.Sg, p.s_magic, p.s_shift);
     p.slot_bytes = (uint32_t)slot;
     p.n_phases = n_steps;
     // measured on B200 (round 1): prefetching a whole phase competes with the demand loads of the phase still running

@@ -1043,6 +1043,7 @@ struct DecodeState {
     char *h_out = nullptr;      // pinned staging of the step's results (logits, then the embeddings row): the caller's arena is pageable
     size_t h_out_cap = 0;
     bool enabled = true, use_graph = true, use_token_kernel = true, inited = false;
+    bool no_token_plan = false;       // the current plan's graph is not one the token kernel takes: node-by-node execution
     bool tp_kv_sharded = false;   // tensor-parallel decode steps have written only this rank's heads into the KV cache ...
     int tp_first_pos = 0, tp_end_pos = 0;   // ... for positions [tp_first_pos, tp_end_pos)
 };
@@ -1473,29 +1474,44 @@ bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, 
     D.h_scalars[1] = O.token;
     FLC(fl_h2d(D.d_npast, &D.h_scalars[0], sizeof(int)));
     FLC(fl_h2d(D.ws.d_tok, &D.h_scalars[1], sizeof(int)));
-    if (g_profile || !D.use_graph) {
-        FLC(fl_event_record(ev0));
-        issue_decode(P, D.d_npast);
-        FLC(fl_event_record(ev1));
-        g_decode_mode = 1;
-        return true;
-    }
-    if (!D.graph || !same_plan(P, D.plan)) {
+    // The persistent token kernel adds every fp32 term in the reference's order (fl_exact.cuh); the one-kernel-per-matrix-group path of
+    // round 1 (k_mv_fused / k_attn_decode) does not, so it only runs on request (FASTLLAMA_B200_MULTI_KERNEL=1, measurements) or
+    // across GPUs without peer mapping.  A graph the token kernel cannot take is executed node by node (reference order as well).
+    static const bool legacy_env = getenv("FASTLLAMA_B200_MULTI_KERNEL") != nullptr;
+    const bool legacy = legacy_env || !D.use_token_kernel || (P.world > 1 && !D.ws.peer_mapped);
+    const bool eager = g_profile || !D.use_graph;
+    if (!same_plan(P, D.plan) || (!legacy && P.world == 1 && !D.token_plan && !D.no_token_plan) || (!eager && !D.graph && !D.no_token_plan)) {
         if (D.graph) { FLC(fl_sync()); FLC(fl_graph_destroy(D.graph)); D.graph = nullptr; }
-        if (D.token_plan) { FLC(fl_token_plan_destroy(D.token_plan)); D.token_plan = nullptr; }
-        if (D.use_token_kernel && (P.world == 1 || D.ws.peer_mapped)) D.token_plan = make_token_plan(P, D.ws, D.d_npast);
-        // one eager pass first: sets kernel attributes, and gives this token's result
+        if (D.token_plan) { FLC(fl_sync()); FLC(fl_token_plan_destroy(D.token_plan)); D.token_plan = nullptr; }
+        D.no_token_plan = false;
+        if (!legacy) {
+            D.token_plan = make_token_plan(P, D.ws, D.d_npast);
+            D.no_token_plan = D.token_plan == nullptr && P.world == 1;      // across GPUs the weights are sharded: the multi-kernel path takes over
+        }
+        D.plan = P;
+        if (!D.no_token_plan) {
+            // one eager pass first: sets kernel attributes, and gives this token's result
+            FLC(fl_event_record(ev0));
+            if (D.token_plan) issue_decode_token_kernel(P, D.token_plan); else issue_decode(P, D.d_npast);
+            FLC(fl_event_record(ev1));
+            if (!eager) {
+                FLC(fl_graph_begin_capture());
+                if (D.token_plan) issue_decode_token_kernel(P, D.token_plan); else issue_decode(P, D.d_npast);
+                FLC(fl_graph_end_capture(&D.graph));
+            }
+            g_decode_mode = D.token_plan ? 2 : 1;
+            if (g_verbose) fprintf(stderr, "[ggml_b200] decode plan %s: %d layers, n_embd %d, n_ctx %d, %s\n", eager ? "built" : "captured", P.n_layer, P.n_embd, P.n_ctx,
+                                   D.token_plan ? "persistent token kernel" : "one kernel per matrix group");
+            return true;       // the eager pass already produced this token (capture does not execute)
+        }
+    }
+    if (D.no_token_plan) return false;          // node by node
+    if (eager) {
         FLC(fl_event_record(ev0));
         if (D.token_plan) issue_decode_token_kernel(P, D.token_plan); else issue_decode(P, D.d_npast);
         FLC(fl_event_record(ev1));
-        FLC(fl_graph_begin_capture());
-        if (D.token_plan) issue_decode_token_kernel(P, D.token_plan); else issue_decode(P, D.d_npast);
-        FLC(fl_graph_end_capture(&D.graph));
-        D.plan = P;
         g_decode_mode = D.token_plan ? 2 : 1;
-        if (g_verbose) fprintf(stderr, "[ggml_b200] decode plan captured: %d layers, n_embd %d, n_ctx %d, %s\n", P.n_layer, P.n_embd, P.n_ctx,
-                               D.token_plan ? "persistent token kernel" : "one kernel per matrix group");
-        return true;       // the eager pass already produced this token (capture does not execute)
+        return true;
     }
     FLC(fl_event_record(ev0));
     FLC(fl_graph_launch(D.graph));
@@ -1513,6 +1529,7 @@ static void decode_state_release() {
     if (D.token_plan) { fl_token_plan_destroy(D.token_plan); D.token_plan = nullptr; }
     if (D.ws.xa) { fl_dev_free(D.ws.xa); D.ws = DecodeWs(); }      // the peer-mapped reduction buffers (tensor parallel) stay: they are per process
     D.plan = DecodePlan();
+    D.no_token_plan = false;
     D.tp_kv_sharded = false;
     g_tp_kv_sharded = false;
     if (g_exec.q8_work) { fl_dev_free(g_exec.q8_work); g_exec.q8_work = nullptr; g_exec.q8_cap = 0; }

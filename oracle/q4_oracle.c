@@ -211,8 +211,10 @@ void orc_quantize_row_q4_1_simd(const float *x, void *vy, int k) {
 }
 
 /* ggml_vec_dot_f32 (lib/ggml.c:2295-2325) as the AVX2 + FMA build computes it: 4 accumulators of 8 lanes over steps of 32    */
-/* (GGML_F32_STEP 32, GGML_F32_EPR 8), the GGML_F32x8_REDUCE tree (:1943-1958), then the leftovers as a rounded product     */
-/* plus a rounded add per element (what the compiled reference does; no fma there).                                           */
+/* (GGML_F32_STEP 32, GGML_F32_EPR 8), the GGML_F32x8_REDUCE tree (:1943-1958), then the leftover loop                        */
+/* "sumf += x[i]*y[i]" as gcc -O3 compiles it for this target: the loop is vectorised (products 8 at a time, then one group   */
+/* of 4, each product ROUNDED and added in order -- no fma), and the scalar epilogue of the last <= 3 elements is contracted   */
+/* to an fma.  Pinned by tests/golden/lora_ops.npz (leftovers 8, 16) and tests/golden/f32_dot.npz (every leftover count).      */
 float orc_vec_dot_f32(int n, const float *x, const float *y) {
     float sum[4][8];
     for (int j = 0; j < 4; j++) for (int l = 0; l < 8; l++) sum[j][l] = 0.0f;
@@ -223,7 +225,10 @@ float orc_vec_dot_f32(int n, const float *x, const float *y) {
     float t[8];
     for (int l = 0; l < 8; l++) t[l] = (sum[0][l] + sum[1][l]) + (sum[2][l] + sum[3][l]);
     float sumf = ((t[0] + t[4]) + (t[1] + t[5])) + ((t[2] + t[6]) + (t[3] + t[7]));
-    for (int i = np; i < n; i++) { const float p = x[i] * y[i]; sumf = sumf + p; }   /* the leftover loop is vectorised by gcc into mul + add, not an fma (pinned by tests/golden/lora_ops.npz) */
+    const int rem = n - np;
+    const int nma = (rem & ~7) + ((rem & 4) ? 4 : 0);
+    for (int i = np; i < np + nma; i++) { const float p = x[i] * y[i]; sumf = sumf + p; }
+    for (int i = np + nma; i < n; i++) sumf = fmaf(x[i], y[i], sumf);
     return sumf;
 }
 

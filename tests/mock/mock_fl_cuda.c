@@ -221,7 +221,7 @@ int fl_dev_rope(const fl_view *t, int n_past, int n_dims, int mode) {
         for (int i0 = 0; i0 < n_dims; i0 += 2) {
             float c = cosf(theta), s = sinf(theta); theta *= ts;
             float *p0 = (float *)at(t, (mode & 2) ? i0 / 2 : i0, i1, i2, i3), *p1 = (float *)at(t, (mode & 2) ? i0 / 2 + n_dims / 2 : i0 + 1, i1, i2, i3);
-            float x0 = *p0, x1 = *p1; *p0 = x0 * c - x1 * s; *p1 = x0 * s + x1 * c;
+            float x0 = *p0, x1 = *p1; *p0 = fmaf(x0, c, -(x1 * s)); *p1 = fmaf(x0, s, x1 * c);   /* the reference build contracts these (GNU mode) */
         }
     }
     return 0;
@@ -229,11 +229,13 @@ int fl_dev_rope(const fl_view *t, int n_past, int n_dims, int mode) {
 int fl_dev_cpy_f32(const fl_view *s, const fl_view *d) { g_launches++; for (int64_t i = 0; i < nel(s); i++) *(float *)lin(d, i) = *(float *)lin(s, i); return 0; }
 int fl_dev_mul_mat_f32(const fl_view *a, const fl_view *b, const fl_view *d) {
     g_launches++;
+    const int64_t K = a->ne[0];
+    float *xs = malloc(sizeof(float) * (K ? K : 1)), *ys = malloc(sizeof(float) * (K ? K : 1));
     for (int64_t i3 = 0; i3 < d->ne[3]; i3++) for (int64_t i2 = 0; i2 < d->ne[2]; i2++) for (int64_t i1 = 0; i1 < d->ne[1]; i1++) for (int64_t i0 = 0; i0 < d->ne[0]; i0++) {
-        const float *x = (const float *)at(a, 0, i0, i2, i3), *y = (const float *)at(b, 0, i1, i2, i3); float acc = 0;
-        for (int64_t k = 0; k < a->ne[0]; k++) acc += x[k] * y[k];
-        *(float *)at(d, i0, i1, i2, i3) = acc;
+        for (int64_t k = 0; k < K; k++) { xs[k] = *(const float *)at(a, k, i0, i2, i3); ys[k] = *(const float *)at(b, k, i1, i2, i3); }
+        *(float *)at(d, i0, i1, i2, i3) = orc_vec_dot_f32((int)K, xs, ys);          /* ggml_vec_dot_f32's order */
     }
+    free(xs); free(ys);
     return 0;
 }
 
@@ -329,7 +331,7 @@ static void run_mv(const fl_mv_args *a) {
                 float x0 = tmp[r], x1 = tmp[r + 1];
                 if (sg < 2) {
                     float theta = (float)n_past; for (int i = 0; i < (r % hd) / 2; i++) theta *= ts;
-                    float c = cosf(theta), s = sinf(theta), y0 = x0 * c - x1 * s, y1 = x0 * s + x1 * c;
+                    float c = cosf(theta), s = sinf(theta), y0 = fmaf(x0, c, -(x1 * s)), y1 = fmaf(x0, s, x1 * c);
                     float *o = sg == 0 ? a->seg_dst[0] + r : a->kcache + (size_t)n_past * a->n_embd + r;
                     o[0] = y0; o[1] = y1;
                 } else { a->vcache[(size_t)r * a->n_ctx + n_past] = x0; a->vcache[(size_t)(r + 1) * a->n_ctx + n_past] = x1; }
@@ -349,11 +351,11 @@ static void run_attn(const mock_op *o) {
     float *p = malloc(sizeof(float) * n_pos);
     for (int h = 0; h < o->at.n_head; h++) {
         float mx = -INFINITY; double sum = 0;
-        for (int j = 0; j < n_pos; j++) { float acc = 0; for (int e = 0; e < hd; e++) acc += o->at.k[(size_t)j * o->at.n_embd + h * hd + e] * o->at.q[h * hd + e]; p[j] = acc * o->at.scale; if (p[j] > mx) mx = p[j]; }
+        for (int j = 0; j < n_pos; j++) { const float acc = orc_vec_dot_f32(hd, o->at.k + (size_t)j * o->at.n_embd + h * hd, o->at.q + h * hd); p[j] = acc * o->at.scale; if (p[j] > mx) mx = p[j]; }
         for (int j = 0; j < n_pos; j++) { float v = h2f(tab_exp[f2h(p[j] - mx)]); sum += v; p[j] = v; }
         float inv = (float)(1.0 / sum);
         for (int j = 0; j < n_pos; j++) p[j] *= inv;
-        for (int d = 0; d < hd; d++) { float acc = 0; for (int j = 0; j < n_pos; j++) acc += o->at.v[((size_t)h * hd + d) * o->at.n_ctx + j] * p[j]; o->at.out[h * hd + d] = acc; }
+        for (int d = 0; d < hd; d++) o->at.out[h * hd + d] = orc_vec_dot_f32(n_pos, o->at.v + ((size_t)h * hd + d) * o->at.n_ctx, p);
     }
     free(p);
 }

@@ -4,8 +4,8 @@ a tiny LLaMA built through the ggml C API like Model::eval builds it, 5-token pr
   * CPU: the reference library still reproduces the fixture bit for bit (pins the fixture; needs oracle/_ref);
   * CPU: our host stack (arena mirrors, executor, decode plan as the token program) on the CPU stand-in of the device layer;
   * GPU: the real thing -- prompt through the tensor-core ingest kernel, decode steps as the persistent token kernel.
-Tolerance for ours: logits within 2e-2 * max|logit| and the same argmax (whole graphs amplify last-ulp
-differences through q8_0 rounding and fp16 table lookups)."""
+Bar for ours: the SAME BITS as the reference library, logits and embeddings, prompt eval and decode steps (every fp32 operation of the
+path follows the reference's order, fl_exact.cuh; the 5-token prompt stays below the 16 columns from which the tcgen05 GEMM takes over)."""
 import os
 
 import numpy as np
@@ -38,9 +38,8 @@ def check_close(outs, gold):
     for i, (lg, emb) in enumerate(outs):
         rl, re = gold[f"logits{i}"], gold[f"emb{i}"]
         assert np.isfinite(lg).all()
-        assert np.abs(rl - lg).max() <= 2e-2 * np.abs(rl).max(), (i, np.abs(rl - lg).max(), np.abs(rl).max())
-        assert np.abs(re - emb).max() <= 2e-2 * np.abs(re).max()
-        assert np.array_equal(rl.argmax(-1), lg.argmax(-1))
+        nd = int((rl.view(np.uint32) != lg.view(np.uint32)).sum()), int((re.view(np.uint32) != emb.view(np.uint32)).sum())
+        assert nd == (0, 0), (i, nd, rl.size, float(np.abs(rl - lg).max()), float(np.abs(rl).max()))
 
 
 @pytest.mark.parametrize("name,t", TYPES)

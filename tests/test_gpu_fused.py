@@ -157,125 +157,127 @@ def test_attn_decode(fl, n_embd, n_head, n_ctx, n_past):
         fl.free(d)
 
 
+@pytest.fixture(scope="module")
+def cpu_model():
+    """The CPU stand-in of the device layer (tests/mock: the oracle's row functions behind the same C ABI), built under its own
+    soname so that it can sit next to the real libfl_cuda.so in this process."""
+    import os
+
+    from fastllama_b200.cuda_abi import FlCuda
+    from tests.mockbuild import ensure_mock
+
+    path = os.path.join(ensure_mock(), "libfl_cpumodel.so")
+    if not os.path.exists(path):
+        pytest.skip("tests/mock not built")
+    return FlCuda(path=path)
+
+
 @pytest.mark.parametrize("t", [GGML_TYPE_Q4_0, GGML_TYPE_Q4_1])
-@pytest.mark.parametrize("n_embd,n_head,n_ff,n_vocab,n_ctx,n_past,n_layer", [(256, 4, 768, 512, 32, 5, 2), (4096, 32, 11008, 32000, 512, 37, 2), (5120, 40, 13824, 32000, 512, 300, 1)])
-def test_token_kernel_equals_step_by_step(fl, t, n_embd, n_head, n_ff, n_vocab, n_ctx, n_past, n_layer):
-    """The persistent token kernel (fl_token_plan_*) runs the same steps as the per-matrix launches and must
-    reproduce them bit for bit: logits, q, attention output, and the KV cache rows it wrote."""
+@pytest.mark.parametrize("n_embd,n_head,n_ff,n_vocab,n_ctx,n_past,n_layer",
+                         [(256, 4, 768, 512, 32, 5, 2), (512, 4, 1408, 300, 64, 40, 2), (4096, 32, 11008, 32000, 512, 37, 2), (4096, 32, 11008, 2000, 512, 300, 1),
+                          (5120, 40, 13824, 32000, 512, 300, 1)])
+def test_token_kernel_has_the_reference_bits(fl, cpu_model, t, n_embd, n_head, n_ff, n_vocab, n_ctx, n_past, n_layer):
+    """The persistent token kernel (fl_token_plan_*) against the CPU model of the same steps, which is built from the oracle's
+    row functions (the reference's AVX2 accumulation order, pinned to the reference library in tests/test_oracle.py): logits, q,
+    attention output and the KV cache rows must be IDENTICAL, bit for bit."""
     from fastllama_b200.cuda_abi import EPI_QKV, EPI_RESADD, EPI_STORE, PRO_RMSNORM, PRO_SILUMUL, FlMvArgs, FlTokenStep
 
     rng = np.random.default_rng(n_embd + n_past)
     hd = n_embd // n_head
-    keep = []
-
-    def dev(a):
-        p = fl.to_device(a)
-        keep.append(p)
-        return p
-
-    def buf(n):
-        p = fl.alloc(n * 4)
-        fl.check(fl.lib.fl_dev_memset(p, 0, n * 4))
-        keep.append(p)
-        return p
-
-    def wq(m, k, s=0.03):
-        return dev(quant((rng.standard_normal((m, k)) * s).astype(np.float32), t))
-
-    def gam(n):
-        return dev((1.0 + 0.1 * rng.standard_normal(n)).astype(np.float32))
-
-    x0 = rng.standard_normal(n_embd).astype(np.float32)
-    dnp = dev(np.array([n_past], dtype=np.int32))
-    layers = []
-    for _ in range(n_layer):
-        kc = rng.standard_normal((n_ctx, n_embd)).astype(np.float32)
-        vc = rng.standard_normal((n_embd, n_ctx)).astype(np.float32)
-        layers.append(dict(wq=wq(n_embd, n_embd), wk=wq(n_embd, n_embd), wv=wq(n_embd, n_embd), wo=wq(n_embd, n_embd), w1=wq(n_ff, n_embd), w3=wq(n_ff, n_embd),
-                           w2=wq(n_embd, n_ff), g1=gam(n_embd), g2=gam(n_embd), kc_h=kc, vc_h=vc))
-    w_out, g_out = wq(n_vocab, n_embd), gam(n_embd)
-    fl.check(fl.lib.fl_dev_rope_table(hd, n_ctx))
-
-    def build(tag):
-        """Fresh buffers (and KV copies) so that both executions start from the same state."""
-        xa, xb, q, att, m1, m3, emb, logits = buf(n_embd), buf(n_embd), buf(n_embd), buf(n_embd), buf(n_ff), buf(n_ff), buf(n_embd), buf(n_vocab)
-        fl.check(fl.lib.fl_h2d(xa, x0.ctypes.data, n_embd * 4))
-        steps, kvs = [], []
-        for L in layers:
-            kc, vc = dev(L["kc_h"]), dev(L["vc_h"])
-            kvs.append((kc, vc))
-            a = FlMvArgs()
-            a.type, a.K, a.nseg, a.pro, a.epi = t, n_embd, 3, PRO_RMSNORM, EPI_QKV
-            for i, w in enumerate((L["wq"], L["wk"], L["wv"])):
-                a.seg_w[i], a.seg_rows[i] = w, n_embd
-            a.seg_dst[0] = q
-            a.x, a.gamma, a.n_past, a.n_ctx, a.n_embd, a.head_dim, a.kcache, a.vcache = xa, L["g1"], dnp, n_ctx, n_embd, hd, kc, vc
-            steps.append(("mv", a))
-            steps.append(("attn", (q, kc, vc, att)))
-            a = FlMvArgs()
-            a.type, a.K, a.nseg, a.pro, a.epi = t, n_embd, 1, 0, EPI_RESADD
-            a.seg_w[0], a.seg_rows[0], a.seg_dst[0], a.x, a.res = L["wo"], n_embd, xb, att, xa
-            steps.append(("mv", a))
-            a = FlMvArgs()
-            a.type, a.K, a.nseg, a.pro, a.epi = t, n_embd, 2, PRO_RMSNORM, EPI_STORE
-            a.seg_w[0], a.seg_rows[0], a.seg_dst[0] = L["w1"], n_ff, m1
-            a.seg_w[1], a.seg_rows[1], a.seg_dst[1] = L["w3"], n_ff, m3
-            a.x, a.gamma = xb, L["g2"]
-            steps.append(("mv", a))
-            a = FlMvArgs()
-            a.type, a.K, a.nseg, a.pro, a.epi = t, n_ff, 1, PRO_SILUMUL, EPI_RESADD
-            a.seg_w[0], a.seg_rows[0], a.seg_dst[0], a.x, a.b, a.res = L["w2"], n_embd, xa, m1, m3, xb
-            steps.append(("mv", a))
-        a = FlMvArgs()
-        a.type, a.K, a.nseg, a.pro, a.epi = t, n_embd, 1, PRO_RMSNORM, EPI_STORE
-        a.seg_w[0], a.seg_rows[0], a.seg_dst[0], a.x, a.gamma, a.normed_out = w_out, n_vocab, logits, xa, g_out, emb
-        steps.append(("mv", a))
-        return steps, dict(xa=(xa, n_embd), q=(q, n_embd), att=(att, n_embd), emb=(emb, n_embd), logits=(logits, n_vocab)), kvs
-
     scale = np.float32(1.0 / math.sqrt(hd))
 
-    def snapshot(outs, kvs):
-        r = {k: fl.to_host(p, (n,), np.float32) for k, (p, n) in outs.items()}
-        for i, (kc, vc) in enumerate(kvs):
-            r[f"k{i}"] = fl.to_host(kc, (n_ctx, n_embd), np.float32)
-            r[f"v{i}"] = fl.to_host(vc, (n_embd, n_ctx), np.float32)
-        return r
+    def wq(m, k, s=0.03):
+        return quant((rng.standard_normal((m, k)) * s).astype(np.float32), t)
 
-    steps, outs, kvs = build("ref")
-    for kind, s in steps:
-        if kind == "mv":
-            fl.check(fl.lib.fl_dev_mv_fused(C.byref(s)))
-        else:
-            fl.check(fl.lib.fl_dev_attn_decode(s[0], s[1], s[2], s[3], dnp, n_embd, n_head, hd, n_ctx, scale))
-    fl.check(fl.lib.fl_sync())
-    want = snapshot(outs, kvs)
+    def gam(n):
+        return (1.0 + 0.1 * rng.standard_normal(n)).astype(np.float32)
 
-    steps, outs, kvs = build("tok")
-    arr = (FlTokenStep * len(steps))()
-    for i, (kind, s) in enumerate(steps):
-        if kind == "mv":
-            arr[i].kind, arr[i].mv = 0, s
-        else:
-            arr[i].kind = 1
-            arr[i].q, arr[i].kcache, arr[i].vcache, arr[i].out, arr[i].n_past = s[0], s[1], s[2], s[3], dnp
-            arr[i].k_row_stride, arr[i].n_head, arr[i].head_dim, arr[i].n_ctx, arr[i].scale = n_embd, n_head, hd, n_ctx, scale
-    plan = C.c_void_p()
-    fl.check(fl.lib.fl_token_plan_create(arr, len(steps), C.byref(plan)))
-    for _ in range(3):                       # relaunching must be idempotent for everything but the residual stream
-        steps2, outs, kvs = build("tok")
-        for i, (kind, s) in enumerate(steps2):
-            if kind == "mv":
-                arr[i].mv = s
-            else:
-                arr[i].q, arr[i].kcache, arr[i].vcache, arr[i].out = s[0], s[1], s[2], s[3]
-        fl.check(fl.lib.fl_token_plan_destroy(plan))
-        fl.check(fl.lib.fl_token_plan_create(arr, len(steps), C.byref(plan)))
-        fl.check(fl.lib.fl_token_plan_launch(plan))
-        fl.check(fl.lib.fl_sync())
-        got = snapshot(outs, kvs)
-        for k in want:
-            assert np.array_equal(got[k], want[k]), (k, np.abs(got[k] - want[k]).max())
-    fl.check(fl.lib.fl_token_plan_destroy(plan))
+    x0 = rng.standard_normal(n_embd).astype(np.float32)
+    layers = []
+    for _ in range(n_layer):
+        layers.append(dict(wq=wq(n_embd, n_embd), wk=wq(n_embd, n_embd), wv=wq(n_embd, n_embd), wo=wq(n_embd, n_embd), w1=wq(n_ff, n_embd), w3=wq(n_ff, n_embd),
+                           w2=wq(n_embd, n_ff), g1=gam(n_embd), g2=gam(n_embd), kc=rng.standard_normal((n_ctx, n_embd)).astype(np.float32),
+                           vc=rng.standard_normal((n_embd, n_ctx)).astype(np.float32)))
+    w_out, g_out = wq(n_vocab, n_embd), gam(n_embd)
+
+    def run(be, relaunches):
+        keep = []
+
+        def dev(a):
+            p = be.to_device(a)
+            keep.append(p)
+            return p
+
+        def buf(n):
+            p = be.alloc(n * 4)
+            be.check(be.lib.fl_dev_memset(p, 0, n * 4))
+            keep.append(p)
+            return p
+
+        be.check(be.lib.fl_dev_rope_table(hd, n_ctx))
+        dnp = dev(np.array([n_past], dtype=np.int32))
+        W = [{k: dev(v) for k, v in L.items() if k not in ("kc", "vc")} for L in layers]
+        d_out, d_gout = dev(w_out), dev(g_out)
+        results = []
+        for _ in range(relaunches):
+            xa, xb, q, att, m1, m3, emb, logits = buf(n_embd), buf(n_embd), buf(n_embd), buf(n_embd), buf(n_ff), buf(n_ff), buf(n_embd), buf(n_vocab)
+            be.check(be.lib.fl_h2d(xa, x0.ctypes.data, n_embd * 4))
+            steps, kvs = [], []
+            for L, Lh in zip(W, layers):
+                kc, vc = dev(Lh["kc"]), dev(Lh["vc"])
+                kvs.append((kc, vc))
+                a = FlMvArgs()
+                a.type, a.K, a.nseg, a.pro, a.epi = t, n_embd, 3, PRO_RMSNORM, EPI_QKV
+                for i, w in enumerate((L["wq"], L["wk"], L["wv"])):
+                    a.seg_w[i], a.seg_rows[i] = w, n_embd
+                a.seg_dst[0] = q
+                a.x, a.gamma, a.n_past, a.n_ctx, a.n_embd, a.head_dim, a.kcache, a.vcache = xa, L["g1"], dnp, n_ctx, n_embd, hd, kc, vc
+                steps.append(("mv", a))
+                steps.append(("attn", (q, kc, vc, att)))
+                a = FlMvArgs()
+                a.type, a.K, a.nseg, a.pro, a.epi = t, n_embd, 1, 0, EPI_RESADD
+                a.seg_w[0], a.seg_rows[0], a.seg_dst[0], a.x, a.res = L["wo"], n_embd, xb, att, xa
+                steps.append(("mv", a))
+                a = FlMvArgs()
+                a.type, a.K, a.nseg, a.pro, a.epi = t, n_embd, 2, PRO_RMSNORM, EPI_STORE
+                a.seg_w[0], a.seg_rows[0], a.seg_dst[0] = L["w1"], n_ff, m1
+                a.seg_w[1], a.seg_rows[1], a.seg_dst[1] = L["w3"], n_ff, m3
+                a.x, a.gamma = xb, L["g2"]
+                steps.append(("mv", a))
+                a = FlMvArgs()
+                a.type, a.K, a.nseg, a.pro, a.epi = t, n_ff, 1, PRO_SILUMUL, EPI_RESADD
+                a.seg_w[0], a.seg_rows[0], a.seg_dst[0], a.x, a.b, a.res = L["w2"], n_embd, xa, m1, m3, xb
+                steps.append(("mv", a))
+            a = FlMvArgs()
+            a.type, a.K, a.nseg, a.pro, a.epi = t, n_embd, 1, PRO_RMSNORM, EPI_STORE
+            a.seg_w[0], a.seg_rows[0], a.seg_dst[0], a.x, a.gamma, a.normed_out = d_out, n_vocab, logits, xa, d_gout, emb
+            steps.append(("mv", a))
+            arr = (FlTokenStep * len(steps))()
+            for i, (kind, s) in enumerate(steps):
+                if kind == "mv":
+                    arr[i].kind, arr[i].mv = 0, s
+                else:
+                    arr[i].kind = 1
+                    arr[i].q, arr[i].kcache, arr[i].vcache, arr[i].out, arr[i].n_past = s[0], s[1], s[2], s[3], dnp
+                    arr[i].k_row_stride, arr[i].n_head, arr[i].head_dim, arr[i].n_ctx, arr[i].scale = n_embd, n_head, hd, n_ctx, scale
+            plan = C.c_void_p()
+            be.check(be.lib.fl_token_plan_create(arr, len(steps), C.byref(plan)))
+            be.check(be.lib.fl_token_plan_launch(plan))
+            be.check(be.lib.fl_sync())
+            assert be.lib.fl_token_plan_error(plan) == 0
+            r = {k: be.to_host(p, (n,), np.float32) for k, (p, n) in dict(xa=(xa, n_embd), q=(q, n_embd), att=(att, n_embd), emb=(emb, n_embd), logits=(logits, n_vocab)).items()}
+            for i, (kc, vc) in enumerate(kvs):
+                r[f"k{i}"] = be.to_host(kc, (n_ctx, n_embd), np.float32)
+                r[f"v{i}"] = be.to_host(vc, (n_embd, n_ctx), np.float32)
+            be.check(be.lib.fl_token_plan_destroy(plan))
+            results.append(r)
+        for d in keep:
+            be.free(d)
+        return results
+
+    want = run(cpu_model, 1)[0]
     assert np.isfinite(want["logits"]).all() and np.abs(want["logits"]).max() > 0
-    for d in keep:
-        fl.free(d)
+    for got in run(fl, 2):                       # a second plan over fresh buffers must give the same bits again
+        for k in want:
+            nd = int((got[k] != want[k]).sum())
+            assert nd == 0, (k, nd, got[k].size, np.abs(got[k] - want[k]).max())

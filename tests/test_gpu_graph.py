@@ -114,6 +114,25 @@ def test_cpy_strided_and_mul_mat_f32(libs):
     assert np.array_equal(bits(r[2]), bits(o[2]))
 
 
+def test_mul_mat_f32_attention_shapes_of_a_prompt_eval(libs):
+    """K*Q and V*P of a multi-token eval (n_batch = 128): big enough for the tiled f32 kernel, ragged against its 64 x 64 tiles, and
+    with the strided operands Model::eval uses (K as a permuted view of the cache, V^T with n_ctx row stride)."""
+    def build(g, a, rng):
+        hd, n_pos, n, heads, n_ctx = 128, 200, 96, 3, 256
+        kc = f32(g, a, rng, hd * heads, n_pos)                                                    # cache rows [pos][n_embd]
+        k = g.permute(a.ctx, g.reshape_3d(a.ctx, kc, hd, heads, n_pos), 0, 2, 1, 3)               # [hd, n_pos, heads]
+        q = f32(g, a, rng, hd, n, heads)
+        kq = g.mul_mat(a.ctx, k, q)                                                               # [n_pos, n, heads]
+        vt = f32(g, a, rng, n_ctx, hd * heads)                                                    # V^T [n_embd][n_ctx]
+        v = g.view_3d(a.ctx, vt, n_pos, hd, heads, n_ctx * 4, n_ctx * 4 * hd, 0)                  # [n_pos, hd, heads]
+        p = f32(g, a, rng, n_pos, n, heads)
+        kqv = g.mul_mat(a.ctx, v, p)                                                              # [hd, n, heads]
+        return [kq, kqv]
+    r, o = both(libs, build)
+    assert np.allclose(r[0], o[0], rtol=0, atol=1e-6 * 128 * 9.0)
+    assert np.allclose(r[1], o[1], rtol=0, atol=1e-6 * 200 * 9.0)
+
+
 @pytest.mark.parametrize("t", [G.Q4_0, G.Q4_1])
 def test_get_rows_and_quantised_mul_mat(libs, t):
     orc = Oracle()

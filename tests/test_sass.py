@@ -38,12 +38,12 @@ def count(text, mnemonic):
 def test_token_kernel_uses_bulk_copies_and_dp4a_and_barely_spills():
     f = sass("fl_token_kernel.o")
     k = next(v for n, v in f.items() if "k_decode_token" in n)
-    assert count(k, "UBLKCP") >= 2                   # weights: global -> shared through the TMA unit
-    assert count(k, "IDP.4A") >= 64                  # block dots
+    assert count(k, "UBLKCP") >= 1                   # weights: global -> shared through the TMA unit (one row piece per producer lane)
+    assert count(k, "IDP.4A") >= 16                  # the four-product sums of the reference's eight accumulators (q4_0 and q4_1 loops, unrolled)
+    assert count(k, "PRMT") >= 16                    # nibbles -> elements 4l .. 4l+3
     assert count(k, "SYNCS") >= 4                    # mbarrier ring
-    # the 24-register producer warpgroup (setmaxnreg) may spill a little; the consumer code must not
     assert count(k, "USETMAXREG") == 2, "producer / consumer register re-allocation (setmaxnreg) is missing"
-    assert count(k, "LDL") + count(k, "STL") <= 40, "the token kernel spills"
+    assert count(k, "LDL") + count(k, "STL") == 0, "the token kernel spills"
 
 
 def test_fused_and_ring_matvecs_use_bulk_copies():
