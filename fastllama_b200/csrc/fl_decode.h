@@ -10,7 +10,7 @@ int flk_attn_decode(cudaStream_t st, const float *q, const float *kcache, const 
                     int k_row_stride, int n_head, int head_dim, int n_ctx, float scale, const uint16_t *exp_tab);
 
 // fl_token_kernel.cu: the persistent per-token kernel
-int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_t *silu_tab, const uint16_t *exp_tab, const void *rope_cs, void **out);
+int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_t *silu_tab, const uint16_t *exp_tab, const void *rope_cs, unsigned *epoch_counter, void **out);
 int flk_token_plan_launch(cudaStream_t st, void *plan);
 int flk_token_plan_destroy(void *plan);
 int flk_token_plan_profile(void *plan, unsigned long long *out, size_t max_words, int *n_ctas);

@@ -342,7 +342,7 @@ extern "C" int fl_dev_rope_table(int n_dims, int n_pos) {
 extern "C" int fl_dev_mv_fused(const fl_mv_args *args) {
     FL_NEED_INIT();
     fl_mv_args a = *args;
-    FL_REQUIRE(a.n_xpeer == 0 && a.n_dst_peer == 0, "fl_dev_mv_fused: peer inputs / outputs exist only inside the token kernel");
+    FL_REQUIRE(a.n_dst_peer == 0 && !a.x_ll && !a.out_ll && !a.res_ll, "fl_dev_mv_fused: dataflow (LL) vectors and peer outputs exist only inside the token kernel");
     a.silu_tab = g.tab_silu;
     if (a.epi == FL_EPI_QKV) {
         FL_REQUIRE(g.rope_cs && g.rope_dims == a.head_dim && g.rope_pos >= a.n_ctx,
@@ -356,14 +356,15 @@ extern "C" int fl_dev_attn_decode(const float *q, const float *kcache, const flo
     FL_NEED_INIT();
     return flk_attn_decode(g.stream, q, kcache, vcache, out, n_past, k_row_stride, n_head, head_dim, n_ctx, scale, g.tab_exp);
 }
-extern "C" int fl_token_plan_create(const fl_token_step *steps, int n_steps, void **plan_out) {
+extern "C" int fl_token_plan_create(const fl_token_step *steps, int n_steps, void **plan_out) { return fl_token_plan_create_ll(steps, n_steps, nullptr, plan_out); }
+extern "C" int fl_token_plan_create_ll(const fl_token_step *steps, int n_steps, unsigned *epoch_counter, void **plan_out) {
     FL_NEED_INIT();
     FL_REQUIRE(steps && n_steps > 0 && plan_out, "fl_token_plan_create: bad arguments");
     for (int i = 0; i < n_steps; i++)
         if (steps[i].kind == 0 && steps[i].mv.epi == FL_EPI_QKV)
             FL_REQUIRE(g.rope_cs && g.rope_dims == steps[i].mv.head_dim && g.rope_pos >= steps[i].mv.n_ctx,
                        "fl_token_plan_create: call fl_dev_rope_table(head_dim, n_ctx) first");
-    return flk_token_plan_create(steps, n_steps, g.tab_silu, g.tab_exp, g.rope_cs, plan_out);
+    return flk_token_plan_create(steps, n_steps, g.tab_silu, g.tab_exp, g.rope_cs, epoch_counter, plan_out);
 }
 extern "C" int fl_token_plan_launch(void *plan) {
     FL_NEED_INIT();

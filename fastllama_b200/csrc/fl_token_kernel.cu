@@ -62,6 +62,8 @@ struct tk_phase {
     float *out;
     int k_row_stride, n_head, head_dim, n_ctx;
     int head_split;              // CTAs per head (each owns head_dim / head_split output dimensions)
+    int out_ll, out_seq, n_out_peer;
+    float *out_peer[7];
     float scale;
 };
 
@@ -70,12 +72,9 @@ struct tk_params {
     int n_phases;
     unsigned *grid_bar;              // [0] arrival counter (zeroed per launch)
     unsigned *err;                   // error block in pinned, device-mapped HOST memory: [0] flag, [1..4] details (the host reads it without a copy)
-    unsigned *xflags_local;          // tensor parallel: flags[q * 32] is written by rank q (through its peer mapping of this buffer)
-    unsigned *xflags_peer[8];        // rank p's flag array as mapped here
     int rank, world;
-    unsigned *ll_count;              // running number of LL reductions of all earlier launches (word 8 * 32 of the rank's own shared buffer)
-    int n_ll;                        // LL reductions per launch
-    int xrelease_sys;                // FASTLLAMA_B200_TP_RELEASE_SYS: every CTA releases at sys scope (measured 644 vs 697 tok/s at TP2)
+    unsigned *ll_count;              // running number of LL exchanges of all earlier launches (a device word that lives with the LL vectors)
+    int n_ll;                        // LL exchanges per launch
     const uint16_t *exp_tab;
     unsigned long long *prof;      // optional: [n_phases][gridDim.x][4] globaltimer stamps of thread 0
     unsigned *prof2;               // optional (PROF kernel only): [n_phases][gridDim.x][TK_CW][8] cycle counts of every consumer warp's tile loop
@@ -116,31 +115,14 @@ __device__ __forceinline__ void tk_wait_ge(const unsigned *p, unsigned target, b
 }
 // Grid barrier: CTA barrier, then one thread publishes the CTA's writes with a gpu-scope release increment and spins on
 // an acquire load; the second CTA barrier hands the acquired view to the other threads, which read shared activations
-// with ld.global.cg only.  xe != 0 extends it across the tensor-parallel GPUs: once the local grid has arrived, CTA 0
-// raises this rank's flag in every peer's memory (sys-scope release over NVLink) and every CTA waits for all peers' flags.
-__device__ __forceinline__ void tk_grid_sync(const tk_params &prm, unsigned target, unsigned xe) {
+// with ld.global.cg only.  Only the step in front of the attention needs it (q and the KV rows of all CTAs); every other
+// hand-over is a dataflow (LL) vector.
+__device__ __forceinline__ void tk_grid_sync(const tk_params &prm, unsigned target, unsigned) {
     // One arrival per CTA.  (Per-warp arrivals -- 16 x 148 atomics on one address -- were measured: +1 us per barrier.)
     tk_bar_consumers(13);
     if (threadIdx.x == 0) {
-        unsigned *err = prm.err;
-        // The phase that just ended may have stored to peer memory.  A gpu-scope release per CTA is enough: CTA 0 acquires all of
-        // them and then fences at sys scope before raising the flag, and causality order composes across the two scopes.
-        if (xe && prm.xrelease_sys) asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(prm.grid_bar) : "memory");
-        else asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(prm.grid_bar) : "memory");
-        tk_wait_ge(prm.grid_bar, target, false, err, 0x100u);
-        if (xe) {
-            if (blockIdx.x == 0) {
-                asm volatile("fence.acq_rel.sys;" ::: "memory");
-                for (int p = 0; p < prm.world; p++)
-                    if (p != prm.rank) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(prm.xflags_peer[p] + 32 * prm.rank), "r"(xe) : "memory");
-            }
-            for (int q = 0; q < prm.world; q++)
-                if (q != prm.rank) {
-                    tk_wait_ge(prm.xflags_local + 32 * q, xe, true, err, 0x200u + (unsigned)q);
-                    unsigned v;                                   // the acquire that orders the data reads behind the flag
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(prm.xflags_local + 32 * q) : "memory");
-                }
-        }
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(prm.grid_bar) : "memory");
+        tk_wait_ge(prm.grid_bar, target, false, prm.err, 0x100u);
     }
     tk_bar_consumers(13);
 }
@@ -226,26 +208,11 @@ __device__ __forceinline__ void tk_load_ll(const float *base, int u, float v[E],
         }
     }
 }
-// x (+ the other ranks' partial sums, in rank order: slots of the local peer-written buffer) (+ xadd) of unit u
+// x (LL vector: polled until every word carries the epoch) (+ xadd) of unit u
 template <int E>
 __device__ __forceinline__ void tk_load_x(const fl_mv_args &A, int u, float v[E], unsigned ll_epoch, unsigned *err) {
-    if (A.ll && A.n_xpeer > 0) {
-        tk_load_ll<E>(A.x, u, v, ll_epoch, err);
-        for (int r = 0; r < A.n_xpeer; r++) {
-            float w[E];
-            tk_load_ll<E>(A.xpeer[r], u, w, ll_epoch, err);
-#pragma unroll
-            for (int k = 0; k < E; k++) v[k] = __fadd_rn(v[k], w[k]);
-        }
-    } else {
-        tk_load_vals<E>((const float4 *)A.x, u, v, true);
-        for (int r = 0; r < A.n_xpeer; r++) {
-            float w[E];
-            tk_load_vals<E>((const float4 *)A.xpeer[r], u, w, true);
-#pragma unroll
-            for (int k = 0; k < E; k++) v[k] = __fadd_rn(v[k], w[k]);
-        }
-    }
+    if (A.x_ll) tk_load_ll<E>(A.x, u, v, ll_epoch, err);
+    else tk_load_vals<E>((const float4 *)A.x, u, v, true);
     if (A.xadd) {
         float w[E];
         tk_load_vals<E>((const float4 *)A.xadd, u, w, true);
@@ -417,6 +384,12 @@ __device__ __forceinline__ void tk_prologue(const fl_mv_args &A, int K, tk_ybloc
 // ---- epilogue of one unit (lane 0 of the warp that holds the complete sums a, b) --------------------
 // `pre` is what the epilogue needs from memory -- the residual pair (RESADD) or the rope (cos, sin) pair (QKV, q and k rows) --
 // loaded by tk_epilogue_preload BEFORE the warp's dot products, so its L2 round trip hides behind them.
+__device__ __forceinline__ void tk_store_ll(float *slot, int row, float v, unsigned e, float *const *peers, int n_peers) {
+    const unsigned uv = __float_as_uint(v);
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(slot + 2 * row), "r"(uv), "r"(e) : "memory");
+    for (int r = 0; r < n_peers; r++)                                                                     // posted stores over NVLink
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(peers[r] + 2 * row), "r"(uv), "r"(e) : "memory");
+}
 __device__ __forceinline__ float2 tk_epilogue_preload(const tk_phase &ph, int seg, int u, int n_past) {
     const fl_mv_args &A = ph.a;
     if (ph.swiglu) return make_float2(0.f, 0.f);
@@ -425,14 +398,22 @@ __device__ __forceinline__ float2 tk_epilogue_preload(const tk_phase &ph, int se
         if (seg < 2) return __ldg((const float2 *)A.rope_cs + (size_t)n_past * (A.head_dim >> 1) + ((r2 % A.head_dim) >> 1));
         return make_float2(0.f, 0.f);
     }
-    if (A.epi == FL_EPI_RESADD) return __ldcg((const float2 *)(A.res + r2));
+    if (A.epi == FL_EPI_RESADD) {
+        if (A.res_ll) {                                   // {value, epoch} words; the vector was polled completely by an earlier step of this CTA
+            const float4 t = __ldcg((const float4 *)(A.res + 2 * r2));
+            return make_float2(t.x, t.z);
+        }
+        return __ldcg((const float2 *)(A.res + r2));
+    }
     return make_float2(0.f, 0.f);
 }
 __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, float a, float b, int n_past, float2 pre, unsigned ll_epoch) {
     const fl_mv_args &A = ph.a;
     if (ph.swiglu) {
         const uint16_t h = __half_as_ushort(__float2half_rn(a));
-        A.seg_dst[0][u] = __fmul_rn(__half2float(__ushort_as_half(__ldg(A.silu_tab + h))), b);
+        const float o = __fmul_rn(__half2float(__ushort_as_half(__ldg(A.silu_tab + h))), b);
+        if (A.out_ll) tk_store_ll(A.seg_dst[0], u, o, ll_epoch, A.dst_peer, A.n_dst_peer);
+        else A.seg_dst[0][u] = o;
         return;
     }
     const int r2 = 2 * u;
@@ -449,26 +430,17 @@ __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, 
         }
         return;
     }
-    float *dst = A.seg_dst[seg] + r2;
     if (A.epi == FL_EPI_RESADD) {
         a = __fadd_rn(a, pre.x);
         b = __fadd_rn(b, pre.y);
     }
-    if (A.ll && A.n_dst_peer > 0) {
-        // LL: every value travels with the epoch in one 8-byte word; seg_dst[0] and dst_peer[] are LL slots (8 bytes per row)
-        const unsigned e = ll_epoch, ua = __float_as_uint(a), ub = __float_as_uint(b);
-        float *d0 = A.seg_dst[seg] + 2 * r2;
-        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(d0), "r"(ua), "r"(e) : "memory");
-        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(d0 + 2), "r"(ub), "r"(e) : "memory");
-        for (int r = 0; r < A.n_dst_peer; r++) {
-            float *d = A.dst_peer[r] + 2 * r2;                                                        // posted stores over NVLink
-            asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(d), "r"(ua), "r"(e) : "memory");
-            asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(d + 2), "r"(ub), "r"(e) : "memory");
-        }
+    if (A.out_ll) {
+        // every value travels with the epoch in one 8-byte word; seg_dst[0] and dst_peer[] are LL vectors (8 bytes per row)
+        tk_store_ll(A.seg_dst[seg], r2, a, ll_epoch, A.dst_peer, A.n_dst_peer);
+        tk_store_ll(A.seg_dst[seg], r2 + 1, b, ll_epoch, A.dst_peer, A.n_dst_peer);
         return;
     }
-    *(float2 *)dst = make_float2(a, b);
-    for (int r = 0; r < A.n_dst_peer; r++) *(float2 *)(A.dst_peer[r] + r2) = make_float2(a, b);     // posted stores over NVLink
+    *(float2 *)(A.seg_dst[seg] + r2) = make_float2(a, b);
 }
 
 // ---- the tile stream of a tile group --------------------------------------------------------------
@@ -506,7 +478,10 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
     constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24, QOFF = (TYPE == FL_TYPE_Q4_0) ? 4 : 8;
     const fl_mv_args &A = ph.a;
     const int S = prm.S;
-    const int g = warp / TK_WPG, wl = warp % TK_WPG;
+    // group g = warp % 4: its four warps (g, g + 4, g + 8, g + 12) share one SM sub-partition, and a phase with few tasks (wo, w2: four per
+    // CTA, one per group, all on warp-of-group 0) runs on warps 0 .. 3, i.e. on four DIFFERENT sub-partitions.  (warp / 4 put those four
+    // chains on one scheduler: w2's tile loop measured 17.7 us instead of ~5.)
+    const int g = warp % TK_TG, wl = warp / TK_TG;
     const int r = lane >> 2, jj = lane & 3;
     const bool swiglu = ph.swiglu != 0;
     const int C = ph.nchunks, nb = ph.nb;
@@ -533,7 +508,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
                 const uint8_t *wp = stage0 + (size_t)s * prm.slot_bytes + row_off;
                 const tk_yblock *yp = ysm + c * TK_CHB;
                 const int nbc = min(TK_CHB, nb - c * TK_CHB);
-#pragma unroll 4
+#pragma unroll 8
                 for (int i = 0; i < nbc; i++) {
                     const uint32_t w = *(const uint32_t *)(wp + i * BB);
                     const float dx = *(const float *)(wp + i * BB - (QOFF + 4 * jj));
@@ -561,7 +536,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
 }
 
 // ---- attention phase: one head, all consumer threads of the CTA ------------------------------------
-__device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params &prm, float *sc, double *red, int head, int part_id, int warp, int lane, int tid) {
+__device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params &prm, float *sc, double *red, int head, int part_id, int warp, int lane, int tid, unsigned lle_out) {
     float *redf = (float *)(red + 20);                // [16] floats; red[0..16] are the double partials
     const int hd = ph.head_dim;
     const int n_pos = *ph.a.n_past + 1;
@@ -643,7 +618,10 @@ __device__ __forceinline__ void tk_attention(const tk_phase &ph, const tk_params
         float o = fx_reduce_f32(acc);
         for (int k = 0; k < nma; k++) o = __fadd_rn(o, __shfl_sync(0xffffffffu, lv, k));
         for (int k = nma; k < rem; k++) o = __fmaf_rn(__shfl_sync(0xffffffffu, lx, k), __shfl_sync(0xffffffffu, ly, k), o);
-        if (lane == 0) ph.out[(size_t)head * hd + d] = o;
+        if (lane == 0) {
+            if (ph.out_ll) tk_store_ll(ph.out, head * hd + d, o, lle_out, ph.out_peer, ph.n_out_peer);
+            else ph.out[(size_t)head * hd + d] = o;
+        }
     }
 }
 // pull the cached positions of this head towards L2 while the grid is still finishing the previous phase
@@ -759,11 +737,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
     int T0 = 0;
     uint32_t cg = 0;                                         // tiles of all earlier phases in this warp's group's stream
     unsigned epoch = 0;
-    // cross-GPU epochs continue across launches AND plans: the running count lives next to the flags (word 8 * 32 of the
-    // rank's own shared buffer), so flags left behind by earlier launches can never satisfy a later wait
-    unsigned xepoch = 0;
-    if (prm.world > 1 && tid == 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(xepoch) : "l"(prm.xflags_local + 8 * 32) : "memory");
-    // LL reductions: every element carries (number of LL reductions before this launch) + (index inside the launch) + 1
+    // LL vectors: every element carries (number of LL exchanges before this launch) + (index inside the launch) + 1.  The running count
+    // lives next to the vectors (fl_token_plan_create_ll), so words left behind by earlier launches or plans never satisfy a later poll.
     unsigned ll_base = 0;
     if (prm.n_ll > 0) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ll_base) : "l"(prm.ll_count) : "memory");
     unsigned *err = prm.err;
@@ -775,15 +750,14 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         const bool attn_here = ph.kind == TK_PH_ATTN && (int)blockIdx.x < ph.n_head * ph.head_split;
         const int a_head = attn_here ? (int)blockIdx.x / ph.head_split : 0, a_part = attn_here ? (int)blockIdx.x % ph.head_split : 0;
         if (attn_here) tk_attention_prefetch(ph, a_head, a_part, tid);
-        const bool ll_in = ph.kind == TK_PH_MATVEC && ph.a.ll && ph.a.n_xpeer > 0;    // input arrives element by element with epochs: no barrier at all
-        const unsigned lle = (ph.kind == TK_PH_MATVEC && ph.a.ll) ? ll_base + (unsigned)ph.a.ll_seq + 1u : 0u;
+        const bool ll_in = ph.kind == TK_PH_MATVEC && ph.a.x_ll;      // input arrives element by element with epochs: no grid barrier at all
+        const unsigned lle_in = ll_in ? ll_base + (unsigned)ph.a.x_seq + 1u : 0u;
+        const unsigned lle_out = ph.kind == TK_PH_MATVEC ? (ph.a.out_ll ? ll_base + (unsigned)ph.a.out_seq + 1u : 0u) : (ph.out_ll ? ll_base + (unsigned)ph.out_seq + 1u : 0u);
         if (pi > 0 && ll_in) {
             tk_bar_consumers(13);                                // only this CTA's warps: the previous phase's tiles have been consumed
         } else if (pi > 0) {
             epoch++;
-            const bool xgpu = ph.kind == TK_PH_MATVEC && ph.a.n_xpeer > 0;   // this phase reads the other GPUs' partial results (flag-barrier form)
-            if (xgpu) xepoch++;
-            if (!(prm.diag & 4)) tk_grid_sync(prm, epoch * gridDim.x, xgpu ? xepoch : 0u);   // results of phase pi-1 are visible everywhere
+            if (!(prm.diag & 4)) tk_grid_sync(prm, epoch * gridDim.x, 0u);   // results of phase pi-1 are visible everywhere
         }
         if (pr) pr[1] = tk_now();
         // Descriptor pi+1: the load is issued now, the store into phs[(pi+1)&1] (which nobody reads any more: everybody is
@@ -792,7 +766,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         const bool copies = tid < (int)(sizeof(tk_phase) / 4) && pi + 1 < prm.n_phases;
         if (copies) next_word = __ldcg((const uint32_t *)&prm.phases[pi + 1] + tid);
         if (ph.kind == TK_PH_ATTN) {
-            if (attn_here && !(prm.diag & 16)) tk_attention(ph, prm, sc, red, a_head, a_part, warp, lane, tid);
+            if (attn_here && !(prm.diag & 16)) tk_attention(ph, prm, sc, red, a_head, a_part, warp, lane, tid, lle_out);
             if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
             tk_bar_consumers(15);                                // the next iteration reads the new descriptor before its grid barrier
             if (pr) pr[2] = pr[3] = tk_now();
@@ -800,21 +774,18 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         }
         const int K = ph.nb * 32;
         if (tid == TK_NT - 1) sl_sh = tk_make_slice_u(ph.units[0], ph.units[1], ph.units[2], 2, prm.grid_magic, prm.grid_shift);
-        if (!(prm.diag & 8)) tk_prologue(ph.a, K, ysm, red, warp, lane, tid, lle, err);
+        if (!(prm.diag & 8)) tk_prologue(ph.a, K, ysm, red, warp, lane, tid, lle_in, err);
         if (copies) ((uint32_t *)&phs[(pi + 1) & 1])[tid] = next_word;
         tk_bar_consumers(15);                                    // activations, slice and next descriptor are in shared memory
         if (pr) pr[2] = tk_now();
         const tk_slice &sl = sl_sh;
         unsigned *pw = (PROF && prm.prof2) ? prm.prof2 + (((size_t)pi * gridDim.x + blockIdx.x) * TK_CW + warp) * 8 : nullptr;
-        if (ph.a.type == FL_TYPE_Q4_0) tk_consume<FL_TYPE_Q4_0, PROF>(ph, prm, sl, T0, cg, ysm, stage0, bar0, warp, lane, pw, lle);
-        else                           tk_consume<FL_TYPE_Q4_1, PROF>(ph, prm, sl, T0, cg, ysm, stage0, bar0, warp, lane, pw, lle);
+        if (ph.a.type == FL_TYPE_Q4_0) tk_consume<FL_TYPE_Q4_0, PROF>(ph, prm, sl, T0, cg, ysm, stage0, bar0, warp, lane, pw, lle_out);
+        else                           tk_consume<FL_TYPE_Q4_1, PROF>(ph, prm, sl, T0, cg, ysm, stage0, bar0, warp, lane, pw, lle_out);
         T0 += sl.ntiles;
         if (pr) pr[3] = tk_now();
     }
-    if (prm.world > 1 && blockIdx.x == 0 && tid == 0) {
-        prm.xflags_local[8 * 32] = xepoch;     // next launch continues from here
-        if (prm.n_ll > 0) *prm.ll_count = ll_base + (unsigned)prm.n_ll;
-    }
+    if (prm.n_ll > 0 && blockIdx.x == 0 && tid == 0) *prm.ll_count = ll_base + (unsigned)prm.n_ll;     // the next launch continues from here
 }
 
 // =================================================================================================
@@ -870,7 +841,7 @@ static int tk_geometry(tk_phase &ph, size_t &tile_bytes) {
     return 0;
 }
 
-int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_t *silu_tab, const uint16_t *exp_tab, const void *rope_cs, void **out) {
+int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_t *silu_tab, const uint16_t *exp_tab, const void *rope_cs, unsigned *epoch_counter, void **out) {
     std::vector<tk_phase> phases((size_t)n_steps);
     for (int i = 0; i < n_steps; i++) {
         tk_phase &ph = phases[i];
@@ -881,6 +852,8 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
             ph.k_row_stride = steps[i].k_row_stride; ph.n_head = steps[i].n_head; ph.head_dim = steps[i].head_dim; ph.n_ctx = steps[i].n_ctx;
             ph.scale = steps[i].scale;
             ph.a.n_past = steps[i].n_past;
+            ph.out_ll = steps[i].out_ll; ph.out_seq = steps[i].out_seq; ph.n_out_peer = steps[i].n_out_peer;
+            for (int r = 0; r < 7; r++) ph.out_peer[r] = steps[i].out_peer[r];
         } else {
             ph.kind = TK_PH_MATVEC;
             ph.a = steps[i].mv;
@@ -888,10 +861,16 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
             ph.a.rope_cs = rope_cs;
         }
     }
-    // w1|w3 followed by a silu(.)*(.) prologue over exactly their outputs: fuse the activation into the first phase
+    // w1|w3 followed by a silu(.)*(.) prologue over exactly their outputs: fuse the activation into the first phase (dataflow plans ask for it)
+    for (int i = 0; i < n_steps; i++)
+        if (phases[i].kind == TK_PH_MATVEC && phases[i].a.swiglu) {
+            const fl_mv_args &a = phases[i].a;
+            FL_REQUIRE(a.nseg == 2 && a.epi == FL_EPI_STORE && a.seg_rows[0] == a.seg_rows[1], "token kernel: a swiglu step needs two equal segments and a plain store");
+            phases[i].swiglu = 1;
+        }
     for (int i = 0; i + 1 < n_steps; i++) {
         tk_phase &p0 = phases[i], &p1 = phases[i + 1];
-        if (p0.kind != TK_PH_MATVEC || p1.kind != TK_PH_MATVEC) continue;
+        if (p0.kind != TK_PH_MATVEC || p1.kind != TK_PH_MATVEC || p0.swiglu) continue;
         const fl_mv_args &a = p0.a;
         if (a.nseg == 2 && a.epi == FL_EPI_STORE && a.seg_rows[0] == a.seg_rows[1] && p1.a.pro == FL_PRO_SILUMUL && p1.a.x == a.seg_dst[0] &&
             p1.a.b == a.seg_dst[1] && p1.a.K == a.seg_rows[0] && p1.a.xadd == nullptr) {
@@ -932,6 +911,7 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     tk_params &p = pl->prm;
     const size_t slot = (max_tile + 127) & ~(size_t)127;
     int S = 64;
+    if (getenv("FASTLLAMA_B200_TK_SLOTS")) S = std::max(8, std::min(64, atoi(getenv("FASTLLAMA_B200_TK_SLOTS")) / 4 * 4));      // testing aid: a shallower ring
     size_t off = 0;
     for (;; S -= 4) {
         if (S < 8) { flk_token_plan_destroy(pl); fl_set_error("token kernel: tiles of %zu bytes do not fit shared memory", slot); return -1; }
@@ -964,26 +944,16 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     FL_CUDA_OK(cudaHostAlloc((void **)&pl->h_err, 64, cudaHostAllocMapped));
     memset(pl->h_err, 0, 64);
     FL_CUDA_OK(cudaHostGetDevicePointer((void **)&p.err, pl->h_err, 0));
-    p.rank = 0; p.world = 1; p.xflags_local = nullptr; p.ll_count = nullptr; p.n_ll = 0;
-    p.xrelease_sys = getenv("FASTLLAMA_B200_TP_RELEASE_SYS") ? 1 : 0;
-    for (int r = 0; r < 8; r++) p.xflags_peer[r] = nullptr;
-    bool uses_peers = false;
-    for (int i = 0; i < n_steps; i++) uses_peers = uses_peers || (phases[i].kind == TK_PH_MATVEC && phases[i].a.n_xpeer > 0);
-    if (uses_peers) {
-        int rank = 0, world = 1;
-        const void *const *peers = fl_shared_peers(&rank, &world);
-        if (!peers) { flk_token_plan_destroy(pl); fl_set_error("token kernel: steps read peer buffers but fl_comm_shared_alloc was never called"); return -1; }
-        p.rank = rank; p.world = world;
-        p.xflags_local = (unsigned *)peers[rank];
-        p.ll_count = p.xflags_local + 9 * 32;
-        for (int i = 0; i < n_steps; i++)
-            if (phases[i].kind == TK_PH_MATVEC && phases[i].a.ll && phases[i].a.n_dst_peer > 0) p.n_ll = std::max(p.n_ll, phases[i].a.ll_seq + 1);
-        for (int r = 0; r < world; r++) p.xflags_peer[r] = (unsigned *)peers[r];
-        for (int i = 0; i < n_steps; i++)
-            if (phases[i].kind == TK_PH_MATVEC && phases[i].a.n_xpeer > 0 && phases[i].a.n_xpeer != world - 1) {
-                flk_token_plan_destroy(pl); fl_set_error("token kernel: a step lists %d peers in a communicator of %d", phases[i].a.n_xpeer, world); return -1;
-            }
+    p.rank = 0; p.world = 1; p.ll_count = epoch_counter; p.n_ll = 0;
+    for (int i = 0; i < n_steps; i++) {
+        const tk_phase &ph = phases[i];
+        if (ph.kind == TK_PH_MATVEC) {
+            if (ph.a.out_ll) p.n_ll = std::max(p.n_ll, ph.a.out_seq + 1);
+            if (ph.a.x_ll) p.n_ll = std::max(p.n_ll, ph.a.x_seq + 1);
+            if (ph.a.out_ll && ph.a.nseg != 1 && !ph.swiglu) { flk_token_plan_destroy(pl); fl_set_error("token kernel: an LL output needs a single segment (or a w1|w3 pair)"); return -1; }
+        } else if (ph.out_ll) p.n_ll = std::max(p.n_ll, ph.out_seq + 1);
     }
+    if (p.n_ll > 0 && !epoch_counter) { flk_token_plan_destroy(pl); fl_set_error("token kernel: steps use LL vectors but no epoch counter was given (fl_token_plan_create_ll)"); return -1; }
     p.prof = nullptr;
     p.prof2 = nullptr;
     if (getenv("FASTLLAMA_B200_TOKEN_PROF")) {

@@ -1001,7 +1001,6 @@ struct LayerPlan {
     fl_mv_args qkv, wo, w13, w2;
     const float *q, *kcache, *vcache;
     float *att;
-    float *part1 = nullptr, *part2 = nullptr;   // tensor-parallel: partial sums of the K-split wo / w2, all-reduced in place
 };
 struct DecodePlan {
     int n_layer = 0, n_embd = 0, n_head = 0, n_ctx = 0, n_past = 0;
@@ -1024,14 +1023,17 @@ struct DecodePlan {
 struct DecodeWs {
     int n_embd = 0, n_ff = 0, n_vocab = 0;
     float *xa = nullptr, *xb = nullptr, *q = nullptr, *att = nullptr, *ff = nullptr, *m1 = nullptr, *m3 = nullptr, *emb = nullptr, *logits = nullptr;
-    float *part1 = nullptr, *part2 = nullptr, *logits_local = nullptr;
+    float *logits_local = nullptr;
     int32_t *d_tok = nullptr;
-    // tensor parallelism: part1/part2 live in the peer-mapped buffer of fl_comm_shared_alloc when it is available, so the
-    // token kernel can sum the ranks' partial results itself (peers[r] = rank r's buffer as mapped on this rank)
+    // The dataflow ("LL") vectors of the token kernel (include/fl_cuda.h, fl_mv_args): {value, epoch} words that hand the
+    // activations from step to step without grid barriers.  Layout of the buffer: 4096 bytes of counters (word 0 = the running epoch),
+    // then X (the residual stream, n_embd words), A (attention output), B (x + wo.att) and H (the FFN's hidden vector, n_ff words).
+    // One GPU: plain device memory.  Tensor parallel: the buffer of fl_comm_shared_alloc, peers[r] = rank r's buffer as mapped here;
+    // every rank stores its row slice of a vector into ALL buffers (NVLink), so each holds the complete gathered vector.
+    void *ll_local = nullptr;   // world == 1: owned here
     void *peers[8] = {nullptr};
     bool peer_mapped = false;
-    bool use_ll = true;         // reductions in LL form ({value, epoch} words, no barrier); FASTLLAMA_B200_TP_NO_LL=1: plain slots + cross-GPU flag barrier
-    size_t ll_slot_bytes = 0;   // bytes of one rank's slot in an LL buffer (n_embd * 8)
+    size_t ll_cap_embd = 0, ll_cap_ff = 0;      // the element counts the buffer was laid out for
 };
 struct DecodeState {
     DecodePlan plan;            // the plan the captured graph was built from
@@ -1079,34 +1081,36 @@ void mv_base(fl_mv_args &a, int type, int K) {
 void ensure_ws(DecodeWs &w, int n_embd, int n_ff, int n_vocab) {
     if (w.xa && w.n_embd == n_embd && w.n_ff == n_ff && w.n_vocab == n_vocab) return;
     if (w.xa) { FLC(fl_sync()); FLC(fl_dev_free(w.xa)); }
-    const size_t total = (size_t)n_embd * 8 + (size_t)n_ff * 2 + (size_t)n_vocab * 2 + 64;
+    const size_t total = (size_t)n_embd * 6 + (size_t)n_ff * 2 + (size_t)n_vocab * 2 + 64;
     float *base = (float *)fl_dev_malloc(total * sizeof(float));
     if (!base) B200_FAIL("decode workspace: %s", fl_last_error());
     w.xa = base; w.xb = w.xa + n_embd; w.q = w.xb + n_embd; w.att = w.q + n_embd; w.ff = w.att + n_embd; w.emb = w.ff + n_embd;
-    w.part1 = w.emb + n_embd; w.part2 = w.part1 + n_embd;
-    w.m1 = w.part2 + n_embd; w.m3 = w.m1 + n_ff; w.logits = w.m3 + n_ff; w.logits_local = w.logits + n_vocab;
+    w.m1 = w.emb + n_embd; w.m3 = w.m1 + n_ff; w.logits = w.m3 + n_ff; w.logits_local = w.logits + n_vocab;
     w.d_tok = (int32_t *)(w.logits_local + n_vocab);
     w.n_embd = n_embd; w.n_ff = n_ff; w.n_vocab = n_vocab;
-    w.peer_mapped = false;
-    if (fl_comm_world() > 1 && getenv("FASTLLAMA_B200_NO_PEER") == nullptr) {
-        // collective: every rank gets here on its first decode step
-        // layout of every rank's buffer: 4096 bytes of flags / counters, then two reduction buffers (after wo, after w2) of `world` slots each;
-        // slot r is written by rank r (into its own buffer and, over NVLink, into everybody else's).  A slot holds n_embd floats (flag-barrier
-        // form) or n_embd {value, epoch} words (LL form); the buffer is sized for the LL form of the largest model (n_embd 8192).
-        const int world = fl_comm_world(), rank = fl_comm_rank();
-        w.use_ll = getenv("FASTLLAMA_B200_TP_NO_LL") == nullptr;
-        const size_t slot_cap = (size_t)std::max(n_embd, 8192) * 8;
-        if (fl_comm_shared_alloc(4096 + (size_t)2 * world * slot_cap, w.peers) == 0) {
-            w.ll_slot_bytes = w.use_ll ? (size_t)n_embd * 8 : (size_t)n_embd * 4;
-            if (!w.use_ll) {                    // flag-barrier form: the plain partial-sum vectors live in the peer buffer itself
-                w.part1 = (float *)((char *)w.peers[rank] + 4096) + (size_t)rank * n_embd;
-                w.part2 = w.part1 + (size_t)world * n_embd;
-            }
+    const int world = fl_comm_world(), rank = fl_comm_rank();
+    if (world > 1) {
+        // collective: every rank gets here on its first decode step.  The peer-mapped buffer is per process (it cannot be freed), so it
+        // is laid out for the largest model of the family (n_embd 8192, n_ff 22016) or this one, whichever is larger.
+        if (!w.peer_mapped) {
+            w.ll_cap_embd = (size_t)std::max(n_embd, 8192); w.ll_cap_ff = (size_t)std::max(n_ff, 22016);
+            if (fl_comm_shared_alloc(4096 + (3 * w.ll_cap_embd + w.ll_cap_ff) * 8, w.peers) != 0)
+                B200_FAIL("tensor-parallel decode needs peer-mapped buffers between the GPUs: %s", fl_last_error());
             w.peer_mapped = true;
-        } else if (g_verbose) {
-            fprintf(stderr, "[ggml_b200] no peer-mapped buffers (%s): tensor-parallel decode keeps the NCCL path\n", fl_last_error());
         }
+        if ((size_t)n_embd > w.ll_cap_embd || (size_t)n_ff > w.ll_cap_ff) B200_FAIL("tensor-parallel decode: model wider than the peer-mapped vectors (n_embd %d, n_ff %d)", n_embd, n_ff);
+    } else {
+        if (w.ll_local && ((size_t)n_embd > w.ll_cap_embd || (size_t)n_ff > w.ll_cap_ff)) { FLC(fl_sync()); FLC(fl_dev_free(w.ll_local)); w.ll_local = nullptr; }
+        if (!w.ll_local) {
+            w.ll_cap_embd = (size_t)n_embd; w.ll_cap_ff = (size_t)n_ff;
+            const size_t bytes = 4096 + (3 * w.ll_cap_embd + w.ll_cap_ff) * 8;
+            w.ll_local = fl_dev_malloc(bytes);
+            if (!w.ll_local) B200_FAIL("decode workspace: %s", fl_last_error());
+            FLC(fl_dev_memset(w.ll_local, 0, bytes));              // epoch 0 is never expected: nothing has arrived yet
+        }
+        w.peers[0] = w.ll_local;
     }
+    (void)rank;
 }
 
 // ---- tensor-parallel weight shards, uploaded straight from the HOST tensors (reference hook point lib/llama.cpp:257-258) -----------
@@ -1292,24 +1296,16 @@ bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, Decode
         L.w2.nseg = 1; L.w2.seg_w[0] = world == 1 ? wfull(w2) : nullptr; L.w2.seg_rows[0] = n_embd; L.w2.seg_dst[0] = xout;
         L.w2.pro = FL_PRO_SILUMUL; L.w2.x = L.w13.seg_dst[0]; L.w2.b = L.w13.seg_dst[1]; L.w2.epi = FL_EPI_RESADD; L.w2.res = L.w13.x;
         if (world > 1) {
-            // ---- tensor-parallel wiring: wq/wk/wv/w1/w3 row-split by heads / n_ff slices, wo/w2 K-split,
-            // fp32 all-reduce of n_embd after wo and after w2; the residual adds move into the next prologue (xadd).
+            // ---- tensor-parallel wiring: EVERY matrix is row-split -- wq/wk/wv by heads, w1/w3 by n_ff slices, wo/w2 and
+            // the output matrix by output rows -- and every activation vector is all-gathered as a dataflow (LL) vector (make_token_plan).
+            // No K-split: a row is always summed over the whole K on one GPU, in the reference's order, so N GPUs produce the bits of one.
             const int nl = n_embd / world, fl = n_ff / world;
-            L.part1 = W.part1; L.part2 = W.part2;
             L.kcache += (size_t)rank * nl; L.vcache += (size_t)rank * nl * n_ctx;   // this rank's heads
             for (int i = 0; i < 3; i++) L.qkv.seg_rows[i] = nl;                         // seg_w[] already point at this rank's rows (wrows)
             L.qkv.kcache = (float *)L.kcache; L.qkv.vcache = (float *)L.vcache;
-            if (il == 0) { L.qkv.x = W.xa; }
-            else { L.qkv.x = W.part2; L.qkv.xadd = W.ff; L.qkv.sum_out = W.xa; }    // x_l = w2 partial sum + ff of the previous layer
-            size_t st = 0;
-            mv_base(L.wo, (int)wo->type, nl);
-            L.wo.nseg = 1; L.wo.seg_w[0] = tp_shard(wo, SH_COLS, rank * (nl / 32), nl / 32, &st); L.wo.row_stride_bytes = st;
-            L.wo.seg_rows[0] = n_embd; L.wo.seg_dst[0] = W.part1; L.wo.pro = FL_PRO_PLAIN; L.wo.x = W.att; L.wo.epi = FL_EPI_STORE;
+            L.wo.seg_w[0] = wrows(wo, rank * nl, nl); L.wo.seg_rows[0] = nl;
             L.w13.seg_rows[0] = L.w13.seg_rows[1] = fl;
-            L.w13.x = W.part1; L.w13.xadd = W.xa; L.w13.sum_out = W.ff;              // ff = wo partial sum + x
-            mv_base(L.w2, (int)w2->type, fl);
-            L.w2.nseg = 1; L.w2.seg_w[0] = tp_shard(w2, SH_COLS, rank * (fl / 32), fl / 32, &st); L.w2.row_stride_bytes = st;
-            L.w2.seg_rows[0] = n_embd; L.w2.seg_dst[0] = W.part2; L.w2.pro = FL_PRO_SILUMUL; L.w2.x = W.m1; L.w2.b = W.m3; L.w2.epi = FL_EPI_STORE;
+            L.w2.seg_w[0] = wrows(w2, rank * nl, nl); L.w2.seg_rows[0] = nl;
         }
         x = xo;
         std::swap(xin, xout);
@@ -1327,7 +1323,6 @@ bool match_decode(const ggml_context *ctx, ggml_cgraph *g, DecodePlan &P, Decode
         PM(W.n_vocab % (2 * world) == 0);
         const int vl = W.n_vocab / world;
         P.head.seg_rows[0] = vl; P.head.seg_dst[0] = W.logits_local;                 // seg_w[0] already points at this rank's rows
-        P.head.x = W.part2; P.head.xadd = W.ff;                                    // final residual add of the last layer
         P.vocab_local = vl; P.logits_local = W.logits_local; P.logits_all = W.logits;
     }
     P.head.epi = FL_EPI_STORE;
@@ -1370,6 +1365,8 @@ void profiled_mv(const fl_mv_args &a) {
     e->total_ms += ms;
 }
 
+// One kernel per matrix group (round 1's path; one GPU only; its dot products add the block terms in another fp32 order than the
+// reference, so it only runs on request: FASTLLAMA_B200_MULTI_KERNEL=1).
 void issue_decode(const DecodePlan &P, const int *d_npast) {
     FLC(fl_dev_dequantize_rows(P.emb_type, P.emb_w, P.emb_stride, P.emb_K, P.emb_ids, 1, P.emb_dst, (size_t)P.emb_K));
     const int hd = P.n_embd / P.n_head;
@@ -1379,65 +1376,84 @@ void issue_decode(const DecodePlan &P, const int *d_npast) {
         profiled_mv(qkv);
         FLC(fl_dev_attn_decode(Lc.q, Lc.kcache, Lc.vcache, Lc.att, d_npast, P.n_embd, P.heads_local, hd, P.n_ctx, P.scale));
         profiled_mv(Lc.wo);
-        if (P.world > 1) FLC(fl_comm_allreduce_f32(Lc.part1, (size_t)P.n_embd));
         profiled_mv(Lc.w13);
         profiled_mv(Lc.w2);
-        if (P.world > 1) FLC(fl_comm_allreduce_f32(Lc.part2, (size_t)P.n_embd));
     }
     profiled_mv(P.head);
-    if (P.world > 1) FLC(fl_comm_allgather_f32(P.logits_local, P.logits_all, (size_t)P.vocab_local));
 }
 
-// The same steps as issue_decode, handed to the persistent token kernel (one cooperative launch per token;
-// fl_token_kernel.cu).  Returns nullptr when the shapes are outside what that kernel handles.
+// The decode step as the program of the persistent token kernel (one cooperative launch per token; fl_token_kernel.cu).  Every
+// activation vector travels as a dataflow (LL) vector -- X: residual stream, A: attention output, B: x + wo.att, H: FFN hidden --
+// so the only grid barrier of a layer is the one in front of the attention (q and the new KV rows of all CTAs).  With `world` GPUs
+// every matrix is row-split and a step stores its row slice into ALL ranks' copies of the vector: the gathered vectors, and with
+// them every later operation, are bit-identical to the one-GPU run.  Returns nullptr when the shapes are outside what the kernel handles.
 void *make_token_plan(const DecodePlan &P, const DecodeWs &W, const int *d_npast) {
     std::vector<fl_token_step> steps;
-    // tensor parallel: a K-split step also pushes its partial sums into the other ranks' buffers, and a step that used
-    // to read the all-reduced vector reads the ranks' slots of the LOCAL buffer instead, in rank order
-    const int rank = fl_comm_rank();
-    // which[0] = the reduction after wo (W.part1), which[1] = after w2 (W.part2); slot r of reduction k inside rank q's buffer:
-    auto slot = [&](int q, int k, int r) { return (char *)W.peers[q] + 4096 + ((size_t)k * P.world + r) * W.ll_slot_bytes; };
-    int ll_next = 0, ll_last[2] = {-1, -1};
-    auto mv = [&](const fl_mv_args &a0) {
-        fl_token_step s;
-        memset(&s, 0, sizeof(s));
-        s.kind = 0;
-        s.mv = a0;
-        const int kin = a0.x == W.part1 ? 0 : a0.x == W.part2 ? 1 : -1;
-        if (P.world > 1 && kin >= 0) {                       // consumer of an all-reduced vector: the ranks' slots of MY buffer, rank order
-            s.mv.x = (const float *)slot(rank, kin, 0);
-            for (int r = 1; r < P.world; r++) s.mv.xpeer[r - 1] = (const float *)slot(rank, kin, r);
-            s.mv.n_xpeer = P.world - 1;
-            if (W.use_ll) { s.mv.ll = 1; s.mv.ll_seq = ll_last[kin]; }
-        }
-        const int kout = (a0.nseg == 1 && a0.seg_dst[0] == W.part1) ? 0 : (a0.nseg == 1 && a0.seg_dst[0] == W.part2) ? 1 : -1;
-        if (P.world > 1 && kout >= 0) {                      // K-split step: slot `rank` of every rank's buffer
-            s.mv.seg_dst[0] = (float *)slot(rank, kout, rank);
-            int n = 0;
-            for (int r = 0; r < P.world; r++)
-                if (r != rank) s.mv.dst_peer[n++] = (float *)slot(r, kout, rank);
-            s.mv.n_dst_peer = n;
-            if (W.use_ll) { s.mv.ll = 1; s.mv.ll_seq = ll_next; ll_last[kout] = ll_next++; }
-        }
-        steps.push_back(s);
+    const int rank = P.world > 1 ? fl_comm_rank() : 0, world = P.world;
+    const int E = P.n_embd, F = W.n_ff, nl = E / world, fl = F / world, hd = E / P.n_head;
+    // vector v (0 X, 1 A, 2 B, 3 H) in rank q's buffer, as mapped here
+    auto vec = [&](int q, int v) -> float * {
+        const size_t off = 4096 + (size_t)(v < 3 ? v : 3) * W.ll_cap_embd * 8;
+        return (float *)((char *)W.peers[q] + off);
     };
-    const int hd = P.n_embd / P.n_head;
-    for (const LayerPlan &Lc : P.layers) {
-        fl_mv_args qkv = Lc.qkv;
-        qkv.n_past = d_npast;
-        mv(qkv);
+    auto peers_of = [&](int v, size_t first_elem, float **dst, int &n) {
+        n = 0;
+        for (int q = 0; q < world; q++)
+            if (q != rank) dst[n++] = vec(q, v) + 2 * first_elem;
+    };
+    enum { VX = 0, VA = 1, VB = 2, VH = 3 };
+    for (int il = 0; il < P.n_layer; il++) {
+        const LayerPlan &Lc = P.layers[il];
+        const int seq0 = 4 * il;                                    // A: seq0, B: seq0 + 1, H: seq0 + 2, X (input of layer il + 1): seq0 + 3
+        fl_token_step s;
+        // wq|wk|wv (this rank's heads): x = embedding row (layer 0) or the gathered residual stream
+        memset(&s, 0, sizeof(s));
+        s.kind = 0; s.mv = Lc.qkv; s.mv.n_past = d_npast; s.mv.xadd = nullptr; s.mv.sum_out = nullptr;
+        if (il == 0) s.mv.x = W.xa;
+        else { s.mv.x = vec(rank, VX); s.mv.x_ll = 1; s.mv.x_seq = seq0 - 1; }
+        steps.push_back(s);
+        // attention over this rank's heads -> slice [rank * nl, +nl) of A everywhere
+        memset(&s, 0, sizeof(s));
+        s.kind = 1; s.q = Lc.q; s.kcache = Lc.kcache; s.vcache = Lc.vcache; s.n_past = d_npast;
+        s.k_row_stride = E; s.n_head = P.heads_local; s.head_dim = hd; s.n_ctx = P.n_ctx; s.scale = P.scale;
+        s.out = vec(rank, VA) + 2 * (size_t)rank * nl; s.out_ll = 1; s.out_seq = seq0;
+        peers_of(VA, (size_t)rank * nl, s.out_peer, s.n_out_peer);
+        steps.push_back(s);
+        // wo rows [rank * nl, +nl): B = wo . A + x
+        memset(&s, 0, sizeof(s));
+        s.kind = 0; s.mv = Lc.wo; s.mv.xadd = nullptr; s.mv.sum_out = nullptr; s.mv.row_stride_bytes = 0;
+        s.mv.K = E; s.mv.pro = FL_PRO_PLAIN; s.mv.x = vec(rank, VA); s.mv.x_ll = 1; s.mv.x_seq = seq0;
+        s.mv.epi = FL_EPI_RESADD;
+        if (il == 0) { s.mv.res = W.xa + (size_t)rank * nl; s.mv.res_ll = 0; }
+        else { s.mv.res = vec(rank, VX) + 2 * (size_t)rank * nl; s.mv.res_ll = 1; }
+        s.mv.seg_dst[0] = vec(rank, VB) + 2 * (size_t)rank * nl; s.mv.out_ll = 1; s.mv.out_seq = seq0 + 1;
+        peers_of(VB, (size_t)rank * nl, s.mv.dst_peer, s.mv.n_dst_peer);
+        steps.push_back(s);
+        // w1|w3 rows [rank * fl, +fl): H = silu(w1 . n) * (w3 . n), n = rms_norm(B) * gamma
+        memset(&s, 0, sizeof(s));
+        s.kind = 0; s.mv = Lc.w13; s.mv.xadd = nullptr; s.mv.sum_out = nullptr;
+        s.mv.x = vec(rank, VB); s.mv.x_ll = 1; s.mv.x_seq = seq0 + 1;
+        s.mv.swiglu = 1; s.mv.seg_dst[0] = vec(rank, VH) + 2 * (size_t)rank * fl; s.mv.seg_dst[1] = nullptr; s.mv.out_ll = 1; s.mv.out_seq = seq0 + 2;
+        peers_of(VH, (size_t)rank * fl, s.mv.dst_peer, s.mv.n_dst_peer);
+        steps.push_back(s);
+        // w2 rows [rank * nl, +nl): X = w2 . H + B
+        memset(&s, 0, sizeof(s));
+        s.kind = 0; s.mv = Lc.w2; s.mv.xadd = nullptr; s.mv.sum_out = nullptr; s.mv.row_stride_bytes = 0;
+        s.mv.K = F; s.mv.pro = FL_PRO_PLAIN; s.mv.b = nullptr; s.mv.x = vec(rank, VH); s.mv.x_ll = 1; s.mv.x_seq = seq0 + 2;
+        s.mv.epi = FL_EPI_RESADD; s.mv.res = vec(rank, VB) + 2 * (size_t)rank * nl; s.mv.res_ll = 1;
+        s.mv.seg_dst[0] = vec(rank, VX) + 2 * (size_t)rank * nl; s.mv.out_ll = 1; s.mv.out_seq = seq0 + 3;
+        peers_of(VX, (size_t)rank * nl, s.mv.dst_peer, s.mv.n_dst_peer);
+        steps.push_back(s);
+    }
+    {
         fl_token_step s;
         memset(&s, 0, sizeof(s));
-        s.kind = 1; s.q = Lc.q; s.kcache = Lc.kcache; s.vcache = Lc.vcache; s.out = Lc.att; s.n_past = d_npast;
-        s.k_row_stride = P.n_embd; s.n_head = P.heads_local; s.head_dim = hd; s.n_ctx = P.n_ctx; s.scale = P.scale;
+        s.kind = 0; s.mv = P.head; s.mv.xadd = nullptr; s.mv.sum_out = nullptr;
+        s.mv.x = vec(rank, VX); s.mv.x_ll = 1; s.mv.x_seq = 4 * P.n_layer - 1;
         steps.push_back(s);
-        mv(Lc.wo);
-        mv(Lc.w13);
-        mv(Lc.w2);
     }
-    mv(P.head);
     void *plan = nullptr;
-    if (fl_token_plan_create(steps.data(), (int)steps.size(), &plan) != 0) {
+    if (fl_token_plan_create_ll(steps.data(), (int)steps.size(), (unsigned *)W.peers[rank], &plan) != 0) {
         if (g_verbose) fprintf(stderr, "[ggml_b200] token kernel not used: %s\n", fl_last_error());
         return nullptr;
     }
@@ -1527,7 +1543,13 @@ static void decode_state_release() {
     if (!fl_is_initialized()) return;
     if (D.graph) { fl_graph_destroy(D.graph); D.graph = nullptr; }
     if (D.token_plan) { fl_token_plan_destroy(D.token_plan); D.token_plan = nullptr; }
-    if (D.ws.xa) { fl_dev_free(D.ws.xa); D.ws = DecodeWs(); }      // the peer-mapped reduction buffers (tensor parallel) stay: they are per process
+    if (D.ws.xa) {
+        fl_dev_free(D.ws.xa);
+        if (D.ws.ll_local) fl_dev_free(D.ws.ll_local);
+        DecodeWs keep;                                   // the peer-mapped vectors (tensor parallel) stay: they are per process
+        if (D.ws.peer_mapped) { memcpy(keep.peers, D.ws.peers, sizeof(keep.peers)); keep.peer_mapped = true; keep.ll_cap_embd = D.ws.ll_cap_embd; keep.ll_cap_ff = D.ws.ll_cap_ff; }
+        D.ws = keep;
+    }
     D.plan = DecodePlan();
     D.no_token_plan = false;
     D.tp_kv_sharded = false;

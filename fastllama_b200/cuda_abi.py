@@ -43,13 +43,14 @@ class FlMvArgs(C.Structure):          # struct fl_mv_args, include/fl_cuda.h
                 ("normed_out", C.c_void_p), ("xadd", C.c_void_p), ("sum_out", C.c_void_p), ("row_stride_bytes", C.c_size_t),
                 ("silu_tab", C.c_void_p), ("epi", C.c_int), ("res", C.c_void_p), ("n_past", C.c_void_p),
                 ("n_ctx", C.c_int), ("n_embd", C.c_int), ("head_dim", C.c_int), ("rope_cs", C.c_void_p), ("kcache", C.c_void_p),
-                ("vcache", C.c_void_p), ("xpeer", C.c_void_p * 7), ("n_xpeer", C.c_int), ("dst_peer", C.c_void_p * 7), ("n_dst_peer", C.c_int), ("ll", C.c_int), ("ll_seq", C.c_int)]
+                ("vcache", C.c_void_p), ("dst_peer", C.c_void_p * 7), ("n_dst_peer", C.c_int), ("x_ll", C.c_int), ("x_seq", C.c_int), ("out_ll", C.c_int),
+                ("out_seq", C.c_int), ("res_ll", C.c_int), ("swiglu", C.c_int)]
 
 
 class FlTokenStep(C.Structure):       # struct fl_token_step, include/fl_cuda.h
     _fields_ = [("kind", C.c_int), ("mv", FlMvArgs), ("q", C.c_void_p), ("kcache", C.c_void_p), ("vcache", C.c_void_p),
                 ("out", C.c_void_p), ("n_past", C.c_void_p), ("k_row_stride", C.c_int), ("n_head", C.c_int), ("head_dim", C.c_int),
-                ("n_ctx", C.c_int), ("scale", C.c_float)]
+                ("n_ctx", C.c_int), ("scale", C.c_float), ("out_ll", C.c_int), ("out_seq", C.c_int), ("n_out_peer", C.c_int), ("out_peer", C.c_void_p * 7)]
 
 
 SIGNATURES = {
@@ -100,6 +101,7 @@ SIGNATURES = {
     "fl_dev_mv_fused_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "fl_dev_mv_fused": (C.c_int, [C.POINTER(FlMvArgs)]),
     "fl_token_plan_create": (C.c_int, [C.POINTER(FlTokenStep), C.c_int, C.POINTER(C.c_void_p)]),
+    "fl_token_plan_create_ll": (C.c_int, [C.POINTER(FlTokenStep), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "fl_token_plan_launch": (C.c_int, [C.c_void_p]),
     "fl_token_plan_destroy": (C.c_int, [C.c_void_p]),
     "fl_token_plan_error": (C.c_int, [C.c_void_p]),

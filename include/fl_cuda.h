@@ -167,9 +167,8 @@ typedef struct fl_mv_args {
     const float *gamma;          /* PRO_RMSNORM: norm weight */
     const float *b;              /* PRO_SILUMUL: the multiplier */
     float *normed_out;           /* PRO_RMSNORM: optional copy of gamma * rms_norm(x) (the "embeddings") */
-    const float *xadd;           /* optional: the prologue input is x + xadd (the residual add that follows an
-                                    all-reduced partial result in tensor-parallel mode) ... */
-    float *sum_out;              /* ... and x + xadd is also written here (by CTA 0): the new residual stream */
+    const float *xadd;           /* optional: the prologue input is x + xadd ... */
+    float *sum_out;              /* ... and x + xadd is also written here (by CTA 0) */
     size_t row_stride_bytes;     /* 0 = dense rows of K/32 blocks; else the (16-B multiple) stride of packed K-slices */
     const uint16_t *silu_tab;    /* filled in by the library */
     int epi;
@@ -178,22 +177,23 @@ typedef struct fl_mv_args {
     int n_ctx, n_embd, head_dim;
     const void *rope_cs;         /* filled in by the library (cos/sin table) */
     float *kcache, *vcache;      /* this layer's K [pos][n_embd] and V [n_embd][n_ctx] cache */
-    /* Tensor parallelism inside the token kernel (fl_token_plan_*, never fl_dev_mv_fused).  Buffers come from
-     * fl_comm_shared_alloc.  A K-split step (wo, w2) PUSHES its partial result: besides seg_dst[0] it stores every
-     * value to dst_peer[0..n_dst_peer) -- the same slot of every other rank's buffer, over NVLink.  The step that
-     * consumes the all-reduced vector reads x + xpeer[0] + ... + xpeer[n_xpeer-1] (+ xadd): the ranks' slots IN RANK
-     * ORDER, all in local memory by then; it is preceded by a cross-GPU barrier. */
-    const float *xpeer[7];
-    int n_xpeer;
+    /* Dataflow vectors of the token kernel (fl_token_plan_*, never fl_dev_mv_fused).  A vector in "LL" form holds one 8-byte word
+     * {value, epoch} per element, so a consumer sees the arrival of every element by itself and NO grid barrier (local or cross-GPU)
+     * separates the producing step from the consuming one; the library keeps the running epoch (epoch = launches so far * exchanges
+     * per launch + seq + 1) next to the buffers.
+     *   x_ll:   x is an LL vector written by an earlier step of this token under sequence number x_seq: the prologue polls until every
+     *           element carries that epoch, and the grid barrier in front of the step is dropped.
+     *   out_ll: seg_dst[0] is an LL vector (element r at byte 8r): output row r is stored as {value, epoch(out_seq)}.  With
+     *           n_dst_peer > 0 the same word also goes to dst_peer[0..n_dst_peer) -- the same vector in every other rank's buffer, over
+     *           NVLink (fl_comm_shared_alloc): a ROW-split step of a tensor-parallel model passes pointers that are pre-offset by its
+     *           first row, so every rank ends up with the complete gathered vector, bit-identical to the one-GPU run.
+     *   res_ll: EPI_RESADD reads the residual from an LL vector (element r at res[2r]) that an earlier step has polled completely.
+     * SwiGLU pairs (w1|w3, see fl_token_kernel.cu) store silu(a)*b the same way when out_ll is set. */
     float *dst_peer[7];
     int n_dst_peer;
-    /* ll != 0: the reduction buffers of this step are in "LL" form -- every float travels with an epoch in one 8-byte word
-     * {value, epoch}, so arrival is detected per element and NO barrier (local or cross-GPU) separates the K-split step from its
-     * consumer.  Producer (n_dst_peer > 0): seg_dst[0] and dst_peer[] are LL slots (8 bytes per row).  Consumer (n_xpeer > 0): x and
-     * xpeer[] are LL slots; it polls until every element carries this token's epoch for reduction number ll_seq (the library keeps
-     * the running epoch next to the buffers), then adds the slots in rank order. */
-    int ll;
-    int ll_seq;
+    int x_ll, x_seq, out_ll, out_seq, res_ll;
+    int swiglu;                  /* nseg == 2 (w1|w3 of the FFN): store silu(seg 0 . x) * (seg 1 . x) to seg_dst[0]; seg_dst[1] is not written.
+                                    (Plans without this flag get the same fusion when the next step is the matching PRO_SILUMUL.) */
 } fl_mv_args;
 int fl_dev_mv_fused_supported(int type, int K, int mtot);
 int fl_dev_mv_fused(const fl_mv_args *args);
@@ -205,8 +205,8 @@ int fl_dev_rope_table(int n_dims, int n_pos);    /* make sure the cos/sin table 
 /* ---- the whole decode step as one persistent kernel ---------------------------------------------
  * A token plan is a list of steps, each either an fl_dev_mv_fused call (kind 0) or an
  * fl_dev_attn_decode call (kind 1) with exactly the arguments above; fl_token_plan_launch runs them in
- * order inside ONE cooperative launch of one CTA per SM, with grid barriers between steps and the
- * weight stream prefetched across them.  Results are bit-identical to issuing the steps one by one. */
+ * order inside ONE cooperative launch of one CTA per SM, with the weight stream prefetched across steps.  Steps are separated by grid
+ * barriers unless the consumer's input is a dataflow ("LL") vector (x_ll), in which case the elements themselves signal arrival. */
 typedef struct fl_token_step {
     int kind;                    /* 0 = matvec (mv), 1 = attention (the fields below) */
     fl_mv_args mv;
@@ -215,8 +215,14 @@ typedef struct fl_token_step {
     const int *n_past;
     int k_row_stride, n_head, head_dim, n_ctx;
     float scale;
+    /* attention output as an LL vector (see fl_mv_args): element h * head_dim + d of out / out_peer[] */
+    int out_ll, out_seq, n_out_peer;
+    float *out_peer[7];
 } fl_token_step;
 int fl_token_plan_create(const fl_token_step *steps, int n_steps, void **plan_out);
+/* the same for steps that use LL vectors: epoch_counter is a zero-initialised device word that lives (and is freed) WITH the LL vectors and
+ * is shared by every plan that uses them -- the kernel advances it by the number of exchanges per launch */
+int fl_token_plan_create_ll(const fl_token_step *steps, int n_steps, unsigned *epoch_counter, void **plan_out);
 int fl_token_plan_launch(void *plan);
 int fl_token_plan_destroy(void *plan);
 /* nonzero after a launch whose in-kernel barriers timed out (a peer never arrived); the results are then invalid */

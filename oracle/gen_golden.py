@@ -129,6 +129,36 @@ def lora_ops():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+F32_DOT_KS = (1, 3, 4, 5, 7, 8, 9, 12, 13, 15, 16, 31, 32, 33, 36, 37, 39, 44, 45, 47, 63, 64, 77, 128, 200)
+
+
+def f32_dot():
+    """f32 x f32 mul_mat of the reference LIBRARY for inner lengths with every kind of leftover count (n % 32): pins how the compiled
+    reference adds the leftovers of ggml_vec_dot_f32 (lib/ggml.c:2316-2319; gcc vectorises that loop, see oracle/q4_oracle.c)."""
+    from oracle.pyoracle import REF_GGML_SO
+    from tests import ggml_api as G
+
+    g = G.Ggml(REF_GGML_SO)
+    rng = np.random.default_rng(4242)
+    out = {}
+    m, n = 6, 5
+    for k in F32_DOT_KS:
+        a = rng.standard_normal((m, k)).astype(np.float32)
+        b = rng.standard_normal((n, k)).astype(np.float32)
+        ar = g.context(4 << 20)
+        ta = g.new_tensor_2d(ar.ctx, G.F32, k, m); ar.set(ta, a)
+        tb = g.new_tensor_2d(ar.ctx, G.F32, k, n); ar.set(tb, b)
+        r = g.mul_mat(ar.ctx, ta, tb)
+        gf = G.new_graph()
+        g.build_forward_expand(gf, r)
+        g.graph_compute(ar.ctx, gf)
+        out[f"a{k}"], out[f"b{k}"], out[f"out{k}"] = a, b, ar.numpy(r).reshape(n, m).copy()
+        ar.free()
+    path = os.path.join(OUT, "f32_dot.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     build_oracle()
     ref = RefGgml()
@@ -152,6 +182,7 @@ def main():
         print("wrote", path, os.path.getsize(path), "bytes")
     llama_toy(ref)
     lora_ops()
+    f32_dot()
 
 
 if __name__ == "__main__":

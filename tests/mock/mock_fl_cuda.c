@@ -255,12 +255,13 @@ enum { OP_MV = 1, OP_ATTN = 2, OP_DEQ = 3, OP_ALLREDUCE = 10, OP_ALLGATHER = 11,
 typedef struct {
     int kind;
     fl_mv_args mv;
-    struct { const float *q, *k, *v; float *out; const int *n_past; int n_embd, n_head, hd, n_ctx; float scale; } at;
+    struct { const float *q, *k, *v; float *out; const int *n_past; int n_embd, n_head, hd, n_ctx; float scale; int out_ll, out_seq, n_out_peer; float *out_peer[7]; } at;
+    int swiglu;                      /* w1|w3 step fused with the silu*mul of the next one (as the token kernel does) */
     struct { int type; const void *W; size_t wrs; int K; const int32_t *ids; int n; float *dst; size_t drs; } dq;
     struct { float *send, *recv; size_t n; } co;
     void *plan;
 } mock_op;
-typedef struct { mock_op *ops; int n, cap; } mock_graph;
+typedef struct { mock_op *ops; int n, cap; volatile unsigned *ll_count; int n_ll; } mock_graph;
 static mock_graph *g_capture = NULL;
 
 /* peer-mapped buffers between the CPU processes of a gloo test: POSIX shared memory, one segment per rank, named by
@@ -297,14 +298,27 @@ static void record(const mock_op *op) {
     if (g_capture->n == g_capture->cap) { g_capture->cap = g_capture->cap ? 2 * g_capture->cap : 64; g_capture->ops = realloc(g_capture->ops, sizeof(mock_op) * g_capture->cap); }
     g_capture->ops[g_capture->n++] = *op;
 }
-static void run_mv(const fl_mv_args *a) {
+/* LL vectors: {value, epoch} words.  Polling is real: in the gloo tests the producer is another process writing through POSIX
+ * shared memory. */
+static float ll_wait(const float *slot, int i, unsigned e) {
+    const volatile unsigned *w = (const volatile unsigned *)slot;
+    long spins = 0;
+    while (w[2 * i + 1] != e) { if (++spins > 2000000000L) { fprintf(stderr, "mock: LL word %d never reached epoch %u (has %u)\n", i, e, w[2 * i + 1]); abort(); } }
+    __sync_synchronize();
+    unsigned v = w[2 * i]; float f; memcpy(&f, &v, 4); return f;
+}
+static void ll_store(float *slot, int i, float v, unsigned e, float *const *peers, int n_peers) {
+    unsigned u; memcpy(&u, &v, 4);
+    volatile unsigned *w = (volatile unsigned *)slot;
+    w[2 * i] = u; __sync_synchronize(); w[2 * i + 1] = e;
+    for (int p = 0; p < n_peers; p++) { volatile unsigned *q = (volatile unsigned *)peers[p]; q[2 * i] = u; __sync_synchronize(); q[2 * i + 1] = e; }
+}
+static void run_mv(const fl_mv_args *a, int swiglu, unsigned e_in, unsigned e_out) {
     const int K = a->K, nb = K / 32, bb = a->type == 2 ? 20 : 24;
     const size_t rstride = a->row_stride_bytes ? a->row_stride_bytes : (size_t)nb * bb;
     float *v = malloc(sizeof(float) * K), *xin = malloc(sizeof(float) * K);
-    const int ist = (a->ll && a->n_xpeer > 0) ? 2 : 1;                      /* LL slots: {value, epoch} words */
     for (int i = 0; i < K; i++) {
-        float t = a->x[ist * i];
-        for (int r = 0; r < a->n_xpeer; r++) t += a->xpeer[r][ist * i];    /* the ranks' slots, rank order */
+        const float t = a->x_ll ? ll_wait(a->x, i, e_in) : a->x[i];
         xin[i] = a->xadd ? t + a->xadd[i] : t;
     }
     if (a->sum_out) memcpy(a->sum_out, xin, sizeof(float) * K);
@@ -319,12 +333,21 @@ static void run_mv(const fl_mv_args *a) {
     void *q8 = malloc((size_t)nb * 40);
     orc_quantize_row_q8_0(v, q8, K);
     const int n_past = a->epi == FL_EPI_QKV ? *a->n_past : 0;
+    float *seg_out[3] = {NULL, NULL, NULL};
     for (int sg = 0; sg < a->nseg; sg++) {
-        float *tmp = malloc(sizeof(float) * a->seg_rows[sg]);
+        float *tmp = seg_out[sg] = malloc(sizeof(float) * a->seg_rows[sg]);
         for (int r = 0; r < a->seg_rows[sg]; r++) {
             const void *wr = (const char *)a->seg_w[sg] + (size_t)r * rstride;
             if (a->type == 2) orc_vec_dot_q4_0_q8_0(K, tmp + r, wr, q8); else orc_vec_dot_q4_1_q8_0(K, tmp + r, wr, q8);
         }
+    }
+    if (swiglu) {
+        for (int r = 0; r < a->seg_rows[0]; r++) {
+            const float o = h2f(tab_silu[f2h(seg_out[0][r])]) * seg_out[1][r];
+            if (a->out_ll) ll_store(a->seg_dst[0], r, o, e_out, a->dst_peer, a->n_dst_peer); else a->seg_dst[0][r] = o;
+        }
+    } else for (int sg = 0; sg < a->nseg; sg++) {
+        float *tmp = seg_out[sg];
         if (a->epi == FL_EPI_QKV) {
             const int hd = a->head_dim; const float ts = powf(10000.0f, -2.0f / hd);
             for (int r = 0; r < a->seg_rows[sg]; r += 2) {
@@ -337,16 +360,14 @@ static void run_mv(const fl_mv_args *a) {
                 } else { a->vcache[(size_t)r * a->n_ctx + n_past] = x0; a->vcache[(size_t)(r + 1) * a->n_ctx + n_past] = x1; }
             }
         } else for (int r = 0; r < a->seg_rows[sg]; r++) {
-            const float o = a->epi == FL_EPI_RESADD ? tmp[r] + a->res[r] : tmp[r];
-            const int ost = (a->ll && a->n_dst_peer > 0) ? 2 : 1;
-            a->seg_dst[sg][ost * r] = o;
-            for (int pr = 0; pr < a->n_dst_peer; pr++) a->dst_peer[pr][ost * r] = o;       /* push into the peers' buffers */
+            const float o = a->epi == FL_EPI_RESADD ? tmp[r] + (a->res_ll ? a->res[2 * r] : a->res[r]) : tmp[r];
+            if (a->out_ll) ll_store(a->seg_dst[sg], r, o, e_out, a->dst_peer, a->n_dst_peer); else a->seg_dst[sg][r] = o;
         }
-        free(tmp);
     }
+    for (int sg = 0; sg < a->nseg; sg++) free(seg_out[sg]);
     free(q8); free(v);
 }
-static void run_attn(const mock_op *o) {
+static void run_attn(const mock_op *o, unsigned e_out) {
     const int hd = o->at.hd, n_pos = *o->at.n_past + 1;
     float *p = malloc(sizeof(float) * n_pos);
     for (int h = 0; h < o->at.n_head; h++) {
@@ -355,7 +376,10 @@ static void run_attn(const mock_op *o) {
         for (int j = 0; j < n_pos; j++) { float v = h2f(tab_exp[f2h(p[j] - mx)]); sum += v; p[j] = v; }
         float inv = (float)(1.0 / sum);
         for (int j = 0; j < n_pos; j++) p[j] *= inv;
-        for (int d = 0; d < hd; d++) o->at.out[h * hd + d] = orc_vec_dot_f32(n_pos, o->at.v + ((size_t)h * hd + d) * o->at.n_ctx, p);
+        for (int d = 0; d < hd; d++) {
+            const float r = orc_vec_dot_f32(n_pos, o->at.v + ((size_t)h * hd + d) * o->at.n_ctx, p);
+            if (o->at.out_ll) ll_store(o->at.out, h * hd + d, r, e_out, o->at.out_peer, o->at.n_out_peer); else o->at.out[h * hd + d] = r;
+        }
     }
     free(p);
 }
@@ -363,15 +387,17 @@ static void run_op(const mock_op *o) {
     g_launches++;
     if (o->kind == OP_PLAN) {
         const mock_graph *pg = o->plan;
+        const unsigned base = pg->ll_count ? *pg->ll_count : 0u;
         for (int i = 0; i < pg->n; i++) {
-            if (pg->ops[i].kind == OP_MV && pg->ops[i].mv.n_xpeer > 0) mock_barrier();       /* the kernel's cross-GPU barrier */
-            run_op(&pg->ops[i]);
-            g_launches--;
+            const mock_op *q = &pg->ops[i];
+            if (q->kind == OP_MV) run_mv(&q->mv, q->swiglu, base + (unsigned)q->mv.x_seq + 1u, base + (unsigned)q->mv.out_seq + 1u);
+            else if (q->kind == OP_ATTN) run_attn(q, base + (unsigned)q->at.out_seq + 1u);
         }
+        if (pg->ll_count) *pg->ll_count = base + (unsigned)pg->n_ll;
         return;
     }
-    if (o->kind == OP_MV) run_mv(&o->mv);
-    else if (o->kind == OP_ATTN) run_attn(o);
+    if (o->kind == OP_MV) run_mv(&o->mv, 0, 0, 0);
+    else if (o->kind == OP_ATTN) run_attn(o, 0);
     else if (o->kind == OP_ALLREDUCE) g_coll(0, o->co.send, o->co.recv, o->co.n);
     else if (o->kind == OP_ALLGATHER) g_coll(1, o->co.send, o->co.recv, o->co.n);
     else for (int i = 0; i < o->dq.n; i++) {
@@ -387,17 +413,38 @@ int fl_dev_attn_decode(const float *q, const float *k, const float *v, float *ou
     if (g_capture) record(&o); else run_op(&o); return 0;
 }
 /* the persistent token kernel: the mock runs its steps one after another */
-int fl_token_plan_create(const fl_token_step *steps, int n, void **out) {
+int fl_token_plan_create_ll(const fl_token_step *steps, int n, unsigned *epoch_counter, void **out) {
     mock_graph *pg = calloc(1, sizeof(mock_graph));
     pg->ops = calloc((size_t)n, sizeof(mock_op)); pg->n = pg->cap = n;
+    pg->ll_count = epoch_counter;
     for (int i = 0; i < n; i++) {
         mock_op *o = &pg->ops[i];
-        if (steps[i].kind == 0) { o->kind = OP_MV; o->mv = steps[i].mv; }
-        else { o->kind = OP_ATTN; o->at.q = steps[i].q; o->at.k = steps[i].kcache; o->at.v = steps[i].vcache; o->at.out = steps[i].out; o->at.n_past = steps[i].n_past;
-               o->at.n_embd = steps[i].k_row_stride; o->at.n_head = steps[i].n_head; o->at.hd = steps[i].head_dim; o->at.n_ctx = steps[i].n_ctx; o->at.scale = steps[i].scale; }
+        if (steps[i].kind == 0) {
+            o->kind = OP_MV; o->mv = steps[i].mv; o->swiglu = steps[i].mv.swiglu;
+            if (o->mv.out_ll && o->mv.out_seq + 1 > pg->n_ll) pg->n_ll = o->mv.out_seq + 1;
+            if (o->mv.x_ll && o->mv.x_seq + 1 > pg->n_ll) pg->n_ll = o->mv.x_seq + 1;
+        } else {
+            o->kind = OP_ATTN; o->at.q = steps[i].q; o->at.k = steps[i].kcache; o->at.v = steps[i].vcache; o->at.out = steps[i].out; o->at.n_past = steps[i].n_past;
+            o->at.n_embd = steps[i].k_row_stride; o->at.n_head = steps[i].n_head; o->at.hd = steps[i].head_dim; o->at.n_ctx = steps[i].n_ctx; o->at.scale = steps[i].scale;
+            o->at.out_ll = steps[i].out_ll; o->at.out_seq = steps[i].out_seq; o->at.n_out_peer = steps[i].n_out_peer;
+            for (int r = 0; r < 7; r++) o->at.out_peer[r] = steps[i].out_peer[r];
+            if (o->at.out_ll && o->at.out_seq + 1 > pg->n_ll) pg->n_ll = o->at.out_seq + 1;
+        }
     }
+    /* the token kernel's SwiGLU fusion (fl_token_kernel.cu, plan creation): w1|w3 followed by silu(.)*(.) over exactly their outputs */
+    for (int i = 0; i + 1 < n; i++) {
+        mock_op *p0 = &pg->ops[i], *p1 = &pg->ops[i + 1];
+        if (p0->kind != OP_MV || p1->kind != OP_MV || p0->swiglu) continue;
+        const fl_mv_args *a = &p0->mv;
+        if (a->nseg == 2 && a->epi == FL_EPI_STORE && a->seg_rows[0] == a->seg_rows[1] && p1->mv.pro == FL_PRO_SILUMUL && p1->mv.x == a->seg_dst[0] &&
+            p1->mv.b == a->seg_dst[1] && p1->mv.K == a->seg_rows[0] && p1->mv.xadd == NULL) {
+            p0->swiglu = 1; p1->mv.pro = FL_PRO_PLAIN; p1->mv.b = NULL;
+        }
+    }
+    if (pg->n_ll > 0 && !epoch_counter) { free(pg->ops); free(pg); return -1; }
     *out = pg; return 0;
 }
+int fl_token_plan_create(const fl_token_step *steps, int n, void **out) { return fl_token_plan_create_ll(steps, n, NULL, out); }
 int fl_token_plan_launch(void *plan) { mock_op o; memset(&o, 0, sizeof(o)); o.kind = OP_PLAN; o.plan = plan; if (g_capture) record(&o); else run_op(&o); return 0; }
 int fl_token_plan_profile(void *plan, unsigned long long *out, size_t n, int *c) { (void)plan; (void)out; (void)n; *c = 0; return -1; }
 int fl_token_plan_profile2(void *plan, unsigned *out, size_t n) { (void)plan; (void)out; (void)n; return -1; }

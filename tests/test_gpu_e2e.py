@@ -3,12 +3,9 @@
   * the drop-in pyfastllama.so of this repo (the reference's UNCHANGED bridge/llama.cpp over libggml_b200)
 via the same Python Model class (fastllama_b200/model.py, mirror of the reference's fastllama.Model).
 
-north_star bar: greedy token-id sequence identical; logits within a stated fp tolerance.  The
-tolerance here is 2e-2 * max|logit|: a last-ulp difference in fp32 summation order can flip an fp16
-table lookup or a q8_0 rounding downstream; one flipped q8_0 step is ~1% of a
-block's largest activation, and on these tiny, large-weight toy models such an event shows up as
-up to ~1e-2 of the logit range (measured with a bit-exact-matmul CPU stand-in of the device layer,
-DESIGN.md "Parity"); without a flip the logits agree to ~1e-7.
+north_star bar: greedy token-id sequence identical; logits within a stated fp tolerance.  The tolerance here is ZERO: the logits after
+the prompt and the decode steps carry the reference's bits (every fp32 operation in the reference's order, fl_exact.cuh; the prompt of
+these tests stays below the 16 columns from which the tcgen05 GEMM -- reordering budget, not bit-identical -- takes over).
 """
 import os
 
@@ -48,5 +45,6 @@ def test_greedy_tokens_and_logits_match_reference(tmp_path, wtype, n_batch):
     our_toks, our_logits = _run(DROPIN, path, n_batch)
     assert len(ref_toks) > 4
     assert our_toks == ref_toks, (our_toks, ref_toks)
-    assert np.abs(our_logits - ref_logits).max() <= 2e-2 * np.abs(ref_logits).max()
+    nd = int((our_logits.view(np.uint32) != ref_logits.view(np.uint32)).sum())
+    assert nd == 0, (nd, our_logits.size, float(np.abs(our_logits - ref_logits).max()))      # the reference's bits, after prompt + decode steps
     assert int(our_logits.argmax()) == int(ref_logits.argmax())

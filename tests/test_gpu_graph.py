@@ -2,11 +2,9 @@
 oracle/_ref/libggml_ref.so) and on libggml_b200 (B200); results are compared op by op and for whole
 LLaMA eval graphs (prompt + decode steps, KV cache carried across ggml_graph_compute calls).
 
-Tolerances (stated per check): table-driven / single-rounding ops are bit-exact; fp32 reductions
-may differ in summation order only -- 1e-6 relative to the sum of magnitudes; whole graphs, where a
-last-ulp difference can flip a q8_0 rounding or an fp16 table lookup downstream (SURVEY.md section
-7; observed: q4_0 run agrees to 1e-6 on every node, the q4_1 run has one silu-table flip in layer 1
-that grows to 6e-3 at the logits), logits within 2e-2 * max|logit| and the same argmax.
+Bar: the reference library's BITS, op by op and at the logits of whole eval graphs -- every fp32 operation follows the reference's
+order (fl_exact.cuh).  The one op with a stated tolerance is rms_norm, whose double-precision sum of squares is added in another order
+(one ulp of the float mean when the double sum sits on a rounding boundary; never observed in these graphs).
 """
 import math
 import os
@@ -91,9 +89,9 @@ def test_rope_and_mask_and_softmax(libs):
         sm = g.soft_max(a.ctx, g.diag_mask_inf(a.ctx, kq, 9))
         return [q, sm]
     r, o = both(libs, build)
-    assert np.allclose(r[0], o[0], rtol=0, atol=1e-6 * np.abs(r[0]).max()), "rope"
+    assert np.array_equal(bits(r[0]), bits(o[0])), "rope"              # host-built cos/sin table (libm), the reference build's fma contraction
     assert np.array_equal(r[1] == 0, o[1] == 0), "mask pattern"
-    assert np.allclose(r[1], o[1], rtol=2e-6, atol=1e-9), "soft_max"
+    assert np.array_equal(bits(r[1]), bits(o[1])), "soft_max"          # fp16 table values: the double sum is exact in any order
     assert np.allclose(o[1].sum(-1), 1.0, atol=1e-3)
 
 
@@ -110,15 +108,16 @@ def test_cpy_strided_and_mul_mat_f32(libs):
         return [xt, kq, merged]
     r, o = both(libs, build)
     assert np.array_equal(bits(r[0]), bits(o[0]))
-    assert np.allclose(r[1], o[1], rtol=0, atol=1e-6 * 16 * 9.0)
+    assert np.array_equal(bits(r[1]), bits(o[1]))          # mul_mat f32: ggml_vec_dot_f32's order, inner length 16 = leftovers only
     assert np.array_equal(bits(r[2]), bits(o[2]))
 
 
 def test_mul_mat_f32_attention_shapes_of_a_prompt_eval(libs):
-    """K*Q and V*P of a multi-token eval (n_batch = 128): big enough for the tiled f32 kernel, ragged against its 64 x 64 tiles, and
-    with the strided operands Model::eval uses (K as a permuted view of the cache, V^T with n_ctx row stride)."""
+    """K*Q and V*P of a multi-token eval with the strided operands Model::eval uses (K as a permuted view of the cache, V^T with n_ctx
+    row stride); inner lengths 128 (no leftovers) and 205 (13 leftovers: 8 + 4 products-then-adds and one fma in the reference build):
+    the same bits as the reference library."""
     def build(g, a, rng):
-        hd, n_pos, n, heads, n_ctx = 128, 200, 96, 3, 256
+        hd, n_pos, n, heads, n_ctx = 128, 205, 96, 3, 256
         kc = f32(g, a, rng, hd * heads, n_pos)                                                    # cache rows [pos][n_embd]
         k = g.permute(a.ctx, g.reshape_3d(a.ctx, kc, hd, heads, n_pos), 0, 2, 1, 3)               # [hd, n_pos, heads]
         q = f32(g, a, rng, hd, n, heads)
@@ -129,8 +128,8 @@ def test_mul_mat_f32_attention_shapes_of_a_prompt_eval(libs):
         kqv = g.mul_mat(a.ctx, v, p)                                                              # [hd, n, heads]
         return [kq, kqv]
     r, o = both(libs, build)
-    assert np.allclose(r[0], o[0], rtol=0, atol=1e-6 * 128 * 9.0)
-    assert np.allclose(r[1], o[1], rtol=0, atol=1e-6 * 200 * 9.0)
+    assert np.array_equal(bits(r[0]), bits(o[0]))
+    assert np.array_equal(bits(r[1]), bits(o[1]))
 
 
 @pytest.mark.parametrize("t", [G.Q4_0, G.Q4_1])
@@ -147,7 +146,7 @@ def test_get_rows_and_quantised_mul_mat(libs, t):
         return [g.get_rows(a.ctx, wt, ids), g.mul_mat(a.ctx, wt, x)]
     r, o = both(libs, build)
     assert np.array_equal(bits(r[0]), bits(o[0]))
-    assert np.allclose(r[1], o[1], rtol=0, atol=4e-6 * np.abs(r[1]).max() * 8)
+    assert np.array_equal(bits(r[1]), bits(o[1]))
 
 
 @pytest.mark.parametrize("t", [G.Q4_0, G.Q4_1])
@@ -170,9 +169,8 @@ def test_llama_eval_prompt_then_decode(libs, t, dims):
             outs.append((c.numpy(named["logits"]).copy(), c.numpy(named["embeddings"]).copy()))
         (rl, re), (ol, oe) = outs
         assert np.isfinite(ol).all()
-        assert np.abs(rl - ol).max() <= 2e-2 * np.abs(rl).max(), (n_past, np.abs(rl - ol).max(), np.abs(rl).max())
-        assert np.abs(re - oe).max() <= 2e-2 * np.abs(re).max()
-        assert np.array_equal(rl.argmax(-1), ol.argmax(-1))
+        nd = int((bits(rl) != bits(ol)).sum()), int((bits(re) != bits(oe)).sum())
+        assert nd == (0, 0), (n_past, nd, rl.size, float(np.abs(rl - ol).max()), float(np.abs(rl).max()))      # the reference library's bits
     import ctypes as C
     assert C.CDLL(OURS).ggml_b200_decode_mode() == (2 if dims == "fused" else 0)
 

@@ -113,10 +113,24 @@ def test_simd_quantizers_match_golden(oracle, lora_golden, name, t):
 
 @pytest.mark.parametrize("r", [8, 16, 40, 64])
 def test_f32_mul_mat_order_matches_golden(oracle, lora_golden, r):
-    """B*A of a LoRA adapter: ggml_vec_dot_f32 in the AVX2 + FMA build's order (32-wide SIMD part, tree reduce, fma leftovers)."""
+    """B*A of a LoRA adapter: ggml_vec_dot_f32 in the AVX2 + FMA build's order (32-wide SIMD part, tree reduce, leftovers as the compiled loop adds them)."""
     g = lora_golden
     got = oracle.mul_mat_f32(g[f"A{r}"], g[f"B{r}"])
     assert np.array_equal(got.view(np.uint32), g[f"BA{r}"].view(np.uint32))
+
+
+def test_f32_dot_leftovers_match_golden(oracle):
+    """ggml_vec_dot_f32 for every leftover count n % 32 (tests/golden/f32_dot.npz, outputs of the reference library): the compiled
+    reference adds leftovers in groups of 8 and one group of 4 as rounded product + rounded add and the last <= 3 as an fma.  The
+    attention products of a prompt eval (inner length = number of positions) go through exactly this."""
+    import os
+
+    from oracle.gen_golden import F32_DOT_KS
+
+    g = np.load(os.path.join(os.path.dirname(GOLDEN_LORA), "f32_dot.npz"))
+    for k in F32_DOT_KS:
+        got = oracle.mul_mat_f32(g[f"a{k}"], g[f"b{k}"])
+        assert np.array_equal(got.view(np.uint32), g[f"out{k}"].view(np.uint32)), k
 
 
 @pytest.mark.parametrize("name,t", TYPES)
