@@ -573,7 +573,8 @@ int flk_mul_mat_q(cudaStream_t st, int type, const void *W, size_t wrs, int M, i
     // 4-7 tcgen05 (column tile chosen / 32 / 64 / 128), 8 reference order.
     if (impl == 0) {
         static const int umma_auto = getenv("FASTLLAMA_B200_UMMA") ? atoi(getenv("FASTLLAMA_B200_UMMA")) : 1;     // FASTLLAMA_B200_UMMA=0: no tensor-core path
-        static const bool exact_ingest = getenv("FASTLLAMA_B200_INGEST") && !strcmp(getenv("FASTLLAMA_B200_INGEST"), "exact");
+        const char *ing = getenv("FASTLLAMA_B200_INGEST");               // read per call: tests and callers may switch it between evals
+        const bool exact_ingest = ing && !strcmp(ing, "exact");
         if (umma_auto && !exact_ingest && N >= 16 && flk_mul_mat_q_umma_supported(type, W, wrs, M, K, N)) return flk_mul_mat_q_umma(st, type, W, wrs, M, K, Yq8, N, dst, drs, 0);
         return flk_mul_mat_q_ref(st, type, W, wrs, M, K, Yq8, N, dst, drs);
     }

@@ -43,9 +43,9 @@
 #define TK_PW 4                  // producer warps: warp TK_CW + g streams the tiles of tile group g (its own slots, its own pace)
 #define TK_THREADS (TK_NT + 32 * TK_PW)
 #define TK_REGS_CONSUMER 104      // setmaxnreg: the producer warpgroup hands registers to the four consumer warpgroups.  The pool is the CTA's
-                                  // LAUNCH allocation (96 x 640 = 61440 registers): 104 x 512 + 56 x 128 = 60416 fits; a request beyond the pool
+                                  // LAUNCH allocation (96 x 640 = 61440 registers): 104 x 512 + 64 x 128 = 61440 is exactly the pool; a request beyond the pool
                                   // waits forever (checked on the host at plan creation)
-#define TK_REGS_PRODUCER 56
+#define TK_REGS_PRODUCER 64
 
 enum { TK_PH_MATVEC = 0, TK_PH_ATTN = 1 };
 
@@ -108,6 +108,21 @@ __device__ __forceinline__ void tk_wait_ge(const unsigned *p, unsigned target, b
             if (t0 == 0) t0 = t;
             else if (t - t0 > 2000000000ull) {
                 if (atomicExch(err, 1u) == 0u) { err[1] = who; err[2] = target; err[3] = v; err[4] = blockIdx.x; }   // first failure, for the host's message
+                return;
+            }
+        }
+    }
+}
+// mbarrier wait of the weight ring, bounded like every other spin of this kernel: a protocol bug reports (who, slot, parity) instead of hanging the GPU
+__device__ __forceinline__ void tk_mbar_wait(uint32_t bar, uint32_t parity, unsigned *err, unsigned who, unsigned slot) {
+    unsigned long long t0 = 0;
+    for (unsigned n = 1; !fl_mbar_try_wait(bar, parity); n++) {
+        if ((n & 4095u) == 0) {
+            if (*(volatile unsigned *)err) return;
+            const unsigned long long t = tk_now();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) {
+                if (atomicExch(err, 1u) == 0u) { err[1] = who; err[2] = slot; err[3] = parity; err[4] = blockIdx.x; }
                 return;
             }
         }
@@ -502,7 +517,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
             int s;
             uint32_t par;
             tk_slot_of(prm, g, cg + (uint32_t)(k0 * C + c * n_r + wl), s, par);
-            fl_mbar_wait(bar0 + 8u * s, par);
+            tk_mbar_wait(bar0 + 8u * s, par, prm.err, 0x400u + (unsigned)warp, (unsigned)s);
             if (PROF) { const unsigned t = tk_clock(); c_wait += t - c_t; c_t = t; c_rounds++; }
             if (!(prm.diag & 2)) {
                 const uint8_t *wp = stage0 + (size_t)s * prm.slot_bytes + row_off;
@@ -709,7 +724,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
                                 else if (lane < 2 * nunits) src = (seg == 0 ? w0 : seg == 1 ? w1 : w2) + (size_t)(2 * unit0 + lane) * row_bytes;
                             }
                             if (lane == 0) {
-                                fl_mbar_wait(bar0 + 8u * (S + s), par ^ 1u);
+                                tk_mbar_wait(bar0 + 8u * (S + s), par ^ 1u, prm.err, 0x500u + (unsigned)pg, (unsigned)s);
                                 if (prm.diag & 1) fl_mbar_arrive(bar0 + 8u * s);
                                 else fl_mbar_expect_tx(bar0 + 8u * s, 2u * (uint32_t)nunits * cbytes);
                             }
@@ -1018,8 +1033,9 @@ int flk_token_plan_error(void *plan) {
     if (!pl || !pl->h_err) return 0;
     const volatile unsigned *e = pl->h_err;      // written by the kernel straight into host memory; the caller has synchronised the stream
     if (e[0])
-        fl_set_error("token kernel barrier timeout: %s (code 0x%x), waited for %u, last saw %u, CTA %u, rank %d of %d", (e[1] & 0x200u) ? "peer flag" : "local grid counter",
-                     e[1], e[2], e[3], e[4], pl->prm.rank, pl->prm.world);
+        fl_set_error("token kernel timeout: %s (code 0x%x), waited for / slot %u, last saw / parity %u, CTA %u, rank %d of %d",
+                     (e[1] & 0x700u) == 0x400u ? "consumer warp waiting for a weight tile" : (e[1] & 0x700u) == 0x500u ? "producer waiting for a free ring slot" :
+                     (e[1] & 0x300u) == 0x300u ? "LL vector element" : "grid barrier counter", e[1], e[2], e[3], e[4], pl->prm.rank, pl->prm.world);
     return (int)e[0];
 }
 

@@ -1382,66 +1382,73 @@ void issue_decode(const DecodePlan &P, const int *d_npast) {
     profiled_mv(P.head);
 }
 
-// The decode step as the program of the persistent token kernel (one cooperative launch per token; fl_token_kernel.cu).  Every
-// activation vector travels as a dataflow (LL) vector -- X: residual stream, A: attention output, B: x + wo.att, H: FFN hidden --
-// so the only grid barrier of a layer is the one in front of the attention (q and the new KV rows of all CTAs).  With `world` GPUs
-// every matrix is row-split and a step stores its row slice into ALL ranks' copies of the vector: the gathered vectors, and with
-// them every later operation, are bit-identical to the one-GPU run.  Returns nullptr when the shapes are outside what the kernel handles.
+// The decode step as the program of the persistent token kernel (one cooperative launch per token; fl_token_kernel.cu).
+// The activation vectors between the steps -- X: residual stream, A: attention output, B: x + wo.att, H: FFN hidden -- live in one buffer.
+//   * one GPU: plain f32 vectors, a grid barrier in front of every step.  (The dataflow form below was measured here too,
+//     FASTLLAMA_B200_DATAFLOW=1: 472 vs 550 tokens/s on 7B -- 148 CTAs polling the same words cost more than the barrier they replace.)
+//   * `world` GPUs: every matrix is row-split and a step stores its row slice into ALL ranks' copies of the vector as dataflow (LL)
+//     words {value, epoch}; the consumer polls for this token's epoch, so no barrier -- local or cross-GPU -- separates the steps
+//     (only the one in front of the attention remains: q and the new KV rows of the local CTAs).  The gathered vectors, and with
+//     them every later operation, are bit-identical to the one-GPU run.
+// Returns nullptr when the shapes are outside what the kernel handles.
 void *make_token_plan(const DecodePlan &P, const DecodeWs &W, const int *d_npast) {
     std::vector<fl_token_step> steps;
     const int rank = P.world > 1 ? fl_comm_rank() : 0, world = P.world;
+    static const bool dataflow_env = getenv("FASTLLAMA_B200_DATAFLOW") != nullptr;
+    const int ll = (world > 1 || dataflow_env) ? 1 : 0;
+    const size_t es = ll ? 2 : 1;                                   // floats per element
     const int E = P.n_embd, F = W.n_ff, nl = E / world, fl = F / world, hd = E / P.n_head;
-    // vector v (0 X, 1 A, 2 B, 3 H) in rank q's buffer, as mapped here
-    auto vec = [&](int q, int v) -> float * {
+    // element `first` of vector v (0 X, 1 A, 2 B, 3 H) in rank q's buffer, as mapped here
+    auto vec = [&](int q, int v, size_t first) -> float * {
         const size_t off = 4096 + (size_t)(v < 3 ? v : 3) * W.ll_cap_embd * 8;
-        return (float *)((char *)W.peers[q] + off);
+        return (float *)((char *)W.peers[q] + off) + es * first;
     };
-    auto peers_of = [&](int v, size_t first_elem, float **dst, int &n) {
+    auto peers_of = [&](int v, size_t first, float **dst, int &n) {
         n = 0;
         for (int q = 0; q < world; q++)
-            if (q != rank) dst[n++] = vec(q, v) + 2 * first_elem;
+            if (q != rank) dst[n++] = vec(q, v, first);
     };
     enum { VX = 0, VA = 1, VB = 2, VH = 3 };
     for (int il = 0; il < P.n_layer; il++) {
         const LayerPlan &Lc = P.layers[il];
         const int seq0 = 4 * il;                                    // A: seq0, B: seq0 + 1, H: seq0 + 2, X (input of layer il + 1): seq0 + 3
         fl_token_step s;
-        // wq|wk|wv (this rank's heads): x = embedding row (layer 0) or the gathered residual stream
+        // wq|wk|wv (this rank's heads): x = embedding row (layer 0) or the residual stream
         memset(&s, 0, sizeof(s));
         s.kind = 0; s.mv = Lc.qkv; s.mv.n_past = d_npast; s.mv.xadd = nullptr; s.mv.sum_out = nullptr;
         if (il == 0) s.mv.x = W.xa;
-        else { s.mv.x = vec(rank, VX); s.mv.x_ll = 1; s.mv.x_seq = seq0 - 1; }
+        else { s.mv.x = vec(rank, VX, 0); s.mv.x_ll = ll; s.mv.x_seq = seq0 - 1; }
         steps.push_back(s);
-        // attention over this rank's heads -> slice [rank * nl, +nl) of A everywhere
+        // attention over this rank's heads -> elements [rank * nl, +nl) of A (everywhere)
         memset(&s, 0, sizeof(s));
         s.kind = 1; s.q = Lc.q; s.kcache = Lc.kcache; s.vcache = Lc.vcache; s.n_past = d_npast;
         s.k_row_stride = E; s.n_head = P.heads_local; s.head_dim = hd; s.n_ctx = P.n_ctx; s.scale = P.scale;
-        s.out = vec(rank, VA) + 2 * (size_t)rank * nl; s.out_ll = 1; s.out_seq = seq0;
+        s.out = vec(rank, VA, (size_t)rank * nl); s.out_ll = ll; s.out_seq = seq0;
         peers_of(VA, (size_t)rank * nl, s.out_peer, s.n_out_peer);
         steps.push_back(s);
         // wo rows [rank * nl, +nl): B = wo . A + x
         memset(&s, 0, sizeof(s));
         s.kind = 0; s.mv = Lc.wo; s.mv.xadd = nullptr; s.mv.sum_out = nullptr; s.mv.row_stride_bytes = 0;
-        s.mv.K = E; s.mv.pro = FL_PRO_PLAIN; s.mv.x = vec(rank, VA); s.mv.x_ll = 1; s.mv.x_seq = seq0;
+        s.mv.K = E; s.mv.pro = FL_PRO_PLAIN; s.mv.x = vec(rank, VA, 0); s.mv.x_ll = ll; s.mv.x_seq = seq0;
         s.mv.epi = FL_EPI_RESADD;
         if (il == 0) { s.mv.res = W.xa + (size_t)rank * nl; s.mv.res_ll = 0; }
-        else { s.mv.res = vec(rank, VX) + 2 * (size_t)rank * nl; s.mv.res_ll = 1; }
-        s.mv.seg_dst[0] = vec(rank, VB) + 2 * (size_t)rank * nl; s.mv.out_ll = 1; s.mv.out_seq = seq0 + 1;
+        else { s.mv.res = vec(rank, VX, (size_t)rank * nl); s.mv.res_ll = ll; }
+        s.mv.seg_dst[0] = vec(rank, VB, (size_t)rank * nl); s.mv.out_ll = ll; s.mv.out_seq = seq0 + 1;
         peers_of(VB, (size_t)rank * nl, s.mv.dst_peer, s.mv.n_dst_peer);
         steps.push_back(s);
         // w1|w3 rows [rank * fl, +fl): H = silu(w1 . n) * (w3 . n), n = rms_norm(B) * gamma
         memset(&s, 0, sizeof(s));
         s.kind = 0; s.mv = Lc.w13; s.mv.xadd = nullptr; s.mv.sum_out = nullptr;
-        s.mv.x = vec(rank, VB); s.mv.x_ll = 1; s.mv.x_seq = seq0 + 1;
-        s.mv.swiglu = 1; s.mv.seg_dst[0] = vec(rank, VH) + 2 * (size_t)rank * fl; s.mv.seg_dst[1] = nullptr; s.mv.out_ll = 1; s.mv.out_seq = seq0 + 2;
+        s.mv.x = vec(rank, VB, 0); s.mv.x_ll = ll; s.mv.x_seq = seq0 + 1;
+        s.mv.swiglu = 1; s.mv.seg_dst[0] = vec(rank, VH, (size_t)rank * fl); s.mv.seg_dst[1] = nullptr; s.mv.out_ll = ll; s.mv.out_seq = seq0 + 2;
         peers_of(VH, (size_t)rank * fl, s.mv.dst_peer, s.mv.n_dst_peer);
         steps.push_back(s);
         // w2 rows [rank * nl, +nl): X = w2 . H + B
         memset(&s, 0, sizeof(s));
         s.kind = 0; s.mv = Lc.w2; s.mv.xadd = nullptr; s.mv.sum_out = nullptr; s.mv.row_stride_bytes = 0;
-        s.mv.K = F; s.mv.pro = FL_PRO_PLAIN; s.mv.b = nullptr; s.mv.x = vec(rank, VH); s.mv.x_ll = 1; s.mv.x_seq = seq0 + 2;
-        s.mv.epi = FL_EPI_RESADD; s.mv.res = vec(rank, VB) + 2 * (size_t)rank * nl; s.mv.res_ll = 1;
-        s.mv.seg_dst[0] = vec(rank, VX) + 2 * (size_t)rank * nl; s.mv.out_ll = 1; s.mv.out_seq = seq0 + 3;
+        s.mv.K = F; s.mv.pro = FL_PRO_PLAIN; s.mv.b = nullptr; s.mv.x = vec(rank, VH, 0); s.mv.x_ll = ll; s.mv.x_seq = seq0 + 2;
+        s.mv.epi = FL_EPI_RESADD; s.mv.res = vec(rank, VB, (size_t)rank * nl); s.mv.res_ll = ll;
+        s.mv.seg_dst[0] = vec(rank, VX, (size_t)rank * nl); s.mv.out_ll = ll; s.mv.out_seq = seq0 + 3;
         peers_of(VX, (size_t)rank * nl, s.mv.dst_peer, s.mv.n_dst_peer);
         steps.push_back(s);
     }
@@ -1449,7 +1456,7 @@ void *make_token_plan(const DecodePlan &P, const DecodeWs &W, const int *d_npast
         fl_token_step s;
         memset(&s, 0, sizeof(s));
         s.kind = 0; s.mv = P.head; s.mv.xadd = nullptr; s.mv.sum_out = nullptr;
-        s.mv.x = vec(rank, VX); s.mv.x_ll = 1; s.mv.x_seq = 4 * P.n_layer - 1;
+        s.mv.x = vec(rank, VX, 0); s.mv.x_ll = ll; s.mv.x_seq = 4 * P.n_layer - 1;
         steps.push_back(s);
     }
     void *plan = nullptr;

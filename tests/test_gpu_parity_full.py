@@ -3,17 +3,12 @@ LLaMA-13B q4_1 file -- through the reference-facing API (Model.ingest / Model.ge
 reference itself (oracle/_ref/pyfastllama_ref.so, CPU, in a child process): same prompt, greedy.
 
 What is asserted (north_star: "logits match the reference CPU path on the same prompt within a stated fp tolerance, greedy token-id
-sequence bit-exact"):
-  * per-step logits (32000 floats) agree within LOGIT_TOL * max|logit| on every step both arms evaluated on the same tokens
-    (measured: 7.5e-2 on the 32-layer 7B file, growing smoothly with depth -- 7.8e-3 / 1.3e-2 / 2.1e-2 / 3.2e-2 / 5.3e-2 at 1 / 2 / 4 / 8 / 16
-    layers, tools/probe_depth.py -- because every activation vector is re-quantised to q8_0 before every matmul: a relative perturbation d
-    turns into sqrt(d * step), step = amax / 127, so a one-ulp difference anywhere saturates at the per-cent level; the CPU stand-in whose
-    matmuls are bit-identical to the reference's shows the same level after one 7B-width layer);
-  * the greedy token sequences are identical -- or, if they part ways at step k, the reference's own decision at step k was
-    numerically undecided: its top-1 / top-2 gap is below twice the logit difference observed there (a tie the fp32 reordering
-    budget of the dot products cannot be expected to break the same way).  The bench line reports which of the two happened.
-The dot products differ from the reference only in fp32 summation order (2e-6 * sum|d q| per dot, tests/test_gpu_rowfns.py); through
-32 layers a last-ulp difference occasionally flips a q8_0 rounding or an fp16 table lookup, which is what LOGIT_TOL covers."""
+sequence bit-exact"): the greedy token sequences are IDENTICAL and the logits of every step (32000 floats) carry the reference's BITS.
+Tolerance zero: every fp32 operation of the path follows the reference's order (fastllama_b200/csrc/fl_exact.cuh) -- anything less
+exact ends up at the per-cent level after a few layers, because every activation vector is re-quantised to q8_0 before every matmul
+(the round-1/early round-2 kernels, which only reordered the fp32 sums, measured 7.5e-2 of max|logit| at 32 layers
+and lost the token sequence at step 10).  A third case ingests a LONG prompt (>= 16 tokens: the tcgen05 GEMM, whose block terms are added
+in another order) and asserts the stated budget for that path, and bit equality again with FASTLLAMA_B200_INGEST=exact."""
 import os
 import sys
 
@@ -25,16 +20,20 @@ sys.path.insert(0, ROOT)
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = 0.15          # of max|reference logit| per step: twice the level measured at 32 layers (see above and DESIGN.md section 5)
 N_TOKENS = 24
 
 
-def _ours(path, n):
+LONG_PROMPT = ("The quick brown fox jumps over the lazy dog, then turns around and does it again while the farmer counts his sheep "
+               "and the sun goes down behind the hills.")      # well over 16 tokens: a multi-token eval on the tensor-core path
+LONG_TOL = 0.15           # of max|reference logit|: what a re-ordered fp32 sum in the prompt's matmuls costs after a few layers (see above)
+
+
+def _ours(path, n, prompt=None, n_batch=1):
     import bench
 
     be = bench.Backend(0)
-    m = be.model(path, n_batch=1)
-    assert m.ingest(bench.PROMPT)
+    m = be.model(path, n_batch=n_batch)
+    assert m.ingest(prompt or bench.PROMPT)
     toks, logits = [], []
     for _ in range(n):
         got = []
@@ -48,14 +47,14 @@ def _ours(path, n):
     return toks, np.stack(logits), mode
 
 
-def _reference(path, n, tmp_path):
+def _reference(path, n, tmp_path, prompt=None, n_batch=1):
     import bench
     from oracle.pyoracle import REF_PYFASTLLAMA_SO
 
     if not os.path.exists(REF_PYFASTLLAMA_SO):
         pytest.skip("oracle/_ref not built")
     lp = str(tmp_path / "ref_logits.npy")
-    r = bench.run_ref_worker({"path": path, "threads": min(32, os.cpu_count() or 1), "prompt": bench.PROMPT, "n_parity": n, "logits_out": lp})
+    r = bench.run_ref_worker({"path": path, "threads": min(32, os.cpu_count() or 1), "prompt": prompt or bench.PROMPT, "n_parity": n, "logits_out": lp, "n_batch": n_batch})
     return r["parity_tokens"], np.load(lp)
 
 
@@ -65,13 +64,8 @@ def _check(ref_tokens, ref_logits, our_tokens, our_logits):
     par = bench.compare_parity(ref_tokens, ref_logits, our_tokens, our_logits)
     print("parity:", par)
     assert par["tokens_compared"] >= N_TOKENS // 2
-    assert par["logits_maxabs_over_range"] <= LOGIT_TOL, par
-    if not par["greedy_ids_equal"]:
-        k = par["first_divergence"]
-        srt = np.sort(ref_logits[k])
-        gap = float(srt[-1] - srt[-2])
-        diff = float(np.abs(our_logits[k] - ref_logits[k]).max())
-        assert gap <= 2.0 * diff, f"greedy tokens diverge at step {k} although the reference's top-2 gap {gap:.3e} exceeds twice the logit difference {diff:.3e}"
+    assert par["greedy_ids_equal"], par
+    assert par["logits_bit_identical"] and par["logits_maxabs_over_range"] == 0.0, par
     return par
 
 
@@ -97,4 +91,17 @@ def test_13b_q4_1_four_layers_against_the_reference(tmp_path):
     our_tokens, our_logits, mode = _ours(path, N_TOKENS)
     assert mode == 2
     _check(ref_tokens, ref_logits, our_tokens, our_logits)
+    # a long prompt, ingested 128 tokens at a time
+    # (the reference's own bits depend on n_batch: the value mix of a multi-token eval is a dot product over ALL its positions, masked ones included)
+    ref_tokens, ref_logits = _reference(path, N_TOKENS, tmp_path, LONG_PROMPT, n_batch=128)
+    os.environ["FASTLLAMA_B200_INGEST"] = "exact"               # the reference-order kernel for every eval: the reference's bits again
+    try:
+        our_tokens, our_logits, _ = _ours(path, N_TOKENS, LONG_PROMPT, n_batch=128)
+    finally:
+        del os.environ["FASTLLAMA_B200_INGEST"]
+    _check(ref_tokens, ref_logits, our_tokens, our_logits)
+    our_tokens, our_logits, _ = _ours(path, N_TOKENS, LONG_PROMPT, n_batch=128)     # default: tcgen05 GEMM for the prompt, reordering budget
+    par = bench.compare_parity(ref_tokens, ref_logits, our_tokens, our_logits)
+    print("parity (tcgen05 prompt ingest):", par)
+    assert par["logits_maxabs_over_range"] <= LONG_TOL, par
     os.remove(path)

@@ -1,4 +1,5 @@
-"""GPU (needs >= 2 B200 on the box; skipped otherwise): tensor-parallel decode over NCCL against the single-GPU run.
+"""GPU (needs >= 2 B200 on the box; skipped otherwise): tensor-parallel decode (row-split matrices, activation vectors gathered over
+NVLink as dataflow vectors inside the token kernel) against the single-GPU run: the same tokens and the same logit BITS.
 Launched like bench.py is: one process per GPU, rendezvous on 127.0.0.1."""
 import os
 import subprocess
@@ -84,5 +85,4 @@ def test_tp2_matches_single_gpu(tmp_path, scenario):
     tp = launch(2, "w2")
     for r in tp:
         assert list(r["toks"]) == list(single["toks"])
-        assert np.abs(r["logits"] - single["logits"]).max() <= 2e-2 * np.abs(single["logits"]).max()
-    assert np.array_equal(tp[0]["logits"], tp[1]["logits"])
+        assert np.array_equal(r["logits"].view(np.uint32), single["logits"].view(np.uint32))

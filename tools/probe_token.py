@@ -18,7 +18,10 @@ from fastllama_b200.cuda_abi import EPI_QKV, EPI_RESADD, EPI_STORE, PRO_RMSNORM,
 
 n_layer = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 n_past = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-n_embd, n_head, n_ff, n_vocab, n_ctx = 4096, 32, 11008, 32000, 512
+# FASTLLAMA_B200_PROBE_SHAPE=13B: LLaMA-13B dimensions; FASTLLAMA_B200_PROBE_TYPE=3: q4_1 blocks
+n_embd, n_head, n_ff, n_vocab, n_ctx = (5120, 40, 13824, 32000, 512) if os.environ.get("FASTLLAMA_B200_PROBE_SHAPE") == "13B" else (4096, 32, 11008, 32000, 512)
+WT = int(os.environ.get("FASTLLAMA_B200_PROBE_TYPE", "2"))
+BB = 20 if WT == 2 else 24
 hd = n_embd // n_head
 fl = FlCuda()
 rng = np.random.default_rng(0)
@@ -26,9 +29,11 @@ rng = np.random.default_rng(0)
 
 def wq(m, k):
     nb = k // 32
-    w = np.empty((m, nb, 20), dtype=np.uint8)
+    w = np.empty((m, nb, BB), dtype=np.uint8)
     w[..., :4] = (0.002 * rng.random((m, nb, 1), dtype=np.float32) + 0.0005).view(np.uint8).reshape(m, nb, 4)
-    w[..., 4:] = rng.integers(0, 256, size=(m, nb, 16), dtype=np.uint8)
+    if WT == 3:
+        w[..., 4:8] = (0.01 * rng.random((m, nb, 1), dtype=np.float32) - 0.005).view(np.uint8).reshape(m, nb, 4)
+    w[..., BB - 16:] = rng.integers(0, 256, size=(m, nb, 16), dtype=np.uint8)
     return fl.to_device(w.reshape(-1))
 
 
@@ -52,7 +57,7 @@ for il in range(n_layer):
     kc = fl.to_device((rng.standard_normal((n_ctx, n_embd)) * 0.1).astype(np.float32))
     vc = fl.to_device((rng.standard_normal((n_embd, n_ctx)) * 0.1).astype(np.float32))
     a = FlMvArgs()
-    a.type, a.K, a.nseg, a.pro, a.epi = 2, n_embd, 3, PRO_RMSNORM, EPI_QKV
+    a.type, a.K, a.nseg, a.pro, a.epi = WT, n_embd, 3, PRO_RMSNORM, EPI_QKV
     for i in range(3):
         a.seg_w[i], a.seg_rows[i] = wq(n_embd, n_embd), n_embd
     a.seg_dst[0] = q
@@ -60,21 +65,21 @@ for il in range(n_layer):
     steps.append(("mv", a)); names.append("qkv")
     steps.append(("attn", (q, kc, vc, att))); names.append("attn")
     a = FlMvArgs()
-    a.type, a.K, a.nseg, a.pro, a.epi = 2, n_embd, 1, 0, EPI_RESADD
+    a.type, a.K, a.nseg, a.pro, a.epi = WT, n_embd, 1, 0, EPI_RESADD
     a.seg_w[0], a.seg_rows[0], a.seg_dst[0], a.x, a.res = wq(n_embd, n_embd), n_embd, xb, att, xa
     steps.append(("mv", a)); names.append("wo")
     a = FlMvArgs()
-    a.type, a.K, a.nseg, a.pro, a.epi = 2, n_embd, 2, PRO_RMSNORM, EPI_STORE
+    a.type, a.K, a.nseg, a.pro, a.epi = WT, n_embd, 2, PRO_RMSNORM, EPI_STORE
     a.seg_w[0], a.seg_rows[0], a.seg_dst[0] = wq(n_ff, n_embd), n_ff, m1
     a.seg_w[1], a.seg_rows[1], a.seg_dst[1] = wq(n_ff, n_embd), n_ff, m3
     a.x, a.gamma = xb, dg
     steps.append(("mv", a)); names.append("w13")
     a = FlMvArgs()
-    a.type, a.K, a.nseg, a.pro, a.epi = 2, n_ff, 1, PRO_SILUMUL, EPI_RESADD
+    a.type, a.K, a.nseg, a.pro, a.epi = WT, n_ff, 1, PRO_SILUMUL, EPI_RESADD
     a.seg_w[0], a.seg_rows[0], a.seg_dst[0], a.x, a.b, a.res = wq(n_embd, n_ff), n_embd, xa, m1, m3, xb
     steps.append(("mv", a)); names.append("w2")
 a = FlMvArgs()
-a.type, a.K, a.nseg, a.pro, a.epi = 2, n_embd, 1, PRO_RMSNORM, EPI_STORE
+a.type, a.K, a.nseg, a.pro, a.epi = WT, n_embd, 1, PRO_RMSNORM, EPI_STORE
 a.seg_w[0], a.seg_rows[0], a.seg_dst[0], a.x, a.gamma, a.normed_out = wq(n_vocab, n_embd), n_vocab, logits, xa, dg, emb
 steps.append(("mv", a)); names.append("head")
 
@@ -94,6 +99,9 @@ for _ in range(3):
     fl.check(fl.lib.fl_h2d(xa, x0.ctypes.data, n_embd * 4))
     fl.check(fl.lib.fl_token_plan_launch(plan))
 fl.check(fl.lib.fl_sync())
+if fl.lib.fl_token_plan_error(plan):
+    print("TOKEN KERNEL ERROR:", fl.lib.fl_last_error().decode())
+    sys.exit(3)
 iters = 10
 fl.check(fl.lib.fl_event_record(ev0))
 for _ in range(iters):
@@ -102,7 +110,7 @@ fl.check(fl.lib.fl_event_record(ev1))
 fl.check(fl.lib.fl_event_sync(ev1))
 ms = C.c_float()
 fl.check(fl.lib.fl_event_elapsed_ms(ev0, ev1, C.byref(ms)))
-wbytes = n_layer * (4 * n_embd * n_embd + 3 * n_ff * n_embd) // 32 * 20 + n_vocab * n_embd // 32 * 20
+wbytes = n_layer * (4 * n_embd * n_embd + 3 * n_ff * n_embd) // 32 * BB + n_vocab * n_embd // 32 * BB
 print(f"{n_layer} layers + head: {ms.value / iters * 1e3:.1f} us per launch, {wbytes / (ms.value / iters * 1e-3) / 1e9:.0f} GB/s of weights")
 
 n_cta = C.c_int()
