@@ -17,12 +17,9 @@
 // rows), four lanes per row, lane jj carrying the reference's accumulators 2jj and 2jj+1 through ALL blocks of the row in order;
 // attention scores and the value mix follow ggml_vec_dot_f32's 32-lane order.  The logits of a token are therefore the bits the
 // reference's x86 build produces (the one known exception: rms_norm's double sum, see fl_ops_kernels.cu).
-// A task's rows are streamed in K-chunks of prm.chb (<= 32) blocks: tile = (task, chunk) = 8 row pieces of <= 640 (q4_0) / 768 (q4_1)
-// bytes, each copied by its own bulk copy to a row pitch that is an odd multiple of 16 bytes, which makes the 32 lanes' weight words
-// fall into 32 different banks.  Every consumer warp owns Sw ring slots (its own full / empty mbarriers): a warp then never waits on a
-// barrier whose previous phase it has not consumed itself -- with slots shared between the warps of a group a fast warp could ask for
-// phase q of a slot whose phase q-1 tile (another warp's) had not landed yet, and mbarrier parity waits answer "done" for that
-// (found on the B200 with shallow rings: garbage tiles, then launch failures).
+// A task's rows are streamed in K-chunks of TK_CHB blocks: tile = (task, chunk) = 8 row pieces of <= 1280 (q4_0) / 1536 (q4_1)
+// bytes, each copied by its own bulk copy to a row pitch of chunk + 16 bytes, which makes the 32 lanes' weight words fall into
+// 32 different banks.  The four consumer warps of a tile group take the tiles of their group's stream in turn.
 // Activations move between phases through L2: they are read with ld.global.cg (L1 is not coherent
 // across SMs inside a kernel) and published by a gpu-scope release before the barrier arrive.
 #include <cuda_fp16.h>
@@ -42,8 +39,7 @@
 #define TK_TG 4                  // tile groups; ring slot s always belongs to group s % 4 (S is a multiple of 4)
 #define TK_WPG 4                 // consumer warps per tile group
 #define TK_GMAX 4                // units (row pairs) per task
-#define TK_CHB_MAX 32            // blocks per K-chunk of a task at most (one tile = 8 row pieces of one chunk); prm.chb is chosen per plan
-#define TK_PD 4                  // software-pipeline depth of the consumers' block loop
+#define TK_CHB 64                // blocks per K-chunk of a task (one tile = 8 row pieces of one chunk)
 #define TK_PW 4                  // producer warps: warp TK_CW + g streams the tiles of tile group g (its own slots, its own pace)
 #define TK_THREADS (TK_NT + 32 * TK_PW)
 #define TK_REGS_CONSUMER 104      // setmaxnreg: the producer warpgroup hands registers to the four consumer warpgroups.  The pool is the CTA's
@@ -82,8 +78,8 @@ struct tk_params {
     const uint16_t *exp_tab;
     unsigned long long *prof;      // optional: [n_phases][gridDim.x][4] globaltimer stamps of thread 0
     unsigned *prof2;               // optional (PROF kernel only): [n_phases][gridDim.x][TK_CW][8] cycle counts of every consumer warp's tile loop
-    int S, Sw, lgSw, chb;            // ring slots in total (16 * Sw), per consumer warp (1, 2 or 4), log2(Sw); blocks per K-chunk
-    uint32_t grid_magic, grid_shift; // n / d == umulhi(n, magic) >> shift (magic 0: d is a power of two, n >> shift); exact for n < 2^31
+    int S, Sg;                       // ring slots in total and per tile group (S = 4 * Sg)
+    uint32_t grid_magic, grid_shift, s_magic, s_shift;  // n / d == umulhi(n, magic) >> shift (magic 0: d is a power of two, n >> shift); exact for n < 2^31; s_*: d = Sg
     uint32_t slot_bytes;
     int l2_prefetch;
     int diag;                        // FASTLLAMA_B200_TK_DIAG (timing experiments only; results are garbage): 1 = no weight copies, 2 = no dot products, 4 = no grid barriers, 8 = no prologue
@@ -127,6 +123,20 @@ __device__ __forceinline__ void tk_mbar_wait(uint32_t bar, uint32_t parity, unsi
             if (t0 == 0) t0 = t;
             else if (t - t0 > 2000000000ull) {
                 if (atomicExch(err, 1u) == 0u) { err[1] = who; err[2] = slot; err[3] = parity; err[4] = blockIdx.x; }
+                return;
+            }
+        }
+    }
+}
+__device__ __forceinline__ void tk_tag_wait(volatile uint32_t *tag, uint32_t want, unsigned *err, unsigned who, unsigned slot) {
+    unsigned long long t0 = 0;
+    for (unsigned n = 1; *tag != want; n++) {
+        if ((n & 4095u) == 0) {
+            if (*(volatile unsigned *)err) return;
+            const unsigned long long t = tk_now();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) {
+                if (atomicExch(err, 1u) == 0u) { err[1] = who; err[2] = slot; err[3] = want; err[4] = blockIdx.x; }
                 return;
             }
         }
@@ -462,12 +472,12 @@ __device__ __forceinline__ void tk_epilogue(const tk_phase &ph, int seg, int u, 
     *(float2 *)(A.seg_dst[seg] + r2) = make_float2(a, b);
 }
 
-// ---- the tile streams -------------------------------------------------------------------------------
+// ---- the tile stream of a tile group --------------------------------------------------------------
 // Tasks (4 units = 8 rows; tk_tile_of) of a phase are dealt to the tile groups round robin, continuing where the previous phase
-// stopped (T0), and inside a group to its four consumer warps: the group's k-th task goes to warp k / ... % 4 of the group.  A warp
-// consumes the chunks of its tasks in order through its OWN slots: its n-th tile of the launch lives in slot warp * Sw + n % Sw with
-// parity (n / Sw) & 1.  Producer g feeds the four warps of group g round by round (a round = up to four tasks, one per warp),
-// chunk by chunk, warp by warp, so the warps advance through K together; it keeps the four warps' tile counts.
+// stopped (T0), and inside a group to its four consumer warps: the group's k-th task goes to warp k % 4.  The group's tiles are
+// streamed round by round (a round = up to four tasks, one per warp), chunk by chunk, warp by warp, so the four warps advance
+// through K together.  Producer and consumers enumerate the same sequence from the same closed forms; position idx of the group's
+// stream (counted over the whole launch) lives in slot 4 * (idx % Sg) + g with parity (idx / Sg) & 1.
 struct tk_stream {
     int first, n_g;              // first task of this group in the phase, number of its tasks
 };
@@ -477,9 +487,10 @@ __device__ __forceinline__ tk_stream tk_stream_of(int g, int T0, int ntasks) {
     st.n_g = st.first < ntasks ? (ntasks - st.first + 3) >> 2 : 0;
     return st;
 }
-__device__ __forceinline__ void tk_slot_of(const tk_params &prm, int warp, uint32_t n, int &s, uint32_t &par) {
-    s = warp * prm.Sw + (int)(n & (uint32_t)(prm.Sw - 1));
-    par = (n >> prm.lgSw) & 1u;
+__device__ __forceinline__ void tk_slot_of(const tk_params &prm, int g, uint32_t idx, int &s, uint32_t &par) {
+    const uint32_t q = tk_div(idx, prm.s_magic, prm.s_shift);          // idx / Sg
+    s = (int)(idx - q * (uint32_t)prm.Sg) * TK_TG + g;
+    par = q & 1u;
 }
 
 // ---- main loop of a matvec phase for one consumer warp ------------------------------------------------
@@ -488,30 +499,9 @@ __device__ __forceinline__ unsigned tk_clock() {
     asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
     return c;
 }
-// one block's operands of one lane (weights word, block scale(s), prepared activations)
-struct tk_blk {
-    uint32_t w;
-    float dx, m;
-    uint4 y;
-    float2 ds;
-};
-template <int TYPE>
-__device__ __forceinline__ void tk_fetch(tk_blk &r, const uint8_t *wp, const tk_yblock *yp, int i, int jj) {
-    constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24, QOFF = (TYPE == FL_TYPE_Q4_0) ? 4 : 8;
-    r.w = *(const uint32_t *)(wp + i * BB);
-    r.dx = *(const float *)(wp + i * BB - (QOFF + 4 * jj));
-    r.m = (TYPE == FL_TYPE_Q4_1) ? *(const float *)(wp + i * BB - (QOFF + 4 * jj) + 4) : 0.0f;
-    r.y = *(const uint4 *)yp[i].q[jj];
-    r.ds = *(const float2 *)&yp[i].d;
-}
-template <int TYPE>
-__device__ __forceinline__ void tk_fma(const tk_blk &r, float &a0, float &a1, float &sm) {
-    if (TYPE == FL_TYPE_Q4_1) sm = __fmaf_rn(r.m, r.ds.y, sm);
-    fx_block(r.w, __fmul_rn(r.dx, r.ds.x), r.y, a0, a1);
-}
 template <int TYPE, bool PROF>
-__device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, uint32_t &cnt, const tk_yblock *ysm,
-                                           uint8_t *stage0, uint32_t bar0, int warp, int lane, unsigned *pw, unsigned lle) {
+__device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &prm, const tk_slice &sl, int T0, uint32_t &cg, const tk_yblock *ysm,
+                                           uint8_t *stage0, volatile uint32_t *tags, uint32_t bar0, int warp, int lane, unsigned *pw, unsigned lle) {
     unsigned c_begin = 0, c_wait = 0, c_dot = 0, c_tail = 0, c_rounds = 0, c_t = 0;
     if (PROF) { c_begin = tk_clock(); c_t = c_begin; }
     constexpr int BB = (TYPE == FL_TYPE_Q4_0) ? 20 : 24, QOFF = (TYPE == FL_TYPE_Q4_0) ? 4 : 8;
@@ -523,7 +513,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
     const int g = warp % TK_TG, wl = warp / TK_TG;
     const int r = lane >> 2, jj = lane & 3;
     const bool swiglu = ph.swiglu != 0;
-    const int C = ph.nchunks, nb = ph.nb, chb = prm.chb;
+    const int C = ph.nchunks, nb = ph.nb;
     const tk_stream st = tk_stream_of(g, T0, sl.ntiles);
     const int n_past = (A.epi == FL_EPI_QKV) ? *A.n_past : 0;
     // the lane that runs the epilogue of pair p: default rows (2p, 2p+1) -> lane 8p; swiglu rows (p, p + 4) -> lane 4p
@@ -531,6 +521,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
     const int pr = swiglu ? (lane >> 2) : (lane >> 3);
     const uint32_t row_off = (uint32_t)r * ph.srow + (uint32_t)(QOFF + 4 * jj);
     for (int k = wl; k < st.n_g; k += TK_WPG) {
+        const int k0 = k - wl, n_r = min(TK_WPG, st.n_g - k0);
         int seg, unit0, nunits;
         tk_tile_of(sl, TK_GMAX, st.first + 4 * k, seg, unit0, nunits);
         float2 pre = make_float2(0.f, 0.f);
@@ -539,34 +530,27 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
         for (int c = 0; c < C; c++) {
             int s;
             uint32_t par;
-            tk_slot_of(prm, warp, cnt++, s, par);
+            const uint32_t idx = cg + (uint32_t)(k0 * C + c * n_r + wl);
+            tk_slot_of(prm, g, idx, s, par);
+            // A parity wait is only meaningful once the slot's PREVIOUS tile has completed its phase: the slots of a group are shared by
+            // its four warps, so the previous tenant may be another warp's tile that has not even been issued yet -- and a parity wait
+            // answers "done" for a phase two ahead (seen on the B200 with shallow rings: garbage tiles, launch failures).  The producer
+            // tags the slot with the stream position once it owns it again (the previous tenant was consumed), then the wait is exact.
+            tk_tag_wait(tags + s, idx + 1u, prm.err, 0x600u + (unsigned)warp, (unsigned)s);
             tk_mbar_wait(bar0 + 8u * s, par, prm.err, 0x400u + (unsigned)warp, (unsigned)s);
             if (PROF) { const unsigned t = tk_clock(); c_wait += t - c_t; c_t = t; c_rounds++; }
             if (!(prm.diag & 2)) {
                 const uint8_t *wp = stage0 + (size_t)s * prm.slot_bytes + row_off;
-                const tk_yblock *yp = ysm + c * chb;
-                const int nbc = min(chb, nb - c * chb);
-                // Software pipeline, depth TK_PD: block i is computed from registers fetched TK_PD blocks earlier (the fetch of block i + 4 follows
-                // the compute of block i in the SAME register set, so it cannot be scheduled any later than one iteration before its use).
-                // Left to itself ptxas issues every LDS ~10 instructions before its use, which a lone warp on a scheduler (wo, w2: four
-                // tasks per CTA) pays in full: 32-36 cycles per block instead of the 16 it takes to issue one.
-                int i = 0;
-                if (nbc >= 2 * TK_PD) {
-                    tk_blk r[TK_PD];
-#pragma unroll
-                    for (int k = 0; k < TK_PD; k++) tk_fetch<TYPE>(r[k], wp, yp, k, jj);
-                    for (; i + 2 * TK_PD <= nbc; i += TK_PD) {
-#pragma unroll
-                        for (int k = 0; k < TK_PD; k++) { tk_fma<TYPE>(r[k], a0, a1, sm); tk_fetch<TYPE>(r[k], wp, yp, i + TK_PD + k, jj); }
-                    }
-#pragma unroll
-                    for (int k = 0; k < TK_PD; k++) tk_fma<TYPE>(r[k], a0, a1, sm);
-                    i += TK_PD;
-                }
-                for (; i < nbc; i++) {
-                    tk_blk t;
-                    tk_fetch<TYPE>(t, wp, yp, i, jj);
-                    tk_fma<TYPE>(t, a0, a1, sm);
+                const tk_yblock *yp = ysm + c * TK_CHB;
+                const int nbc = min(TK_CHB, nb - c * TK_CHB);
+#pragma unroll 8
+                for (int i = 0; i < nbc; i++) {
+                    const uint32_t w = *(const uint32_t *)(wp + i * BB);
+                    const float dx = *(const float *)(wp + i * BB - (QOFF + 4 * jj));
+                    const uint4 y = *(const uint4 *)yp[i].q[jj];
+                    const float2 ds = *(const float2 *)&yp[i].d;
+                    if (TYPE == FL_TYPE_Q4_1) sm = __fmaf_rn(*(const float *)(wp + i * BB - (QOFF + 4 * jj) + 4), ds.y, sm);
+                    fx_block(w, __fmul_rn(dx, ds.x), y, a0, a1);
                 }
             }
             // the tile has been read (the chains above consumed every shared load of the warp): hand the slot back
@@ -580,6 +564,7 @@ __device__ __forceinline__ void tk_consume(const tk_phase &ph, const tk_params &
         if (leader && pr < nunits) tk_epilogue(ph, seg, unit0 + pr, tot, other, n_past, pre, lle);
         if (PROF) { const unsigned t = tk_clock(); c_tail += t - c_t; c_t = t; }
     }
+    cg += (uint32_t)(st.n_g * C);
     if (PROF && lane == 0 && pw) {
         pw[0] = 0; pw[1] = c_wait; pw[2] = c_dot; pw[3] = c_tail; pw[4] = c_rounds; pw[5] = tk_clock() - c_begin; pw[6] = (unsigned)sl.ntiles; pw[7] = 0;
     }
@@ -694,6 +679,7 @@ template <bool PROF>
 __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = (uint64_t *)smem;
+    volatile uint32_t *tags = (volatile uint32_t *)(smem + (size_t)16 * prm.S);     // behind the 2 * S mbarriers: which tile of its group's stream a slot holds
     tk_yblock *ysm = (tk_yblock *)(smem + prm.off_y);
     double *red = (double *)(smem + prm.off_red);            // 32 doubles
     float *sc = (float *)(smem + prm.off_sc);                // attention: [n_ctx] + [256]
@@ -717,6 +703,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
             for (int s = 0; s < S; s++) {
                 fl_mbar_init(bar0 + 8u * s, 1);                  // full: the producer's expect_tx arrival + the copies' bytes
                 fl_mbar_init(bar0 + 8u * (S + s), 1);            // empty: the one consumer warp that owns the tile
+                tags[s] = 0u;
             }
             fl_mbar_fence_init();
         }
@@ -726,8 +713,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
             // All 32 lanes walk the stream; lane 0 waits for the slot and posts the byte count, lanes 0-7 issue one row piece each.
             const uint64_t pol = fl_policy_evict_first();
             int T0 = 0;                                                          // tasks of all earlier phases (this CTA): rotates the groups
-            uint32_t cntp = 0;                                                   // tiles handed to each of the group's four warps so far, mod 8, one byte per warp
-                                                                                 // (slot and parity only need the count mod 2 * Sw <= 8)
+            uint32_t cg = 0;                                                     // tiles of all earlier phases in this group's stream
             for (int pi = 0; pi < prm.n_phases; pi++) {
                 // The descriptor lives in global memory; everything the tile loop needs is pulled into registers once per phase
                 // (one L2 round trip, hidden because the producer runs ahead).
@@ -745,14 +731,14 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
                 for (int k0 = 0; k0 < st.n_g; k0 += TK_WPG) {
                     const int n_r = min(TK_WPG, st.n_g - k0);
                     for (int c = 0; c < C; c++) {
-                        const uint32_t cbytes = (uint32_t)min(prm.chb, nb - c * prm.chb) * bb;
+                        const uint32_t cbytes = (uint32_t)min(TK_CHB, nb - c * TK_CHB) * bb;
                         for (int wl = 0; wl < n_r; wl++) {
                             int seg, unit0, nunits;
                             tk_tile_of(sl, TK_GMAX, st.first + 4 * (k0 + wl), seg, unit0, nunits);
                             int s;
                             uint32_t par;
-                            tk_slot_of(prm, wl * TK_TG + pg, (cntp >> (8 * wl)) & 7u, s, par);
-                            cntp = (cntp & ~(0xFFu << (8 * wl))) | ((((cntp >> (8 * wl)) + 1u) & 7u) << (8 * wl));
+                            const uint32_t idx = cg + (uint32_t)(k0 * C + c * n_r + wl);
+                            tk_slot_of(prm, pg, idx, s, par);
                             // row piece of this lane: default rows 2*unit0 .. 2*unit0 + 2*nunits - 1 of the segment's matrix;
                             // swiglu: lanes 0-3 rows unit0.. of w1, lanes 4-7 the same rows of w3
                             const uint8_t *src = nullptr;
@@ -762,15 +748,17 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
                             }
                             if (lane == 0) {
                                 tk_mbar_wait(bar0 + 8u * (S + s), par ^ 1u, prm.err, 0x500u + (unsigned)pg, (unsigned)s);
+                                tags[s] = idx + 1u;                  // the slot is ours again: consumers may now wait for this tile's phase
                                 if (prm.diag & 1) fl_mbar_arrive(bar0 + 8u * s);
                                 else fl_mbar_expect_tx(bar0 + 8u * s, 2u * (uint32_t)nunits * cbytes);
                             }
                             __syncwarp();
                             if (src && !(prm.diag & 1))
-                                fl_bulk_g2s_hint(fl_smem_u32(stage0 + (size_t)s * prm.slot_bytes + (size_t)lane * srow), src + (size_t)c * ((size_t)prm.chb * bb), cbytes, bar0 + 8u * s, pol);
+                                fl_bulk_g2s_hint(fl_smem_u32(stage0 + (size_t)s * prm.slot_bytes + (size_t)lane * srow), src + (size_t)c * (TK_CHB * bb), cbytes, bar0 + 8u * s, pol);
                         }
                     }
                 }
+                cg += (uint32_t)(st.n_g * C);
                 T0 += sl.ntiles;
             }
         }
@@ -786,7 +774,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
     tk_bar_consumers(15);
     asm volatile("bar.sync 14, %0;" ::"r"(TK_THREADS) : "memory");     // mbarriers initialised
     int T0 = 0;
-    uint32_t cnt = 0;                                        // tiles this warp has consumed so far (whole launch): selects its slot and parity
+    uint32_t cg = 0;                                         // tiles of all earlier phases in this warp's group's stream
     unsigned epoch = 0;
     // LL vectors: every element carries (number of LL exchanges before this launch) + (index inside the launch) + 1.  The running count
     // lives next to the vectors (fl_token_plan_create_ll), so words left behind by earlier launches or plans never satisfy a later poll.
@@ -831,8 +819,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) k_decode_token(const tk_params 
         if (pr) pr[2] = tk_now();
         const tk_slice &sl = sl_sh;
         unsigned *pw = (PROF && prm.prof2) ? prm.prof2 + (((size_t)pi * gridDim.x + blockIdx.x) * TK_CW + warp) * 8 : nullptr;
-        if (ph.a.type == FL_TYPE_Q4_0) tk_consume<FL_TYPE_Q4_0, PROF>(ph, prm, sl, T0, cnt, ysm, stage0, bar0, warp, lane, pw, lle_out);
-        else                           tk_consume<FL_TYPE_Q4_1, PROF>(ph, prm, sl, T0, cnt, ysm, stage0, bar0, warp, lane, pw, lle_out);
+        if (ph.a.type == FL_TYPE_Q4_0) tk_consume<FL_TYPE_Q4_0, PROF>(ph, prm, sl, T0, cg, ysm, stage0, tags, bar0, warp, lane, pw, lle_out);
+        else                           tk_consume<FL_TYPE_Q4_1, PROF>(ph, prm, sl, T0, cg, ysm, stage0, tags, bar0, warp, lane, pw, lle_out);
         T0 += sl.ntiles;
         if (pr) pr[3] = tk_now();
     }
@@ -867,7 +855,10 @@ static int tk_geometry(tk_phase &ph, size_t &tile_bytes) {
     const int nb = a.K / 32;
     const size_t row_bytes = a.row_stride_bytes ? a.row_stride_bytes : (size_t)nb * bb;
     FL_REQUIRE(bb > 0 && a.K > 0 && a.K % 32 == 0 && row_bytes % 16 == 0, "token kernel: unsupported matrix K=%d", a.K);
-    FL_REQUIRE(((size_t)nb * bb) % 16 == 0, "token kernel: K=%d gives rows that are not multiples of 16 bytes", a.K);
+    // the 32 lanes of a warp (8 rows x 4 lanes) hit 32 different banks when the row pitch is an odd multiple of 16 bytes
+    const uint32_t chunk_bytes = (uint32_t)std::min(nb, TK_CHB) * bb;
+    FL_REQUIRE(chunk_bytes % 16 == 0 && ((size_t)nb * bb) % 16 == 0, "token kernel: K=%d gives row pieces that are not multiples of 16 bytes", a.K);
+    const uint32_t srow = (chunk_bytes / 16) % 2 ? chunk_bytes : chunk_bytes + 16;
     ph.units[0] = ph.units[1] = ph.units[2] = 0;
     if (ph.swiglu) {
         ph.units[0] = a.seg_rows[0];
@@ -884,15 +875,9 @@ static int tk_geometry(tk_phase &ph, size_t &tile_bytes) {
     FL_REQUIRE(a.epi != FL_EPI_RESADD || ((uintptr_t)a.res & 7) == 0, "token kernel: residual is not 8-byte aligned");
     FL_REQUIRE((long)ph.units[0] + ph.units[1] + ph.units[2] < (1 << 23), "token kernel: too many rows");
     ph.kind = TK_PH_MATVEC;
-    ph.nb = nb; ph.row_bytes = (uint32_t)row_bytes;
-    tile_bytes = 0;
+    ph.nb = nb; ph.nchunks = (nb + TK_CHB - 1) / TK_CHB; ph.srow = srow; ph.row_bytes = (uint32_t)row_bytes;
+    tile_bytes = (size_t)2 * TK_GMAX * srow;
     return 0;
-}
-// K-chunk of chb blocks: the pitch of a row piece in a ring slot.  The 32 lanes of a warp (8 rows x 4 lanes) hit 32 different banks
-// when the pitch is an odd multiple of 16 bytes.
-static uint32_t tk_row_pitch(int nb, int chb, int bb) {
-    const uint32_t chunk_bytes = (uint32_t)std::min(nb, chb) * bb;
-    return (chunk_bytes / 16) % 2 ? chunk_bytes : chunk_bytes + 16;
 }
 
 int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_t *silu_tab, const uint16_t *exp_tab, const void *rope_cs, unsigned *epoch_counter, void **out) {
@@ -963,46 +948,24 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     FL_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     fl_token_plan_impl *pl = new fl_token_plan_impl();
     tk_params &p = pl->prm;
-    // Ring geometry: 16 consumer warps x Sw slots of one tile (8 row pieces of chb blocks).  Two slots per warp (a tile lands while the
-    // previous one is consumed) with the largest chunk that fits; a single slot per warp only if even 8-block chunks do not fit.
-    (void)max_tile;
-    auto layout = [&](int S, size_t slot, size_t &off) {
-        p.off_y = ((size_t)(2 * S) * 8 + 127) & ~(size_t)127;
+    const size_t slot = (max_tile + 127) & ~(size_t)127;
+    int S = 64;
+    if (getenv("FASTLLAMA_B200_TK_SLOTS")) S = std::max(8, std::min(64, atoi(getenv("FASTLLAMA_B200_TK_SLOTS")) / 4 * 4));      // testing aid: a shallower ring
+    size_t off = 0;
+    for (;; S -= 4) {
+        if (S < 8) { flk_token_plan_destroy(pl); fl_set_error("token kernel: tiles of %zu bytes do not fit shared memory", slot); return -1; }
+        p.off_y = ((size_t)(2 * S) * 8 + (size_t)S * 4 + 127) & ~(size_t)127;          // 2 * S mbarriers, S slot tags
         p.off_red = (p.off_y + max_y + 127) & ~(size_t)127;
         p.off_sc = (p.off_red + 32 * sizeof(double) + 127) & ~(size_t)127;
         off = (p.off_sc + ((size_t)max_ctx + 32) * sizeof(float) + 127) & ~(size_t)127;
-        return off + (size_t)S * slot <= (size_t)optin - 1024;
-    };
-    auto slot_bytes_for = [&](int chb) {
-        size_t mx = 0;
-        for (int i = 0; i < n_steps; i++)
-            if (phases[i].kind == TK_PH_MATVEC) mx = std::max(mx, (size_t)2 * TK_GMAX * tk_row_pitch(phases[i].nb, chb, fl_block_bytes(phases[i].a.type)));
-        return (mx + 127) & ~(size_t)127;
-    };
-    int Sw = 0, chb = 0;
-    size_t slot = 0, off = 0;
-    const int sw_max = getenv("FASTLLAMA_B200_TK_SLOTS") ? std::max(1, std::min(2, atoi(getenv("FASTLLAMA_B200_TK_SLOTS")) / TK_CW)) : 2;      // testing aid: a shallower ring
-    for (int sw = sw_max; sw >= 1 && !Sw; sw /= 2)
-        for (int c = TK_CHB_MAX; c >= 8 && !Sw; c -= 4) {
-            bool ok = true;                                       // row pieces must be multiples of 16 bytes (q4_0: chb % 4, q4_1: chb % 2)
-            for (int i = 0; i < n_steps; i++)
-                if (phases[i].kind == TK_PH_MATVEC && ((size_t)std::min(phases[i].nb, c) * fl_block_bytes(phases[i].a.type)) % 16 != 0) ok = false;
-            if (!ok) continue;
-            slot = slot_bytes_for(c);
-            if (layout(TK_CW * sw, slot, off)) { Sw = sw; chb = c; }
-        }
-    if (!Sw) { flk_token_plan_destroy(pl); fl_set_error("token kernel: the activations (%zu bytes) and 16 tiles do not fit shared memory", max_y); return -1; }
-    const int S = TK_CW * Sw;
-    layout(S, slot, off);
-    for (int i = 0; i < n_steps; i++)
-        if (phases[i].kind == TK_PH_MATVEC) {
-            phases[i].nchunks = (phases[i].nb + chb - 1) / chb;
-            phases[i].srow = tk_row_pitch(phases[i].nb, chb, fl_block_bytes(phases[i].a.type));
-        }
+        if (off + (size_t)S * slot <= (size_t)optin - 1024) break;
+    }
     p.off_rowbuf = p.off_cnt = 0;
     p.off_stage0 = (uint32_t)off;
-    p.S = S; p.Sw = Sw; p.lgSw = Sw == 4 ? 2 : Sw == 2 ? 1 : 0; p.chb = chb;
+    p.S = S;
+    p.Sg = S / TK_TG;
     tk_magic((uint32_t)sm, p.grid_magic, p.grid_shift);
+    tk_magic((uint32_t)p.Sg, p.s_magic, p.s_shift);
     p.slot_bytes = (uint32_t)slot;
     p.n_phases = n_steps;
     // measured on B200 (round 1): prefetching a whole phase competes with the demand loads of the phase still running
@@ -1095,7 +1058,7 @@ int flk_token_plan_error(void *plan) {
     const volatile unsigned *e = pl->h_err;      // written by the kernel straight into host memory; the caller has synchronised the stream
     if (e[0])
         fl_set_error("token kernel timeout: %s (code 0x%x), waited for / slot %u, last saw / parity %u, CTA %u, rank %d of %d",
-                     (e[1] & 0x700u) == 0x400u ? "consumer warp waiting for a weight tile" : (e[1] & 0x700u) == 0x500u ? "producer waiting for a free ring slot" :
+                     (e[1] & 0x700u) == 0x600u ? "consumer warp waiting for a slot tag" : (e[1] & 0x700u) == 0x400u ? "consumer warp waiting for a weight tile" : (e[1] & 0x700u) == 0x500u ? "producer waiting for a free ring slot" :
                      (e[1] & 0x300u) == 0x300u ? "LL vector element" : "grid barrier counter", e[1], e[2], e[3], e[4], pl->prm.rank, pl->prm.world);
     return (int)e[0];
 }
