@@ -226,6 +226,9 @@ __device__ __forceinline__ void tk_load_ll(const float *base, int u, float v[E],
             v[2 * k + 1] = __uint_as_float(t[k].z);
         }
         if (ok) return;
+        // a failed round backs off: 148 CTAs x 512 threads spinning on the same words would otherwise keep the L2 busy with the polls
+        // themselves -- and with it the stores they are waiting for and the weight stream
+        __nanosleep(n < 4 ? 40u : 200u);
         if ((n & 255u) == 0) {                       // bounded like every other spin of this kernel
             if (*(volatile unsigned *)err) return;
             const unsigned long long now = tk_now();
