@@ -118,41 +118,48 @@ void flk_exact_release() {
 // One warp per (src0 row, CT consecutive src1 rows) of an (i2, i3) slice.
 // ------------------------------------------------------------------------------------------------
 #define MF_CT 8
-__global__ void __launch_bounds__(256) k_mul_mat_f32_ref4(const fl_view a, const fl_view b, const fl_view d) {
+// 3 CTAs per SM (<= 80 registers): the kernel is a stream of L1/L2 hits, occupancy is what hides them.  (The first version let ptxas
+// unroll the k loop into 202 registers = 8 warps per SM: 535 us per attention product of a 128-token eval, half of the eval.)
+__global__ void __launch_bounds__(256, 3) k_mul_mat_f32_ref4(const fl_view a, const fl_view b, const fl_view d) {
     const int lane = threadIdx.x & 31;
     const int K = (int)a.ne[0], np = K & ~31;
     const int64_t M0 = d.ne[0], M1 = d.ne[1];
     const int64_t ct = (M1 + MF_CT - 1) / MF_CT;
     const int64_t total = M0 * ct * d.ne[2] * d.ne[3];
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t xs = a.nb[0], ys = b.nb[0], yr = b.nb[1];
     for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += nwarps) {
         int64_t r = t;
+        // consecutive warps: consecutive src0 rows against the SAME src1 rows (which then come from L1)
         const int64_t i0 = r % M0; r /= M0;
         const int64_t c1 = r % ct; r /= ct;
         const int64_t i2 = r % d.ne[2];
         const int64_t i3 = r / d.ne[2];
         const char *x = (const char *)a.data + i0 * a.nb[1] + i2 * a.nb[2] + i3 * a.nb[3];
-        const char *y[MF_CT];
-#pragma unroll
-        for (int c = 0; c < MF_CT; c++) y[c] = (const char *)b.data + min(c1 * MF_CT + c, M1 - 1) * b.nb[1] + i2 * b.nb[2] + i3 * b.nb[3];
+        const char *y0 = (const char *)b.data + (c1 * MF_CT) * yr + i2 * b.nb[2] + i3 * b.nb[3];
+        const int ncol = (int)min((int64_t)MF_CT, M1 - c1 * MF_CT);
         float acc[MF_CT];
+        int yoff[MF_CT];                               // column offsets fit 32 bits (8 rows of one operand)
 #pragma unroll
-        for (int c = 0; c < MF_CT; c++) acc[c] = 0.0f;
+        for (int c = 0; c < MF_CT; c++) { acc[c] = 0.0f; yoff[c] = (int)((int64_t)min(c, ncol - 1) * yr); }
+#pragma unroll 1
         for (int k = lane; k < np; k += 32) {
-            const float xv = *(const float *)(x + (int64_t)k * a.nb[0]);
+            const float xv = *(const float *)(x + (int64_t)k * xs);
+            const char *yk = y0 + (int64_t)k * ys;
 #pragma unroll
-            for (int c = 0; c < MF_CT; c++) acc[c] = __fmaf_rn(xv, *(const float *)(y[c] + (int64_t)k * b.nb[0]), acc[c]);
+            for (int c = 0; c < MF_CT; c++) acc[c] = __fmaf_rn(xv, *(const float *)(yk + yoff[c]), acc[c]);
         }
+        const int rem = K - np, nma = fx_left_nma(rem);
+        // lane l fetches leftover element np + l; the sum is continued in order through shuffles (fx_left_nma: products-then-adds, then fmas)
+        const float lx = (lane < rem) ? *(const float *)(x + (int64_t)(np + lane) * xs) : 0.0f;
 #pragma unroll
         for (int c = 0; c < MF_CT; c++) {
+            const float ly = (lane < rem) ? *(const float *)(y0 + yoff[c] + (int64_t)(np + lane) * ys) : 0.0f;
             float s = fx_reduce_f32(acc[c]);
-            const int64_t i1 = c1 * MF_CT + c;
-            if (lane == 0 && i1 < M1) {
-                const int nma = np + fx_left_nma(K - np);                  // leftovers: fx_left_nma
-                for (int k = np; k < nma; k++) s = __fadd_rn(s, __fmul_rn(*(const float *)(x + (int64_t)k * a.nb[0]), *(const float *)(y[c] + (int64_t)k * b.nb[0])));
-                for (int k = nma; k < K; k++) s = __fmaf_rn(*(const float *)(x + (int64_t)k * a.nb[0]), *(const float *)(y[c] + (int64_t)k * b.nb[0]), s);
-                *(float *)((char *)d.data + i0 * d.nb[0] + i1 * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]) = s;
-            }
+            const float lp = __fmul_rn(lx, ly);
+            for (int k = 0; k < nma; k++) s = __fadd_rn(s, __shfl_sync(0xffffffffu, lp, k));
+            for (int k = nma; k < rem; k++) s = __fmaf_rn(__shfl_sync(0xffffffffu, lx, k), __shfl_sync(0xffffffffu, ly, k), s);
+            if (lane == 0 && c < ncol) *(float *)((char *)d.data + i0 * d.nb[0] + (c1 * MF_CT + c) * d.nb[1] + i2 * d.nb[2] + i3 * d.nb[3]) = s;
         }
     }
 }
@@ -162,7 +169,7 @@ int flk_mul_mat_f32_ref4(cudaStream_t st, const fl_view &a, const fl_view &b, co
     const int64_t total = d.ne[0] * ((d.ne[1] + MF_CT - 1) / MF_CT) * d.ne[2] * d.ne[3];
     if (total <= 0 || a.ne[0] <= 0) return 0;
     int64_t blocks = (total + 7) / 8;
-    const int64_t cap = (int64_t)flk_sm_count() * 16;
+    const int64_t cap = (int64_t)flk_sm_count() * 3 * 8;          // 3 resident CTAs per SM, a few waves
     if (blocks > cap) blocks = cap;
     k_mul_mat_f32_ref4<<<(int)blocks, 256, 0, st>>>(a, b, d);
     fl_count_launch();
