@@ -246,11 +246,11 @@ int fl_comm_allgather_f32(const float *send_dev, float *recv_dev, size_t n_per_r
 /* Peer-visible scratch for collectives fused into the token kernel: every rank allocates `bytes` (zeroed) of device
  * memory, the CUDA IPC handles travel through the NCCL communicator, and each rank maps the others' buffers over
  * NVLink.  peers_out[r] = pointer, valid on THIS rank, to rank r's buffer (r = own rank: the local allocation).
- * The first 4096 bytes are reserved for the cross-GPU barrier flags.  Collective call; returns nonzero when peer
- * mapping is unavailable (the caller then keeps the NCCL path). */
+ * The caller lays the buffer out (libggml_b200: 4096 bytes of counters, then the dataflow vectors of the decode step).  Collective
+ * call; returns nonzero when peer mapping is unavailable (tensor-parallel decode then refuses to run: its gathers need peer memory). */
 int fl_comm_shared_alloc(size_t bytes, void **peers_out);
 /* copy blocks [blk0, blk0 + nblk) of every row of a quantised matrix into a packed matrix whose row
- * stride is dst_row_stride bytes (the K-split shard of wo / w2) */
+ * stride is dst_row_stride bytes (a column slice; not used by the decode plan any more: every matrix is row-split) */
 int fl_dev_pack_cols(int type, const void *W, size_t w_row_stride_bytes, int M, int blk0, int nblk, void *dst, size_t dst_row_stride);
 
 /* CUDA-graph capture of everything issued on the library stream between begin and end */

@@ -18,8 +18,9 @@ from fastllama_b200.cuda_abi import EPI_QKV, EPI_RESADD, EPI_STORE, PRO_RMSNORM,
 
 n_layer = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 n_past = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-# FASTLLAMA_B200_PROBE_SHAPE=13B: LLaMA-13B dimensions; FASTLLAMA_B200_PROBE_TYPE=3: q4_1 blocks
-n_embd, n_head, n_ff, n_vocab, n_ctx = (5120, 40, 13824, 32000, 512) if os.environ.get("FASTLLAMA_B200_PROBE_SHAPE") == "13B" else (4096, 32, 11008, 32000, 512)
+# FASTLLAMA_B200_PROBE_SHAPE=13B / 30B / 65B: those models' dimensions; FASTLLAMA_B200_PROBE_TYPE=3: q4_1 blocks
+SHAPES = {"7B": (4096, 32, 11008, 32000, 512), "13B": (5120, 40, 13824, 32000, 512), "30B": (6656, 52, 17920, 32000, 512), "65B": (8192, 64, 22016, 32000, 512)}
+n_embd, n_head, n_ff, n_vocab, n_ctx = SHAPES[os.environ.get("FASTLLAMA_B200_PROBE_SHAPE", "7B")]
 WT = int(os.environ.get("FASTLLAMA_B200_PROBE_TYPE", "2"))
 BB = 20 if WT == 2 else 24
 hd = n_embd // n_head
