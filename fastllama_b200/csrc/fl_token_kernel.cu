@@ -950,13 +950,17 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
     FL_CUDA_OK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
     FL_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     fl_token_plan_impl *pl = new fl_token_plan_impl();
+    struct plan_guard {                               // every error return below frees what has been allocated so far
+        fl_token_plan_impl *p;
+        ~plan_guard() { if (p) flk_token_plan_destroy(p); }
+    } guard{pl};
     tk_params &p = pl->prm;
     const size_t slot = (max_tile + 127) & ~(size_t)127;
     int S = 64;
     if (getenv("FASTLLAMA_B200_TK_SLOTS")) S = std::max(8, std::min(64, atoi(getenv("FASTLLAMA_B200_TK_SLOTS")) / 4 * 4));      // testing aid: a shallower ring
     size_t off = 0;
     for (;; S -= 4) {
-        if (S < 8) { flk_token_plan_destroy(pl); fl_set_error("token kernel: tiles of %zu bytes do not fit shared memory", slot); return -1; }
+        if (S < 8) { fl_set_error("token kernel: tiles of %zu bytes do not fit shared memory", slot); return -1; }
         p.off_y = ((size_t)(2 * S) * 8 + (size_t)S * 4 + 127) & ~(size_t)127;          // 2 * S mbarriers, S slot tags
         p.off_red = (p.off_y + max_y + 127) & ~(size_t)127;
         p.off_sc = (p.off_red + 32 * sizeof(double) + 127) & ~(size_t)127;
@@ -992,10 +996,10 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
         if (ph.kind == TK_PH_MATVEC) {
             if (ph.a.out_ll) p.n_ll = std::max(p.n_ll, ph.a.out_seq + 1);
             if (ph.a.x_ll) p.n_ll = std::max(p.n_ll, ph.a.x_seq + 1);
-            if (ph.a.out_ll && ph.a.nseg != 1 && !ph.swiglu) { flk_token_plan_destroy(pl); fl_set_error("token kernel: an LL output needs a single segment (or a w1|w3 pair)"); return -1; }
+            if (ph.a.out_ll && ph.a.nseg != 1 && !ph.swiglu) { fl_set_error("token kernel: an LL output needs a single segment (or a w1|w3 pair)"); return -1; }
         } else if (ph.out_ll) p.n_ll = std::max(p.n_ll, ph.out_seq + 1);
     }
-    if (p.n_ll > 0 && !epoch_counter) { flk_token_plan_destroy(pl); fl_set_error("token kernel: steps use LL vectors but no epoch counter was given (fl_token_plan_create_ll)"); return -1; }
+    if (p.n_ll > 0 && !epoch_counter) { fl_set_error("token kernel: steps use LL vectors but no epoch counter was given (fl_token_plan_create_ll)"); return -1; }
     p.prof = nullptr;
     p.prof2 = nullptr;
     if (getenv("FASTLLAMA_B200_TOKEN_PROF")) {
@@ -1018,8 +1022,9 @@ int flk_token_plan_create(const fl_token_step *steps, int n_steps, const uint16_
                32 * TK_PW, fa.numRegs, TK_THREADS);
     int per_sm = 0;
     FL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_token<false>, TK_THREADS, pl->smem));
-    if (per_sm < 1) { const size_t need = pl->smem; flk_token_plan_destroy(pl); fl_set_error("token kernel: one CTA per SM does not fit (smem %zu)", need); return -1; }
+    if (per_sm < 1) { const size_t need = pl->smem; fl_set_error("token kernel: one CTA per SM does not fit (smem %zu)", need); return -1; }
     pl->n_kernels = sm;
+    guard.p = nullptr;
     *out = pl;
     return 0;
 }

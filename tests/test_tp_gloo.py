@@ -64,8 +64,8 @@ m.close()
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(MOCK, "pyfastllama.so")), reason="tests/mock not built (needs the drop-in library)")
-@pytest.mark.parametrize("n_batch", [1, 8])
-def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch, scenario="decode"):
+@pytest.mark.parametrize("n_batch,world", [(1, 2), (8, 2), (1, 4)])
+def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch, world, scenario="decode"):
     """The mock maps POSIX shared memory between the ranks like fl_comm_shared_alloc maps peer HBM, so the sharded plan runs as the
     token program: every step stores its row slice of a vector into both ranks' copies and the consumers poll the epochs."""
     peer = True
@@ -74,7 +74,8 @@ def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch, scenario=
 
     orc = Oracle()
     path = str(tmp_path / "toy.bin")
-    write_synthetic_numpy(path, Q4_0, n_vocab=512, n_embd=256, n_mult=64, n_head=4, n_layer=3, seed=5, std=0.01,
+    # world 4 needs n_ff % (32 * 4) == 0: n_mult 256 gives n_ff 768
+    write_synthetic_numpy(path, Q4_0, n_vocab=512, n_embd=256, n_mult=64 if world == 2 else 256, n_head=4, n_layer=3, seed=5, std=0.01,
                           quantize=lambda w, t: orc.quantize_q4(w, t))
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
@@ -94,7 +95,7 @@ def test_tensor_parallel_decode_matches_single_rank(tmp_path, n_batch, scenario=
         return [np.load(str(tmp_path / tag) + f".rank{r}.npz") for r in range(world)]
 
     single = launch(1, "w1")[0]
-    tp = launch(2, "w2")
+    tp = launch(world, f"w{world}")
     assert int(single["mode"]) == 2                                   # one rank: the token program
     for r in tp:
         assert int(r["mode"]) == 2                                    # two ranks: the token program as well
@@ -107,4 +108,4 @@ def test_tensor_parallel_kv_gather_before_replicated_eval_and_state(tmp_path):
     """Decode steps shard the KV cache by head; a later multi-token eval and save_state need all heads: the ranks
     all-gather the sharded positions first (ggml_b200.cpp tp_gather_kv).  Same tokens as one rank, and each rank's state
     file resumes identically."""
-    test_tensor_parallel_decode_matches_single_rank(tmp_path, 4, scenario="reingest")
+    test_tensor_parallel_decode_matches_single_rank(tmp_path, 4, 2, scenario="reingest")
