@@ -1512,6 +1512,12 @@ bool run_decode_plan(const ggml_context *ctx, ggml_cgraph *g, DecodeOutputs &O, 
             D.no_token_plan = D.token_plan == nullptr && P.world == 1;      // across GPUs the weights are sharded: the multi-kernel path takes over
         }
         D.plan = P;
+        if (P.world > 1) {
+            // The ranks reach their first step of a new plan at different times (shard uploads, page faults of an mmap'ed model), but the
+            // token kernel's polls for the other ranks' vector elements give up after 2 s: line the ranks up first (one tiny collective).
+            FLC(fl_comm_allreduce_f32(D.ws.m3, 1));
+            FLC(fl_sync());
+        }
         if (!D.no_token_plan) {
             // one eager pass first: sets kernel attributes, and gives this token's result
             FLC(fl_event_record(ev0));
